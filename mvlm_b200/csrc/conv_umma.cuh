@@ -1,0 +1,73 @@
+// Implicit-GEMM convolution on tcgen05/TMEM fed by TMA (sm_100a).
+//
+// Replaces the torch.nn.Conv2d (+ BatchNorm2d + ReLU + residual add + cat)
+// call sites of the reference CNN: paulsenpredictor.py:251-273 (ResidualBlock),
+// :385-402 / :404-432 (MVLMModel top-level convs).
+//
+// Layout contract
+//   activations : NHWC bf16, channel stride `cs` (elements) a multiple of 8;
+//                 a conv reads `cin` channels (multiple of 16) starting at the
+//                 base pointer.
+//   weights     : packed bf16 [cout_pad][KW][KH][cin]  (K-major rows; one row
+//                 per output channel; rows >= cout_real are zero).
+//   GEMM view   : M = output pixels (128-row sub-tiles of 8 image rows x 16
+//                 px), N = output channels (N_TILE per CTA), K = KW*KH*cin.
+#pragma once
+#include "common.cuh"
+
+namespace mvlm {
+
+struct ConvEpilogue {
+  const float* bias = nullptr;  // [cout_pad] fp32, added first
+  // act_pre = relu(v*pre_scale+pre_shift), v = acc+bias (BEFORE the residuals)
+  const float* pre_scale = nullptr;
+  const float* pre_shift = nullptr;
+  __nv_bfloat16* out_pre = nullptr;
+  int pre_cs = 0, pre_co = 0;
+  // v += res1 + res2
+  const __nv_bfloat16* res1 = nullptr;
+  int res1_cs = 0, res1_co = 0;
+  const __nv_bfloat16* res2 = nullptr;
+  int res2_cs = 0, res2_co = 0;
+  // raw output (after residuals)
+  __nv_bfloat16* out_raw = nullptr;
+  int raw_cs = 0, raw_co = 0;
+  // act_post = relu(v*post_scale+post_shift) (AFTER the residuals)
+  const float* post_scale = nullptr;
+  const float* post_shift = nullptr;
+  __nv_bfloat16* out_post = nullptr;
+  int post_cs = 0, post_co = 0;
+  // fp32 NCHW output (N, cout_real, H*up_sy, W*up_sx) at pixel (y*sy+py, x*sx+px)
+  float* out_f32 = nullptr;
+  // fused per-(image, channel) arg-max keys, see peaks.cu (atomicMax on u64)
+  unsigned long long* argmax_keys = nullptr;
+  int cout_real = 0;
+  int up_sy = 1, up_sx = 1, up_py = 0, up_px = 0;
+};
+
+struct ConvShape {
+  const __nv_bfloat16* in = nullptr;  // NHWC
+  int n = 0, h = 0, w = 0;
+  int cin = 0;    // channels read (multiple of 16)
+  int in_cs = 0;  // channel stride of the input buffer
+  const __nv_bfloat16* wpacked = nullptr;
+  int cout_pad = 0;  // rows of wpacked; multiple of n_tile
+  int n_tile = 0;    // 32, 64, 80, 96 or 128
+  int kh = 3, kw = 3;
+  int y_off0 = -1, x_off0 = -1;  // input offset of tap (0,0)
+};
+
+struct alignas(64) ConvParams {
+  CUtensorMap tm_a;
+  CUtensorMap tm_b;
+  ConvShape s;
+  ConvEpilogue e;
+  int tiles_x, tiles_y, n_nt, total_tiles;
+};
+
+// Builds the tensor maps and validates the shape.  Returns MVLM_* code.
+int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out);
+// Launches the persistent kernel for a planned conv.
+int conv_launch(const ConvParams& p, cudaStream_t stream);
+
+}  // namespace mvlm

@@ -1,0 +1,141 @@
+"""Parity of the tcgen05 implicit-GEMM conv (mvlm_conv2d_bf16) against torch fp32 conv2d
+on the same bf16-rounded operands.  Tolerance: fp32 accumulation-order noise only,
+|err| <= 2e-3 * max|ref| + bf16 output rounding (2^-8 relative) where the output is bf16.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x_nhwc, w_oihw, bias, kh, kw, y_off0, x_off0):
+    """fp32 reference of a conv whose tap (ky,kx) reads input (y+y_off0+ky, x+x_off0+kx)."""
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    w = w_oihw.to(torch.bfloat16).float()
+    n, c, h, wd = x.shape
+    # pad so that tap (0,0) offset becomes 0
+    pt, pl = -y_off0, -x_off0
+    pb, pr = kh - 1 + y_off0, kw - 1 + x_off0
+    xp = F.pad(x, (pl, pr, pt, pb))
+    y = F.conv2d(xp, w, bias)
+    return y.permute(0, 2, 3, 1).contiguous()  # NHWC fp32
+
+
+CASES = [
+    # n, h, w, cin, cs_in, cout, n_tile, kh, kw
+    (2, 32, 32, 64, 64, 64, 64, 3, 3),
+    (1, 16, 16, 256, 256, 128, 128, 3, 3),
+    (3, 64, 64, 128, 128, 64, 64, 3, 3),
+    (2, 32, 48, 256, 256, 256, 128, 3, 3),   # two N tiles, non-square
+    (2, 32, 32, 64, 64, 32, 32, 3, 3),
+    (2, 16, 16, 32, 64, 32, 32, 3, 3),       # cin 32 read from a 64-stride buffer
+    (2, 32, 32, 80, 80, 256, 128, 3, 3),     # cin = 64 + 16 (partial last chunk)
+    (2, 32, 32, 256, 256, 73, 80, 3, 3),     # cout 73 padded to 80
+    (1, 32, 32, 96, 96, 84, 96, 3, 3),
+    (2, 32, 32, 64, 64, 128, 128, 1, 1),     # 1x1 resample conv
+    (5, 8, 8, 256, 256, 128, 128, 3, 3),     # map smaller than the 16x16 tile
+    (5, 4, 4, 128, 128, 64, 64, 3, 3),
+    (2, 24, 40, 64, 64, 64, 64, 3, 3),       # ragged: not a multiple of 16
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cs,cout,n_tile,kh,kw", CASES)
+def test_conv_raw(lib, n, h, w, cin, cs, cout, n_tile, kh, kw):
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(1234 + n * 7 + h + cin)
+    x = torch.randn((n, h, w, cs), generator=g, device="cuda").to(torch.bfloat16)
+    wt = (torch.randn((cout, cin, kh, kw), generator=g, device="cuda") / (cin * kh * kw) ** 0.5)
+    bias = torch.randn((cout,), generator=g, device="cuda")
+    cout_pad = ((cout + n_tile - 1) // n_tile) * n_tile
+    wp = ops.pack_conv_weight(wt, cout_pad, cin)
+    bias_p = torch.zeros(cout_pad, device="cuda")
+    bias_p[:cout] = bias
+    out = torch.full((n, h, w, cout_pad), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv2d_bf16(x, wp, cin=cin, n_tile=n_tile, kh=kh, kw=kw, bias=bias_p, out_raw=(out, 0))
+    torch.cuda.synchronize()
+    ref = _ref_conv(x[..., :cin], wt, bias, kh, kw, -(kh // 2), -(kw // 2))
+    got = out[..., :cout].float()
+    assert torch.isfinite(got).all()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * scale + scale * 2.0 ** -8, (err, scale)
+    if cout_pad > cout:
+        assert (out[..., cout:].float() == 0).all()
+
+
+def test_conv_full_epilogue(lib):
+    """bias + act_pre + two residuals + raw + act_post + fp32 NCHW out + fused argmax keys."""
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    n, h, w, cin, cout, n_tile = 2, 32, 32, 128, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((n, h, w, cin), generator=g, device="cuda").to(torch.bfloat16)
+    wt = torch.randn((cout, cin, 3, 3), generator=g, device="cuda") / (cin * 9) ** 0.5
+    bias = torch.randn((cout,), generator=g, device="cuda")
+    s1, t1, s2, t2 = (torch.randn((cout,), generator=g, device="cuda") for _ in range(4))
+    r1 = torch.randn((n, h, w, 256), generator=g, device="cuda").to(torch.bfloat16)
+    r2 = torch.randn((n, h, w, 128), generator=g, device="cuda").to(torch.bfloat16)
+    wp = ops.pack_conv_weight(wt, cout, cin)
+    out_pre = torch.zeros((n, h, w, 128), device="cuda", dtype=torch.bfloat16)
+    out_raw = torch.zeros((n, h, w, 256), device="cuda", dtype=torch.bfloat16)
+    out_post = torch.zeros((n, h, w, 256), device="cuda", dtype=torch.bfloat16)
+    out_f32 = torch.zeros((n, cout, h, w), device="cuda")
+    keys = torch.zeros((n * cout,), device="cuda", dtype=torch.int64)
+    ops.conv2d_bf16(x, wp, n_tile=n_tile, bias=bias, pre=(s1, t1, out_pre, 0), res1=(r1, 128), res2=(r2, 0),
+                    out_raw=(out_raw, 64), post=(s2, t2, out_post, 128), out_f32=out_f32, argmax_keys=keys,
+                    cout_real=cout)
+    torch.cuda.synchronize()
+    v = _ref_conv(x, wt, bias, 3, 3, -1, -1)
+    scale = v.abs().max().item()
+    tol = 2e-3 * scale
+    pre_ref = torch.relu(v * s1 + t1)
+    assert (out_pre.float() - pre_ref).abs().max().item() <= tol * s1.abs().max().item() + pre_ref.abs().max().item() * 2.0 ** -8
+    v2 = v + r1[..., 128:256].float() + r2.float()
+    assert (out_raw[..., 64:192].float() - v2).abs().max().item() <= tol + v2.abs().max().item() * 2.0 ** -8
+    assert (out_raw[..., :64] == 0).all() and (out_raw[..., 192:] == 0).all()
+    post_ref = torch.relu(v2 * s2 + t2)
+    assert (out_post[..., 128:].float() - post_ref).abs().max().item() <= tol * s2.abs().max().item() + post_ref.abs().max().item() * 2.0 ** -8
+    assert (out_f32 - v2.permute(0, 3, 1, 2)).abs().max().item() <= tol
+    # fused argmax == argmax of the fp32 map the same kernel wrote (bit-exact, first index on ties)
+    k = keys.view(n, cout)
+    idx = 0xFFFFFFFF - (k & 0xFFFFFFFF)
+    ref_idx = out_f32.view(n, cout, -1).argmax(dim=-1)
+    assert torch.equal(idx, ref_idx)
+
+
+def test_conv_upsample_phase(lib):
+    """conv3x3(nearest_up2(x)) == four 2x2 phase convs at the low resolution (conv11 path,
+    paulsenpredictor.py:428-429)."""
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    n, h, w, c, cout = 2, 32, 32, 80, 73
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((n, h, w, c), generator=g, device="cuda").to(torch.bfloat16)
+    x[..., 73:] = 0
+    wt = torch.randn((cout, 73, 3, 3), generator=g, device="cuda") / (73 * 9) ** 0.5
+    bias = torch.randn((cout,), generator=g, device="cuda")
+    bias_p = torch.zeros(80, device="cuda")
+    bias_p[:cout] = bias
+    out = torch.zeros((n, cout, 2 * h, 2 * w), device="cuda")
+    for a in range(2):
+        for b in range(2):
+            # rows: a=0 -> offsets {-1: w0, 0: w1+w2}; a=1 -> {0: w0+w1, +1: w2}
+            wr = torch.stack([wt[:, :, 0], wt[:, :, 1] + wt[:, :, 2]], 2) if a == 0 else \
+                torch.stack([wt[:, :, 0] + wt[:, :, 1], wt[:, :, 2]], 2)      # (co,ci,2,3)
+            wc = torch.stack([wr[..., 0], wr[..., 1] + wr[..., 2]], 3) if b == 0 else \
+                torch.stack([wr[..., 0] + wr[..., 1], wr[..., 2]], 3)          # (co,ci,2,2)
+            wp = ops.pack_conv_weight(wc.contiguous(), 80, 80)
+            ops.conv2d_bf16(x, wp, n_tile=80, kh=2, kw=2, y_off0=a - 1, x_off0=b - 1, bias=bias_p,
+                            out_f32=out, cout_real=cout, up=(2, 2, a, b))
+    torch.cuda.synchronize()
+    xu = F.interpolate(x[..., :73].float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(xu, wt.to(torch.bfloat16).float(), bias, padding=1)
+    scale = ref.abs().max().item()
+    # combined phase weights are rounded to bf16 after summation -> bf16-level difference
+    assert (out - ref).abs().max().item() <= 1.5e-2 * scale
