@@ -70,6 +70,83 @@ int mvlm_conv2d_bf16(const mvlm_conv_args* args, void* stream);
 int mvlm_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cout_pad,
                           int cin_pad, void* out_bf16, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Stage 1: batched multi-view orthographic rasteriser.                       */
+/* Replaces ObjVTKRenderer3D.render_3d_multi_rgb_geometry_depth               */
+/*   src/mvlm/utils/render3d.py:114-177 (+ camera :53-59,:136,:150-152, depth  */
+/*   encoder :73-77,:166-170, flip :177, /255 :191) and obj_to_actor's         */
+/*   material src/mvlm/utils/utils3d.py:26-64.                                 */
+/* rot: (V,9) float64 row-major R = Ry(ry)*Rx(rx)*Rz(rz) per view.             */
+/* channel_mode: 0 RGB+depth, 1 geometry+depth, 2 RGB, 3 depth, 4 geometry.    */
+/* zbuf_workspace: V*H*W*8 bytes.  Any of the four outputs may be NULL.        */
+/* ------------------------------------------------------------------------- */
+size_t mvlm_raster_workspace_bytes(int n_views, int h, int w);
+int mvlm_raster_multiview(const float* verts, const float* uvs, const int32_t* tris, int n_tris,
+                          const uint8_t* tex, int tex_h, int tex_w, const double* rot, int n_views,
+                          int h, int w, int channel_mode, void* zbuf_workspace,
+                          uint8_t* out_u8 /* (V,H,W,4) */, float* out_f32 /* (V,H,W,C) */,
+                          int32_t* out_tri_id /* (V,H,W) */, float* out_depth /* (V,H,W) */,
+                          void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Stage 2: stacked-hourglass heat-map CNN (MVLMModel),                       */
+/*   src/mvlm/prediction/paulsenpredictor.py:364-432 driven by                 */
+/*   predict_landmarks_from_images :167-217.                                   */
+/* names/ptrs: the torch state_dict (fp32 device tensors, reference key names).*/
+/* forward: exactly one of img_u8 (V,H,W,4 packed u8 from the rasteriser) or    */
+/* img_f32 (V,H,W,cin fp32 in [0,1], the reference's image_stack layout).       */
+/* out_heatmaps (V,L,H,W) fp32 and out_peaks (L,V,3) fp32 are each optional.    */
+/* ------------------------------------------------------------------------- */
+typedef struct mvlm_hourglass mvlm_hourglass;
+size_t mvlm_hourglass_workspace_bytes(int n_landmarks, int cin, int n_views, int h, int w);
+double mvlm_hourglass_flops_per_view(int n_landmarks, int cin, int h, int w);
+int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, int n_entries,
+                          int n_landmarks, int cin, int n_views, int h, int w, void* workspace,
+                          size_t workspace_bytes, mvlm_hourglass** out);
+int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
+                           float* out_heatmaps, float* out_peaks, void* stream);
+int mvlm_hourglass_num_launches(const mvlm_hourglass* net);
+/* layer-wise parity probes: "r3", "hg1", "sum_temp", "x10" -> NHWC bf16 tensor in the workspace */
+int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c);
+void mvlm_hourglass_destroy(mvlm_hourglass* net);
+
+/* ------------------------------------------------------------------------- */
+/* Stage 3: heat-map peaks.  Replaces find_heat_map_maxima /                   */
+/*   find_maxima_in_batch_of_heatmaps, paulsenpredictor.py:112-165.            */
+/* method 0 = "simple", 1 = "moment".  heatmaps (V,L,H,W) fp32 -> (L,V,3).     */
+/* ------------------------------------------------------------------------- */
+int mvlm_heatmap_peaks(const float* heatmaps, int n_views, int n_landmarks, int h, int w, int method,
+                       float* out_peaks, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Stage 4: peaks -> view rays.  Replaces Estimator3D.estimate_landmark_lines  */
+/*   src/mvlm/utils/estimator3d.py:31-90.  rot as in mvlm_raster_multiview.    */
+/* ------------------------------------------------------------------------- */
+int mvlm_rays_from_peaks(const float* peaks /* (L,V,3) */, const double* rot /* (V,9) */, int n_landmarks,
+                         int n_views, int image_size, double* out_starts, double* out_ends, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Stage 5a: filter + RANSAC + least squares.  Replaces                        */
+/*   estimate_landmarks_from_lines estimator3d.py:158-183 (filters :140-155,   */
+/*   RANSAC :92-137, LSQ utils3d.py:99-124).  mode 0 = quantile, 1 = absolute. */
+/* draws: (L,H,8) uint32 seeded hypothesis table, line index = draw mod n.     */
+/* ------------------------------------------------------------------------- */
+size_t mvlm_consensus_workspace_bytes(int n_landmarks, int n_views, int n_hyp);
+int mvlm_consensus(const float* peaks, const double* starts, const double* ends, int n_landmarks,
+                   int n_views, int mode, double threshold_quantile, float threshold_absolute,
+                   const uint32_t* draws, int n_hyp, double dist_thres, void* workspace,
+                   size_t workspace_bytes, double* out_landmarks /* (L,3) */, double* out_errors /* (L) */,
+                   int32_t* out_nlines /* (L) or NULL */, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Stage 5b: snap to the mesh surface.  Replaces                               */
+/*   Estimator3D.project_landmarks_to_surface estimator3d.py:252-285.          */
+/* ------------------------------------------------------------------------- */
+size_t mvlm_snap_workspace_bytes(int n_landmarks, int n_tris);
+int mvlm_snap_to_mesh(const float* verts, const int32_t* tris, int n_tris, const double* landmarks,
+                      int n_landmarks, void* workspace, size_t workspace_bytes, double* out /* (L,3) */,
+                      int32_t* out_tri /* (L) or NULL */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,8 +52,6 @@ def load() -> C.CDLL:
     lib.mvlm_last_error.restype = C.c_char_p
     lib.mvlm_launch_count.restype = C.c_longlong
     lib.mvlm_launch_count.argtypes = [C.c_int]
-    for name in dir(lib):
-        pass
     _lib = lib
     _declare(lib)
     return lib
@@ -65,6 +63,22 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_version": ([], i32),
         "mvlm_conv2d_bf16": ([C.POINTER(ConvArgs), vp], i32),
         "mvlm_pack_conv_weight": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
+        "mvlm_raster_workspace_bytes": ([i32, i32, i32], C.c_size_t),
+        "mvlm_raster_multiview": ([vp, vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
+        "mvlm_hourglass_workspace_bytes": ([i32, i32, i32, i32, i32], C.c_size_t),
+        "mvlm_hourglass_flops_per_view": ([i32, i32, i32, i32], f64),
+        "mvlm_hourglass_create": ([C.POINTER(C.c_char_p), C.POINTER(vp), i32, i32, i32, i32, i32, i32, vp,
+                                   C.c_size_t, C.POINTER(vp)], i32),
+        "mvlm_hourglass_forward": ([vp, vp, vp, vp, vp, vp], i32),
+        "mvlm_hourglass_num_launches": ([vp], i32),
+        "mvlm_hourglass_probe": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
+        "mvlm_hourglass_destroy": ([vp], None),
+        "mvlm_heatmap_peaks": ([vp, i32, i32, i32, i32, i32, vp, vp], i32),
+        "mvlm_rays_from_peaks": ([vp, vp, i32, i32, i32, vp, vp, vp], i32),
+        "mvlm_consensus_workspace_bytes": ([i32, i32, i32], C.c_size_t),
+        "mvlm_consensus": ([vp, vp, vp, i32, i32, i32, f64, f32, vp, i32, f64, vp, C.c_size_t, vp, vp, vp, vp], i32),
+        "mvlm_snap_workspace_bytes": ([i32, i32], C.c_size_t),
+        "mvlm_snap_to_mesh": ([vp, vp, i32, vp, i32, vp, C.c_size_t, vp, vp, vp], i32),
     }
     sigs.update(_EXTRA_SIGS)
     for name, (argtypes, restype) in sigs.items():

@@ -25,6 +25,11 @@ NVCC_FLAGS = [
 ]
 
 
+# Stages whose arithmetic must round after every operation, like numpy / the C oracle
+# (bit-identical rasteriser decisions, float32 ray chain, numpy-like fp64 consensus).
+NO_FMAD = {"raster.cu", "rays.cu", "consensus.cu"}
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (Path(cand).exists() or cand == "nvcc"):
@@ -56,6 +61,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_time):
             return obj
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if src.name in NO_FMAD:
+            cmd.insert(1, "--fmad=false")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -6,6 +6,8 @@
 #include "../../include/mvlm_b200.h"
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "hourglass.cuh"
+#include "stages.cuh"
 
 namespace mvlm {
 
@@ -90,6 +92,108 @@ int mvlm_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
+}
+
+size_t mvlm_raster_workspace_bytes(int n_views, int h, int w) {
+  return static_cast<size_t>(n_views) * h * w * sizeof(unsigned long long);
+}
+
+int mvlm_raster_multiview(const float* verts, const float* uvs, const int32_t* tris, int n_tris, const uint8_t* tex,
+                          int tex_h, int tex_w, const double* rot, int n_views, int h, int w, int channel_mode,
+                          void* zbuf_workspace, uint8_t* out_u8, float* out_f32, int32_t* out_tri_id,
+                          float* out_depth, void* stream) {
+  RasterArgs a;
+  a.verts = verts; a.uvs = uvs; a.tris = tris; a.nt = n_tris; a.tex = tex; a.th = tex_h; a.tw = tex_w;
+  a.rot = rot; a.n_views = n_views; a.h = h; a.w = w; a.channel_mode = channel_mode;
+  a.zbuf = static_cast<unsigned long long*>(zbuf_workspace);
+  a.out_u8 = out_u8; a.out_f32 = out_f32; a.out_tri = out_tri_id; a.out_z = out_depth;
+  return raster_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+struct mvlm_hourglass {
+  HourglassNet net;
+};
+
+size_t mvlm_hourglass_workspace_bytes(int n_landmarks, int cin, int n_views, int h, int w) {
+  HourglassNet dry;
+  if (dry.build(nullptr, n_landmarks, cin, n_views, h, w, nullptr, 0, true) != MVLM_OK) return 0;
+  return dry.workspace_needed();
+}
+
+double mvlm_hourglass_flops_per_view(int n_landmarks, int cin, int h, int w) {
+  HourglassNet dry;
+  if (dry.build(nullptr, n_landmarks, cin, 1, h, w, nullptr, 0, true) != MVLM_OK) return 0.0;
+  return dry.flops_per_view();
+}
+
+int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, int n_entries, int n_landmarks, int cin,
+                          int n_views, int h, int w, void* workspace, size_t workspace_bytes, mvlm_hourglass** out) {
+  MVLM_REQUIRE(names && ptrs && out, "mvlm_hourglass_create: null pointer");
+  std::map<std::string, const float*> sd;
+  for (int i = 0; i < n_entries; ++i) sd[names[i]] = static_cast<const float*>(ptrs[i]);
+  mvlm_hourglass* h_ = new mvlm_hourglass();
+  const int rc = h_->net.build(&sd, n_landmarks, cin, n_views, h, w, workspace, workspace_bytes, false);
+  if (rc != MVLM_OK) {
+    delete h_;
+    return rc;
+  }
+  *out = h_;
+  return MVLM_OK;
+}
+
+int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, float* out_heatmaps,
+                           float* out_peaks, void* stream) {
+  MVLM_REQUIRE(net, "mvlm_hourglass_forward: null handle");
+  return net->net.forward(img_u8, img_f32, out_heatmaps, out_peaks, static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_hourglass_num_launches(const mvlm_hourglass* net) { return net ? net->net.n_ops() : 0; }
+
+int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c) {
+  MVLM_REQUIRE(net && name && ptr && h && w && c, "mvlm_hourglass_probe: null pointer");
+  auto it = net->net.probes.find(name);
+  MVLM_REQUIRE(it != net->net.probes.end(), "mvlm_hourglass_probe: unknown probe %s", name);
+  *ptr = it->second.p; *h = it->second.h; *w = it->second.w; *c = it->second.c;
+  return MVLM_OK;
+}
+
+void mvlm_hourglass_destroy(mvlm_hourglass* net) { delete net; }
+
+int mvlm_heatmap_peaks(const float* heatmaps, int n_views, int n_landmarks, int h, int w, int method,
+                       float* out_peaks, void* stream) {
+  return peaks_from_heatmaps(heatmaps, n_views, n_landmarks, h, w, method, out_peaks,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_rays_from_peaks(const float* peaks, const double* rot, int n_landmarks, int n_views, int image_size,
+                         double* out_starts, double* out_ends, void* stream) {
+  return rays_from_peaks(peaks, rot, n_landmarks, n_views, image_size, out_starts, out_ends,
+                         static_cast<cudaStream_t>(stream));
+}
+
+size_t mvlm_consensus_workspace_bytes(int n_landmarks, int n_views, int n_hyp) {
+  return consensus_workspace_bytes(n_landmarks, n_views, n_hyp);
+}
+
+int mvlm_consensus(const float* peaks, const double* starts, const double* ends, int n_landmarks, int n_views,
+                   int mode, double threshold_quantile, float threshold_absolute, const uint32_t* draws, int n_hyp,
+                   double dist_thres, void* workspace, size_t workspace_bytes, double* out_landmarks,
+                   double* out_errors, int32_t* out_nlines, void* stream) {
+  ConsensusArgs a;
+  a.peaks = peaks; a.starts = starts; a.ends = ends; a.l = n_landmarks; a.v = n_views; a.mode = mode;
+  a.threshold_quantile = threshold_quantile; a.threshold_absolute = threshold_absolute;
+  a.draws = draws; a.n_hyp = n_hyp; a.dist_thres = dist_thres;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  a.out_landmarks = out_landmarks; a.out_errors = out_errors; a.out_nlines = out_nlines;
+  return consensus_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+size_t mvlm_snap_workspace_bytes(int n_landmarks, int n_tris) { return snap_workspace_bytes(n_landmarks, n_tris); }
+
+int mvlm_snap_to_mesh(const float* verts, const int32_t* tris, int n_tris, const double* landmarks, int n_landmarks,
+                      void* workspace, size_t workspace_bytes, double* out, int32_t* out_tri, void* stream) {
+  return snap_launch(verts, tris, n_tris, landmarks, n_landmarks, workspace, workspace_bytes, out, out_tri,
+                     static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,527 @@
+// Stacked-hourglass heat-map CNN as a static plan of fused launches (see hourglass.cuh).
+//
+// Dataflow of the reference model (src/mvlm/prediction/paulsenpredictor.py):
+//   MVLMModel.forward :404-432, HourGlassModule.forward :301-361, ResidualBlock.forward :267-273,
+//   eval mode (BatchNorm running statistics folded to scale/shift, dropout = identity).
+// Only outputs[-1] (the conv11 branch) is consumed by the predictor (:204-205), so conv8 and its
+// up-sampling (:418-419) are never scheduled.
+//
+// Every stored activation is NHWC bf16.  A ResidualBlock is three conv launches (+1 for the 1x1
+// resample) whose epilogues write (i) the raw output into its channel slice of the block output
+// with the residual slice added (torch.cat + residual, :273), (ii) the next conv's
+// BatchNorm+ReLU'd input, and (iii) the BatchNorm+ReLU'd input of the block's designated consumer.
+// conv11 on the nearest-x2 up-sampled conv10 output (:428-429) is evaluated as four 2x2 "phase"
+// convolutions at the low resolution (taps that read the same low-res pixel are pre-summed), with
+// the per-(view, landmark) arg-max fused into the epilogue, so the (V,L,256,256) fp32 heat maps
+// (1.9 GB at V=100) are only materialised on request.
+#include "hourglass.cuh"
+
+#include <math.h>
+
+namespace mvlm {
+
+namespace {
+
+__global__ void fold_bn_kernel(const float* w, const float* b, const float* m, const float* v, float eps, int n,
+                               float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = w[i] / sqrtf(v[i] + eps);
+  scale[i] = s;
+  shift[i] = b[i] - m[i] * s;
+}
+
+// OIHW fp32 -> [cout_pad][kw][kh][cin_pad] bf16
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int k, int cout_pad, int cin_pad,
+                                   __nv_bfloat16* __restrict__ out) {
+  const long long total = 1ll * cout_pad * k * k * cin_pad;
+  for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+    const int ci = static_cast<int>(i % cin_pad);
+    long long r = i / cin_pad;
+    const int ky = static_cast<int>(r % k);
+    r /= k;
+    const int kx = static_cast<int>(r % k);
+    const int co = static_cast<int>(r / k);
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[((1ll * co * cin + ci) * k + ky) * k + kx];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// conv3x3(nearest_up2(x)) phase (a,b): 2x2 taps at low resolution, [cout_pad][kx(2)][ky(2)][cin_pad] bf16.
+//   a=0: rows {-1: w[0], 0: w[1]+w[2]}   a=1: rows {0: w[0]+w[1], +1: w[2]}   (same for columns with b)
+__global__ void pack_phase_weight_kernel(const float* __restrict__ w, int cout, int cin, int a, int b, int cout_pad,
+                                         int cin_pad, __nv_bfloat16* __restrict__ out) {
+  const long long total = 1ll * cout_pad * 4 * cin_pad;
+  for (long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x; i < total; i += 1ll * gridDim.x * blockDim.x) {
+    const int ci = static_cast<int>(i % cin_pad);
+    long long r = i / cin_pad;
+    const int ky = static_cast<int>(r % 2);
+    r /= 2;
+    const int kx = static_cast<int>(r % 2);
+    const int co = static_cast<int>(r / 2);
+    float v = 0.f;
+    if (co < cout && ci < cin) {
+      const float* q = w + (1ll * co * cin + ci) * 9;
+      // source rows / cols of the 3x3 kernel folded into this low-res tap
+      const int r0 = a == 0 ? (ky == 0 ? 0 : 1) : (ky == 0 ? 0 : 2);
+      const int r1 = a == 0 ? (ky == 0 ? 0 : 2) : (ky == 0 ? 1 : 2);
+      const int c0 = b == 0 ? (kx == 0 ? 0 : 1) : (kx == 0 ? 0 : 2);
+      const int c1 = b == 0 ? (kx == 0 ? 0 : 2) : (kx == 0 ? 1 : 2);
+      for (int rr = r0; rr <= r1; ++rr)
+        for (int cc = c0; cc <= c1; ++cc) v += q[rr * 3 + cc];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void pad_bias_kernel(const float* b, int n, int n_pad, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) out[i] = i < n ? b[i] : 0.f;
+}
+
+inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+HourglassNet::~HourglassNet() {
+  for (void* p : owned_) cudaFree(p);
+}
+
+void* HourglassNet::ws_alloc(size_t bytes) {
+  const size_t aligned = (bytes + 1023) & ~static_cast<size_t>(1023);
+  void* p = (dry_ || ws_ == nullptr) ? nullptr : ws_ + ws_off_;
+  ws_off_ += aligned;
+  return p;
+}
+
+HourglassNet::T HourglassNet::alloc(int h, int w, int c) {
+  T t;
+  t.h = h; t.w = w; t.c = c;
+  t.p = static_cast<__nv_bfloat16*>(ws_alloc(static_cast<size_t>(V_) * h * w * c * sizeof(__nv_bfloat16)));
+  return t;
+}
+
+HourglassNet::T HourglassNet::scratch(int h, int w, int c, int slot) {
+  char key[64];
+  snprintf(key, sizeof(key), "%d_%d_%d_%d", h, w, c, slot);
+  auto it = scratch_.find(key);
+  if (it != scratch_.end()) return it->second;
+  T t = alloc(h, w, c);
+  scratch_[key] = t;
+  return t;
+}
+
+int HourglassNet::bn(const std::string& name, int c, const float** scale, const float** shift) {
+  *scale = *shift = nullptr;
+  if (dry_) return MVLM_OK;
+  auto it = bn_cache_.find(name);
+  if (it == bn_cache_.end()) {
+    const char* suffix[4] = {".weight", ".bias", ".running_mean", ".running_var"};
+    const float* src[4];
+    for (int k = 0; k < 4; ++k) {
+      auto f = sd_->find(name + suffix[k]);
+      MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s%s", name.c_str(), suffix[k]);
+      src[k] = f->second;
+    }
+    float* buf = nullptr;
+    MVLM_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * 2 * c));
+    owned_.push_back(buf);
+    fold_bn_kernel<<<ceil_div(c, 128), 128>>>(src[0], src[1], src[2], src[3], 1e-5f, c, buf, buf + c);
+    MVLM_CHECK_CUDA(cudaGetLastError());
+    it = bn_cache_.emplace(name, std::make_pair(buf, buf + c)).first;
+  }
+  *scale = it->second.first;
+  *shift = it->second.second;
+  return MVLM_OK;
+}
+
+int HourglassNet::packed(const std::string& name, int cout, int cin, int k, int cout_pad, int cin_pad,
+                         const __nv_bfloat16** out) {
+  *out = nullptr;
+  if (dry_) return MVLM_OK;
+  auto f = sd_->find(name);
+  MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s", name.c_str());
+  __nv_bfloat16* buf = nullptr;
+  const size_t n = static_cast<size_t>(cout_pad) * k * k * cin_pad;
+  MVLM_CHECK_CUDA(cudaMalloc(&buf, n * sizeof(__nv_bfloat16)));
+  owned_.push_back(buf);
+  pack_weight_kernel<<<256, 256>>>(f->second, cout, cin, k, cout_pad, cin_pad, buf);
+  MVLM_CHECK_CUDA(cudaGetLastError());
+  *out = buf;
+  return MVLM_OK;
+}
+
+int HourglassNet::bias(const std::string& name, int cout, int cout_pad, const float** out) {
+  *out = nullptr;
+  if (dry_) return MVLM_OK;
+  auto f = sd_->find(name);
+  MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s", name.c_str());
+  float* buf = nullptr;
+  MVLM_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * cout_pad));
+  owned_.push_back(buf);
+  pad_bias_kernel<<<ceil_div(cout_pad, 128), 128>>>(f->second, cout, cout_pad, buf);
+  MVLM_CHECK_CUDA(cudaGetLastError());
+  *out = buf;
+  return MVLM_OK;
+}
+
+int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& wname, int cout, int cout_pad,
+                            int n_tile, int k, ConvEpilogue e, bool with_bias) {
+  // algorithmic FLOPs use the true (unpadded) channel counts of the reference layer
+  const int cin_real = (wname == "conv7") ? L_ : cin;
+  flops_ += 2.0 * cout * cin_real * k * k * in.h * in.w;
+  NetOp op;
+  op.kind = NetOp::CONV;
+  op.tag = tag;
+  if (!dry_) {
+    ConvShape s;
+    s.in = in.p; s.n = V_; s.h = in.h; s.w = in.w; s.cin = cin; s.in_cs = in.c;
+    const __nv_bfloat16* wp;
+    int rc = packed(wname + ".weight", cout, cin_real, k, cout_pad, cin, &wp);
+    if (rc) return rc;
+    s.wpacked = wp; s.cout_pad = cout_pad; s.n_tile = n_tile; s.kh = k; s.kw = k;
+    s.y_off0 = -(k / 2); s.x_off0 = -(k / 2);
+    if (with_bias) {
+      rc = bias(wname + ".bias", cout, cout_pad, &e.bias);
+      if (rc) return rc;
+    }
+    rc = conv_plan(s, e, &op.conv);
+    if (rc) return rc;
+  }
+  ops_.push_back(op);
+  return MVLM_OK;
+}
+
+int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act,
+                     T* y_out) {
+  const int h = a_in.h, w = a_in.w;
+  T y = alloc(h, w, cout);
+  T skip = x;
+  int rc;
+  if (cin != cout) {
+    ConvEpilogue e;
+    e.out_raw = y.p; e.raw_cs = cout; e.raw_co = 0;
+    rc = emit_conv("rb.resample", ar, cin, p + ".resample.2", cout, cout, cout < 128 ? cout : 128, 1, e, false);
+    if (rc) return rc;
+    skip = y;  // the three convs accumulate in place
+  }
+  const float *ps = nullptr, *pt = nullptr;
+  if (post_bn) {
+    rc = bn(post_bn, cout, &ps, &pt);
+    if (rc) return rc;
+    *post_act = alloc(h, w, cout);
+  }
+  const int c1 = cout / 2, c2 = cout / 4;
+  T a1 = scratch(h, w, c1 < 64 ? 64 : c1, 1);
+  T a2 = scratch(h, w, c2 < 64 ? 64 : c2, 2);
+  const int widths[3] = {c1, c2, c2};
+  const int offs[3] = {0, c1, c1 + c2};
+  const int cins[3] = {cin, c1, c2};
+  const T ins[3] = {a_in, a1, a2};
+  const T pres[3] = {a1, a2, T()};
+  const char* pre_bn[3] = {".bn2", ".bn3", nullptr};
+  const char* names[3] = {".conv1", ".conv2", ".conv3"};
+  for (int i = 0; i < 3; ++i) {
+    ConvEpilogue e;
+    if (pre_bn[i]) {
+      rc = bn(p + pre_bn[i], widths[i], &e.pre_scale, &e.pre_shift);
+      if (rc) return rc;
+      e.out_pre = pres[i].p; e.pre_cs = pres[i].c; e.pre_co = 0;
+    }
+    e.res1 = skip.p; e.res1_cs = skip.c; e.res1_co = offs[i];
+    e.out_raw = y.p; e.raw_cs = cout; e.raw_co = offs[i];
+    if (post_bn) {
+      e.post_scale = dry_ ? nullptr : ps + offs[i];
+      e.post_shift = dry_ ? nullptr : pt + offs[i];
+      e.out_post = post_act->p; e.post_cs = cout; e.post_co = offs[i];
+    }
+    const int nt = widths[i] < 128 ? widths[i] : 128;
+    rc = emit_conv("rb.conv", ins[i], cins[i], p + names[i], widths[i], widths[i], nt, 3, e, false);
+    if (rc) return rc;
+  }
+  *y_out = y;
+  return MVLM_OK;
+}
+
+int HourglassNet::emit_pool(T in, T out_raw, const char* bn_name, T out_act) {
+  NetOp op;
+  op.kind = NetOp::POOL;
+  op.in0 = in.p; op.out_raw = out_raw.p; op.out_act = out_act.p;
+  op.h = in.h; op.w = in.w; op.c = in.c;
+  if (bn_name) {
+    int rc = bn(bn_name, in.c, &op.scale, &op.shift);
+    if (rc) return rc;
+  }
+  ops_.push_back(op);
+  return MVLM_OK;
+}
+
+int HourglassNet::emit_upadd(T low, T skip, T out_raw, const char* bn_name, T out_act) {
+  NetOp op;
+  op.kind = NetOp::UPADD;
+  op.in0 = low.p; op.in1 = skip.p; op.out_raw = out_raw.p; op.out_act = out_act.p;
+  op.h = skip.h; op.w = skip.w; op.c = skip.c;
+  if (bn_name) {
+    int rc = bn(bn_name, skip.c, &op.scale, &op.shift);
+    if (rc) return rc;
+  }
+  ops_.push_back(op);
+  return MVLM_OK;
+}
+
+int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
+  const int F = 256;
+  int rc;
+  T skips[5];
+  T none;
+  rc = rb(p + ".rb1", x, a_x, none, F, F, nullptr, nullptr, &skips[0]);
+  if (rc) return rc;
+  T cur = x, a_low;
+  const int low_blocks[5] = {2, 4, 6, 8, 10};
+  const int skip_blocks[4] = {3, 5, 7, 9};
+  for (int lvl = 0; lvl < 5; ++lvl) {
+    const std::string lb = p + ".rb" + std::to_string(low_blocks[lvl]);
+    T pooled = alloc(cur.h / 2, cur.w / 2, F), a = alloc(cur.h / 2, cur.w / 2, F);
+    rc = emit_pool(cur, pooled, (lb + ".bn1").c_str(), a);
+    if (rc) return rc;
+    const int nxt = lvl < 4 ? skip_blocks[lvl] : 11;
+    const std::string post = p + ".rb" + std::to_string(nxt) + ".bn1";
+    T low;
+    rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_low, &low);
+    if (rc) return rc;
+    if (lvl < 4) {
+      rc = rb(p + ".rb" + std::to_string(skip_blocks[lvl]), low, a_low, none, F, F, nullptr, nullptr, &skips[lvl + 1]);
+      if (rc) return rc;
+    }
+    cur = low;
+  }
+  T low2, a2, low3;
+  rc = rb(p + ".rb11", cur, a_low, none, F, F, (p + ".rb12.bn1").c_str(), &a2, &low2);
+  if (rc) return rc;
+  rc = rb(p + ".rb12", low2, a2, none, F, F, nullptr, nullptr, &low3);
+  if (rc) return rc;
+  cur = low3;
+  const int ups[4][2] = {{13, 14}, {15, 16}, {17, 18}, {19, 20}};
+  for (int lvl = 0; lvl < 4; ++lvl) {
+    T skip = skips[4 - lvl];
+    T s = alloc(skip.h, skip.w, F), a = alloc(skip.h, skip.w, F);
+    const std::string b1 = p + ".rb" + std::to_string(ups[lvl][0]);
+    const std::string b2 = p + ".rb" + std::to_string(ups[lvl][1]);
+    rc = emit_upadd(cur, skip, s, (b1 + ".bn1").c_str(), a);
+    if (rc) return rc;
+    T l1, a1, l2;
+    rc = rb(b1, s, a, none, F, F, (b2 + ".bn1").c_str(), &a1, &l1);
+    if (rc) return rc;
+    rc = rb(b2, l1, a1, none, F, F, nullptr, nullptr, &l2);
+    if (rc) return rc;
+    cur = l2;
+  }
+  T add5 = alloc(skips[0].h, skips[0].w, F);
+  rc = emit_upadd(cur, skips[0], add5, nullptr, T());
+  if (rc) return rc;
+  *out = add5;
+  return MVLM_OK;
+}
+
+int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_landmarks, int cin, int n_views, int h,
+                        int w, void* workspace, size_t workspace_bytes, bool dry) {
+  MVLM_REQUIRE(n_landmarks > 0 && n_landmarks <= 128, "hourglass: n_landmarks=%d unsupported", n_landmarks);
+  MVLM_REQUIRE(cin >= 1 && cin <= 4, "hourglass: image channels=%d unsupported", cin);
+  MVLM_REQUIRE(n_views > 0 && h >= 64 && w >= 64 && h % 64 == 0 && w % 64 == 0,
+               "hourglass: image size %dx%d must be a positive multiple of 64", h, w);
+  MVLM_REQUIRE(dry || (sd && workspace), "hourglass: null state_dict/workspace");
+  sd_ = sd; dry_ = dry;
+  V_ = n_views; H_ = h; W_ = w; L_ = n_landmarks; cin_ = cin;
+  Lp_ = pad_to(L_, 16);
+  if (Lp_ == 112) Lp_ = 128;
+  if (Lp_ == 48) Lp_ = 64;
+  if (Lp_ == 16) Lp_ = 32;
+  ws_ = static_cast<uint8_t*>(workspace); ws_size_ = workspace_bytes; ws_off_ = 0;
+  ops_.clear(); flops_ = 0.0;
+  int rc;
+  const int F = 256, h2 = h / 2, w2 = w / 2;
+
+  // ---- stem (:405-407) + conv2 block at full resolution (:410)
+  T a_c2 = alloc(h, w, 64), ar_c2 = alloc(h, w, 64);
+  {
+    NetOp op;
+    op.kind = NetOp::STEM;
+    StemArgs& st = op.stem;
+    st.n = V_; st.h = h; st.w = w; st.cin = cin;
+    st.out_a = a_c2.p; st.out_b = ar_c2.p;
+    if (!dry_) {
+      auto fw = sd_->find("conv1.weight"), fb = sd_->find("conv1.bias");
+      MVLM_REQUIRE(fw != sd_->end() && fb != sd_->end(), "hourglass: missing conv1.weight/bias");
+      // own copies: the caller's state_dict tensors need not outlive create()
+      float* wcopy = nullptr;
+      MVLM_CHECK_CUDA(cudaMalloc(&wcopy, sizeof(float) * (64 * cin * 9 + 64)));
+      owned_.push_back(wcopy);
+      MVLM_CHECK_CUDA(cudaMemcpy(wcopy, fw->second, sizeof(float) * 64 * cin * 9, cudaMemcpyDeviceToDevice));
+      MVLM_CHECK_CUDA(cudaMemcpy(wcopy + 64 * cin * 9, fb->second, sizeof(float) * 64, cudaMemcpyDeviceToDevice));
+      st.w_oihw = wcopy; st.bias = wcopy + 64 * cin * 9;
+      if ((rc = bn("bn1", 64, &st.s0, &st.t0))) return rc;
+      if ((rc = bn("conv2.bn1", 64, &st.sa, &st.ta))) return rc;
+      if ((rc = bn("conv2.resample.0", 64, &st.sb, &st.tb))) return rc;
+    }
+    flops_ += 2.0 * 64 * cin * 9 * h * w;
+    ops_.push_back(op);
+  }
+  T none, y2, y3, r3, a3, a4, a_h1, ar4;
+  if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, nullptr, nullptr, &y2))) return rc;
+  // ---- maxpool (:411), conv3, conv4 (:412-413)
+  T x1 = alloc(h2, w2, 128);
+  a3 = alloc(h2, w2, 128);
+  if ((rc = emit_pool(y2, x1, "conv3.bn1", a3))) return rc;
+  if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3))) return rc;
+  ar4 = alloc(h2, w2, 128);
+  {
+    NetOp op;
+    op.kind = NetOp::BNRELU;
+    op.in0 = y3.p; op.out_act = ar4.p; op.h = h2; op.w = w2; op.c = 128;
+    if ((rc = bn("conv4.resample.0", 128, &op.scale, &op.shift))) return rc;
+    ops_.push_back(op);
+  }
+  if ((rc = rb("conv4", y3, a4, ar4, 128, F, "hg1.rb1.bn1", &a_h1, &r3))) return rc;
+  probes["r3"] = {r3.p, r3.h, r3.w, r3.c};
+  // ---- hourglass 1 (:414), conv5+bn2+relu (:416), conv6 (:417), conv7 + sum (:420-422)
+  T hg1;
+  if ((rc = hourglass("hg1", r3, a_h1, &hg1))) return rc;
+  probes["hg1"] = {hg1.p, hg1.h, hg1.w, hg1.c};
+  T ll1 = alloc(h2, w2, F);
+  {
+    ConvEpilogue e;
+    if ((rc = bn("bn2", F, &e.pre_scale, &e.pre_shift))) return rc;
+    e.out_pre = ll1.p; e.pre_cs = F; e.pre_co = 0;
+    if ((rc = emit_conv("conv5", hg1, F, "conv5", F, F, 128, 3, e, true))) return rc;
+  }
+  T x6 = alloc(h2, w2, Lp_);
+  {
+    ConvEpilogue e;
+    e.out_raw = x6.p; e.raw_cs = Lp_; e.raw_co = 0;
+    if ((rc = emit_conv("conv6", ll1, F, "conv6", L_, Lp_, Lp_, 3, e, true))) return rc;
+  }
+  T sum = alloc(h2, w2, F), a_h2;
+  {
+    ConvEpilogue e;
+    e.res1 = r3.p; e.res1_cs = F; e.res1_co = 0;
+    e.res2 = ll1.p; e.res2_cs = F; e.res2_co = 0;
+    e.out_raw = sum.p; e.raw_cs = F; e.raw_co = 0;
+    a_h2 = alloc(h2, w2, F);
+    if ((rc = bn("hg2.rb1.bn1", F, &e.post_scale, &e.post_shift))) return rc;
+    e.out_post = a_h2.p; e.post_cs = F; e.post_co = 0;
+    if ((rc = emit_conv("conv7", x6, Lp_, "conv7", F, F, 128, 3, e, true))) return rc;
+  }
+  probes["sum_temp"] = {sum.p, sum.h, sum.w, sum.c};
+  // ---- hourglass 2 (:424), conv9+bn3+relu (:426), conv10 (:427)
+  T hg2;
+  if ((rc = hourglass("hg2", sum, a_h2, &hg2))) return rc;
+  T ll2 = alloc(h2, w2, F);
+  {
+    ConvEpilogue e;
+    if ((rc = bn("bn3", F, &e.pre_scale, &e.pre_shift))) return rc;
+    e.out_pre = ll2.p; e.pre_cs = F; e.pre_co = 0;
+    if ((rc = emit_conv("conv9", hg2, F, "conv9", F, F, 128, 3, e, true))) return rc;
+  }
+  T x10 = alloc(h2, w2, Lp_);
+  {
+    ConvEpilogue e;
+    e.out_raw = x10.p; e.raw_cs = Lp_; e.raw_co = 0;
+    if ((rc = emit_conv("conv10", ll2, F, "conv10", L_, Lp_, Lp_, 3, e, true))) return rc;
+  }
+  probes["x10"] = {x10.p, x10.h, x10.w, x10.c};
+  // ---- conv11 on nearest-x2(conv10) (:428-429) as four 2x2 phase convs with fused arg-max
+  keys_ = static_cast<unsigned long long*>(ws_alloc(sizeof(unsigned long long) * V_ * L_));
+  {
+    NetOp op;
+    op.kind = NetOp::MEMSET;
+    op.ptr = keys_; op.bytes = sizeof(unsigned long long) * V_ * L_;
+    ops_.push_back(op);
+  }
+  flops_ += 2.0 * L_ * L_ * 9 * h * w;  // algorithmic FLOPs of the reference's conv11
+  const float* b11 = nullptr;
+  if ((rc = bias("conv11.bias", L_, Lp_, &b11))) return rc;
+  for (int a = 0; a < 2; ++a) {
+    for (int b = 0; b < 2; ++b) {
+      NetOp op;
+      op.kind = NetOp::CONV;
+      op.is_head = true;
+      op.tag = "conv11.phase";
+      if (!dry_) {
+        auto f = sd_->find("conv11.weight");
+        MVLM_REQUIRE(f != sd_->end(), "hourglass: missing conv11.weight");
+        __nv_bfloat16* wp = nullptr;
+        MVLM_CHECK_CUDA(cudaMalloc(&wp, sizeof(__nv_bfloat16) * Lp_ * 4 * Lp_));
+        owned_.push_back(wp);
+        pack_phase_weight_kernel<<<64, 256>>>(f->second, L_, L_, a, b, Lp_, Lp_, wp);
+        MVLM_CHECK_CUDA(cudaGetLastError());
+        ConvShape s;
+        s.in = x10.p; s.n = V_; s.h = h2; s.w = w2; s.cin = Lp_; s.in_cs = Lp_;
+        s.wpacked = wp; s.cout_pad = Lp_; s.n_tile = Lp_; s.kh = 2; s.kw = 2;
+        s.y_off0 = a - 1; s.x_off0 = b - 1;
+        ConvEpilogue e;
+        e.bias = b11;
+        e.argmax_keys = keys_;
+        e.cout_real = L_;
+        e.up_sy = 2; e.up_sx = 2; e.up_py = a; e.up_px = b;
+        if ((rc = conv_plan(s, e, &op.conv))) return rc;
+      }
+      ops_.push_back(op);
+    }
+  }
+  {
+    NetOp op;
+    op.kind = NetOp::PEAKS;
+    ops_.push_back(op);
+  }
+  if (!dry_) {
+    MVLM_REQUIRE(ws_off_ <= ws_size_, "hourglass: workspace too small (%zu needed, %zu given)", ws_off_, ws_size_);
+    MVLM_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  return MVLM_OK;
+}
+
+int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
+                          cudaStream_t stream) {
+  MVLM_REQUIRE(!dry_, "hourglass: forward on a dry plan");
+  MVLM_REQUIRE(out_peaks || out_heatmaps, "hourglass: no output requested");
+  for (NetOp& op : ops_) {
+    int rc = MVLM_OK;
+    switch (op.kind) {
+      case NetOp::STEM: {
+        StemArgs st = op.stem;
+        st.img_u8 = img_u8; st.img_f32 = img_f32;
+        rc = stem_launch(st, stream);
+        break;
+      }
+      case NetOp::CONV:
+        if (op.is_head) {
+          ConvParams p = op.conv;
+          p.e.out_f32 = out_heatmaps;
+          rc = conv_launch(p, stream);
+        } else {
+          rc = conv_launch(op.conv, stream);
+        }
+        break;
+      case NetOp::POOL:
+        rc = pool2_act(op.in0, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
+        break;
+      case NetOp::UPADD:
+        rc = upadd_act(op.in0, op.in1, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
+        break;
+      case NetOp::BNRELU:
+        rc = bn_relu(op.in0, static_cast<size_t>(V_) * op.h * op.w, op.c, op.scale, op.shift, op.out_act, stream);
+        break;
+      case NetOp::MEMSET:
+        MVLM_CHECK_CUDA(cudaMemsetAsync(op.ptr, 0, op.bytes, stream));
+        break;
+      case NetOp::PEAKS:
+        if (out_peaks) rc = peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
+        break;
+    }
+    if (rc != MVLM_OK) return rc;
+  }
+  return MVLM_OK;
+}
+
+}  // namespace mvlm

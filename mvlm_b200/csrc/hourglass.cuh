@@ -1,0 +1,80 @@
+// Stacked-hourglass heat-map CNN plan: the whole network as a static list of fused launches.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_umma.cuh"
+#include "stages.cuh"
+
+namespace mvlm {
+
+struct NetOp {
+  enum Kind { CONV, POOL, UPADD, BNRELU, STEM, MEMSET, PEAKS } kind;
+  ConvParams conv;  // CONV
+  // eltwise / memset
+  const __nv_bfloat16* in0 = nullptr;
+  const __nv_bfloat16* in1 = nullptr;
+  __nv_bfloat16* out_raw = nullptr;
+  __nv_bfloat16* out_act = nullptr;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int h = 0, w = 0, c = 0;
+  StemArgs stem;
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool is_head = false;  // conv11 phase: out_f32 patched per forward call
+  const char* tag = "";
+};
+
+class HourglassNet {
+ public:
+  HourglassNet() = default;
+  ~HourglassNet();
+  // dry == true: only computes the workspace size (no CUDA calls).
+  int build(const std::map<std::string, const float*>* sd, int n_landmarks, int cin, int n_views, int h, int w,
+            void* workspace, size_t workspace_bytes, bool dry);
+  int forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
+              cudaStream_t stream);
+
+  size_t workspace_needed() const { return ws_off_; }
+  int n_views() const { return V_; }
+  int n_landmarks() const { return L_; }
+  int height() const { return H_; }
+  int width() const { return W_; }
+  double flops_per_view() const { return flops_; }
+  int n_ops() const { return static_cast<int>(ops_.size()); }
+  const std::vector<NetOp>& ops() const { return ops_; }
+  // intermediate tensors exposed for layer-wise parity tests: name -> (ptr, h, w, c)
+  struct Probe { const __nv_bfloat16* p; int h, w, c; };
+  std::map<std::string, Probe> probes;
+
+ private:
+  struct T { __nv_bfloat16* p = nullptr; int h = 0, w = 0, c = 0; };
+  T alloc(int h, int w, int c);
+  T scratch(int h, int w, int c, int slot);
+  void* ws_alloc(size_t bytes);
+  int bn(const std::string& name, int c, const float** scale, const float** shift);
+  int packed(const std::string& name, int cout, int cin, int k, int cout_pad, int cin_pad, const __nv_bfloat16** out);
+  int bias(const std::string& name, int cout, int cout_pad, const float** out);
+  int emit_conv(const char* tag, T in, int cin, const std::string& wname, int cout, int cout_pad, int n_tile, int k,
+                ConvEpilogue e, bool with_bias);
+  int rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act, T* y_out);
+  int hourglass(const std::string& p, T x, T a_x, T* out);
+  int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
+  int emit_upadd(T low, T skip, T out_raw, const char* bn_name, T out_act);
+
+  const std::map<std::string, const float*>* sd_ = nullptr;
+  bool dry_ = true;
+  int V_ = 0, H_ = 0, W_ = 0, L_ = 0, Lp_ = 0, cin_ = 0;
+  uint8_t* ws_ = nullptr;
+  size_t ws_size_ = 0, ws_off_ = 0;
+  std::vector<void*> owned_;
+  std::map<std::string, std::pair<float*, float*>> bn_cache_;
+  std::map<std::string, T> scratch_;
+  std::vector<NetOp> ops_;
+  unsigned long long* keys_ = nullptr;
+  double flops_ = 0.0;
+};
+
+}  // namespace mvlm

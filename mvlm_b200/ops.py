@@ -63,3 +63,144 @@ def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = Non
     a.cout_real = cout_real if cout_real is not None else wpacked.shape[0]
     a.up_sy, a.up_sx, a.up_py, a.up_px = up
     check(lib.mvlm_conv2d_bf16(C.byref(a), cur_stream()), "mvlm_conv2d_bf16")
+
+
+# --------------------------------------------------------------------------------------------
+# stage wrappers (device tensors in, device tensors out)
+# --------------------------------------------------------------------------------------------
+CHANNEL_MODES = {"RGB+depth": 0, "geometry+depth": 1, "RGB": 2, "depth": 3, "geometry": 4}
+MODE_CHANNELS = {0: 4, 1: 2, 2: 3, 3: 1, 4: 1}
+
+
+def raster_multiview(verts, uvs, tris, tex, rot, h: int, w: int, channel_mode: str = "RGB+depth",
+                     want_f32: bool = False, want_tri: bool = False, want_z: bool = False, zbuf=None, out_u8=None):
+    """verts (Nv,3) f32, uvs (Nv,2) f32|None, tris (Nt,3) i32, tex (Th,Tw,3) u8|None, rot (V,9|3,3) f64 -- all cuda.
+    Returns dict(u8=(V,H,W,4) u8, f32=(V,H,W,C)|None, tri=(V,H,W) i32|None, z=(V,H,W) f32|None)."""
+    lib = _lib.load()
+    dev = verts.device
+    mode = CHANNEL_MODES[channel_mode]
+    v = rot.shape[0]
+    if zbuf is None:
+        zbuf = torch.empty((v, h, w), dtype=torch.int64, device=dev)
+    if out_u8 is None:
+        out_u8 = torch.empty((v, h, w, 4), dtype=torch.uint8, device=dev)
+    f32 = torch.empty((v, h, w, MODE_CHANNELS[mode]), dtype=torch.float32, device=dev) if want_f32 else None
+    tri = torch.empty((v, h, w), dtype=torch.int32, device=dev) if want_tri else None
+    z = torch.empty((v, h, w), dtype=torch.float32, device=dev) if want_z else None
+    th, tw = (tex.shape[0], tex.shape[1]) if tex is not None else (0, 0)
+    check(lib.mvlm_raster_multiview(ptr(verts), ptr(uvs), ptr(tris), tris.shape[0], ptr(tex), th, tw, ptr(rot), v, h, w,
+                                    mode, ptr(zbuf), ptr(out_u8), ptr(f32), ptr(tri), ptr(z), cur_stream()),
+          "mvlm_raster_multiview")
+    return {"u8": out_u8, "f32": f32, "tri": tri, "z": z}
+
+
+class Hourglass:
+    """Owns the device copy of a state_dict, the workspace and the planned network for a fixed
+    (n_views, H, W).  `forward` runs the whole CNN (+ fused arg-max) on the current stream."""
+
+    def __init__(self, state_dict: dict, n_landmarks: int, cin: int, n_views: int, h: int, w: int, device="cuda"):
+        lib = _lib.load()
+        self.n_landmarks, self.cin, self.n_views, self.h, self.w = n_landmarks, cin, n_views, h, w
+        self.device = torch.device(device)
+        self._sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()
+                    if v.is_floating_point()}
+        nbytes = lib.mvlm_hourglass_workspace_bytes(n_landmarks, cin, n_views, h, w)
+        if nbytes == 0:
+            raise _lib.MvlmError("mvlm_hourglass_workspace_bytes: " + lib.mvlm_last_error().decode())
+        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        names = list(self._sd.keys())
+        arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        arr_p = (C.c_void_p * len(names))(*[self._sd[n].data_ptr() for n in names])
+        handle = C.c_void_p()
+        check(lib.mvlm_hourglass_create(arr_n, arr_p, len(names), n_landmarks, cin, n_views, h, w,
+                                        self.workspace.data_ptr(), nbytes, C.byref(handle)), "mvlm_hourglass_create")
+        self._h = handle
+        self.flops_per_view = lib.mvlm_hourglass_flops_per_view(n_landmarks, cin, h, w)
+        self.num_launches = lib.mvlm_hourglass_num_launches(handle)
+
+    def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True):
+        """img: (V,H,W,4) uint8 (rasteriser output) or (V,H,W,cin) float32; returns (peaks (L,V,3) f32, heatmaps|None)."""
+        lib = _lib.load()
+        assert img.shape[0] == self.n_views and img.shape[1] == self.h and img.shape[2] == self.w
+        u8 = img if img.dtype == torch.uint8 else None
+        f32 = img.contiguous() if img.dtype == torch.float32 else None
+        if u8 is None and f32 is None:
+            raise TypeError("img must be uint8 (V,H,W,4) or float32 (V,H,W,cin)")
+        if f32 is not None and f32.shape[3] != self.cin:
+            raise ValueError(f"expected {self.cin} channels, got {f32.shape[3]}")
+        peaks = torch.empty((self.n_landmarks, self.n_views, 3), dtype=torch.float32, device=self.device) if want_peaks else None
+        hm = torch.empty((self.n_views, self.n_landmarks, self.h, self.w), dtype=torch.float32, device=self.device) \
+            if want_heatmaps else None
+        check(lib.mvlm_hourglass_forward(self._h, ptr(u8), ptr(f32), ptr(hm), ptr(peaks), cur_stream()),
+              "mvlm_hourglass_forward")
+        return peaks, hm
+
+    def probe(self, name: str) -> torch.Tensor:
+        """Copy of an intermediate NHWC bf16 tensor (layer-wise parity tests)."""
+        lib = _lib.load()
+        p, h, w, c = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.mvlm_hourglass_probe(self._h, name.encode(), C.byref(p), C.byref(h), C.byref(w), C.byref(c)), "probe")
+        off = p.value - self.workspace.data_ptr()
+        n = self.n_views * h.value * w.value * c.value
+        return self.workspace[off:off + 2 * n].view(torch.bfloat16).view(self.n_views, h.value, w.value, c.value).clone()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().mvlm_hourglass_destroy(self._h)
+                self._h = None
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def heatmap_peaks(heatmaps: torch.Tensor, selection_method: str = "simple") -> torch.Tensor:
+    lib = _lib.load()
+    method = {"simple": 0, "moment": 1}[selection_method]
+    v, l, h, w = heatmaps.shape
+    hm = heatmaps.contiguous()
+    out = torch.empty((l, v, 3), dtype=torch.float32, device=hm.device)
+    check(lib.mvlm_heatmap_peaks(ptr(hm), v, l, h, w, method, ptr(out), cur_stream()), "mvlm_heatmap_peaks")
+    return out
+
+
+def rays_from_peaks(peaks: torch.Tensor, rot: torch.Tensor, image_size: int):
+    lib = _lib.load()
+    l, v = peaks.shape[:2]
+    starts = torch.empty((l, v, 3), dtype=torch.float64, device=peaks.device)
+    ends = torch.empty_like(starts)
+    check(lib.mvlm_rays_from_peaks(ptr(peaks), ptr(rot), l, v, image_size, ptr(starts), ptr(ends), cur_stream()),
+          "mvlm_rays_from_peaks")
+    return starts, ends
+
+
+def consensus(peaks, starts, ends, draws, mode: str = "quantile", threshold_quantile: float = 0.5,
+              threshold_absolute: float = 0.5, dist_thres: float = 100.0, workspace=None):
+    """Returns (landmarks (L,3) f64, errors (L,) f64, n_lines (L,) i32) on the device."""
+    lib = _lib.load()
+    if mode not in ("quantile", "absolute"):
+        raise ValueError(f"Unknown mode for line matching in Estimator: {mode}")
+    l, v = peaks.shape[:2]
+    n_hyp = draws.shape[1]
+    nbytes = lib.mvlm_consensus_workspace_bytes(l, v, n_hyp)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty((nbytes,), dtype=torch.uint8, device=peaks.device)
+    lm = torch.empty((l, 3), dtype=torch.float64, device=peaks.device)
+    err = torch.empty((l,), dtype=torch.float64, device=peaks.device)
+    nl = torch.empty((l,), dtype=torch.int32, device=peaks.device)
+    check(lib.mvlm_consensus(ptr(peaks), ptr(starts), ptr(ends), l, v, 0 if mode == "quantile" else 1,
+                             float(threshold_quantile), float(threshold_absolute), ptr(draws), n_hyp, float(dist_thres),
+                             ptr(workspace), workspace.numel(), ptr(lm), ptr(err), ptr(nl), cur_stream()), "mvlm_consensus")
+    return lm, err, nl
+
+
+def snap_to_mesh(verts, tris, landmarks, workspace=None):
+    lib = _lib.load()
+    l, nt = landmarks.shape[0], tris.shape[0]
+    nbytes = lib.mvlm_snap_workspace_bytes(l, nt)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty((nbytes,), dtype=torch.uint8, device=verts.device)
+    out = torch.empty((l, 3), dtype=torch.float64, device=verts.device)
+    tid = torch.empty((l,), dtype=torch.int32, device=verts.device)
+    check(lib.mvlm_snap_to_mesh(ptr(verts), ptr(tris), nt, ptr(landmarks), l, ptr(workspace), workspace.numel(), ptr(out),
+                                ptr(tid), cur_stream()), "mvlm_snap_to_mesh")
+    return out, tid

@@ -1,0 +1,163 @@
+"""Drop-in boundary: the reference's Pipeline (src/mvlm/pipeline/general_pipeline.py:39-146).
+
+`predict_one_file(path)` keeps the reference's signature, error behaviour and stage prints.  When
+the three components are the B200 ones (the default), the scan stays on the GPU from mesh upload
+to the final (L,3) landmarks ("fused" path); if a user swapped in their own Predictor2D /
+renderer / estimator, the reference's seam-by-seam numpy flow is used instead.
+"""
+from __future__ import annotations
+
+__all__ = ["Pipeline"]
+
+import abc
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from ..io_obj import Mesh, load_obj
+from ..prediction.paulsenpredictor import PaulsenModel
+from ..utils import Estimator3D, ObjRenderer3D
+
+
+class TimeMixin:
+    def __init__(self):
+        self.start_time = time.time()
+        self.end_time = None
+
+    def tic(self):
+        self.start_time = time.time()
+
+    def toc(self):
+        self.end_time = time.time()
+        return self.end_time - self.start_time
+
+    def toc_p(self):
+        return self.p_time(self.toc())
+
+    def p_time(self, t):
+        return f"{t:08.6f} s"
+
+
+class Pipeline(abc.ABC, TimeMixin):
+    def __init__(self, render_image_stack: bool = False, offscreen: bool = True, n_views: int = 8,
+                 render_image_folder: Path | None = None, visualize_rays: bool = False,
+                 screenshot_folder: Path | None = None, *, image_size: tuple = (256, 256),
+                 channel_mode: str = "RGB+depth", n_hypotheses: int = 1, seed: int | None = None,
+                 transforms: np.ndarray | None = None, device: str = "cuda", verbose: bool = True):
+        TimeMixin.__init__(self)
+        self.render_image_stack = render_image_stack
+        self.render_image_folder = render_image_folder
+        self.n_views = n_views
+        self.visualize_rays = visualize_rays  # accepted for compatibility; the VTK ray viewer is out of scope
+        self.screenshot_folder = screenshot_folder
+        self.verbose = verbose
+        self.device = torch.device(device)
+
+        self.renderer_3d = ObjRenderer3D(image_size=image_size, offscreen=offscreen, n_views=n_views,
+                                         channel_mode=channel_mode, device=device)
+        self.renderer_3d.transforms = transforms
+        self.renderer_3d.verbose = verbose
+        self.estimator_3d = Estimator3D(n_hypotheses=n_hypotheses, seed=seed, device=device)
+        self.estimator_3d.verbose = verbose
+        self.predictor_2d = None  # assigned by the subclasses
+        self.last_error = None    # "Landmarks [Error]" of the last scan (general_pipeline.py:109)
+
+    def _print(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def get_lm_count(self) -> int:
+        if self.predictor_2d is None:
+            raise ValueError("Predictor2D is not initialized.")
+        return self.predictor_2d.get_lm_count()
+
+    # ------------------------------------------------------------------ general_pipeline.py:67-131
+    def predict_one_file(self, file_name: Path, landmark_indices: list[int] | None = None,
+                         view_indices: list[int] | None = None, clip_rays_to_mesh: bool = True):
+        if self.predictor_2d is None:
+            raise ValueError("Predictor2D is not initialized.")
+        file_name = Path(file_name)
+        full_s = time.time()
+        if not file_name.exists():
+            print(f"File {file_name} does not exist")
+            return None
+        fused = (isinstance(self.predictor_2d, PaulsenModel) and type(self.renderer_3d) is ObjRenderer3D
+                 and type(self.estimator_3d) is Estimator3D and not self.render_image_stack
+                 and self.predictor_2d.selection_method == "simple")
+        if fused:
+            r = self.renderer_3d
+            if not file_name.is_file():
+                raise FileNotFoundError(f"File {file_name} is not a file")
+            if not file_name.suffix == ".obj":
+                raise ValueError(f"File {file_name} is not an .obj file. Only .obj files are supported.")
+            self.tic()
+            mesh = load_obj(file_name)
+            self._print("Render [1] - Setup time: ", self.toc_p())
+            landmarks = self.predict_mesh(mesh)
+            self._print("Landmarks 3D Total: ", self.p_time(time.time() - full_s))
+            return landmarks
+        return self._predict_seams(file_name, full_s)
+
+    def predict_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None) -> np.ndarray:
+        """Fused device path for an already loaded scan (host arrays in, (L,3) float64 out)."""
+        r, p, e = self.renderer_3d, self.predictor_2d, self.estimator_3d
+        if transforms is None:
+            transforms = r.generate_3d_transformations()
+        transforms = np.asarray(transforms)
+        dmesh = r.upload(mesh)
+        out = r.render_device(dmesh, transforms)
+        peaks = p.predict_landmarks_device(out["u8"])
+        starts, ends = e.estimate_landmark_lines_device(peaks, transforms, r.image_size[0])
+        if e.seed is not None:
+            draws = e.seeded_draws(peaks.shape[0])
+        else:
+            # reference RNG replay needs the per-landmark line counts -> one small D2H of the peak values
+            draws = e.reference_draws(peaks.cpu().numpy())
+        draws_d = torch.from_numpy(draws.view(np.int32)).to(self.device)
+        lm, err, _ = e.estimate_landmarks_from_lines_device(peaks, starts, ends, draws_d)
+        from .. import ops
+
+        snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm)
+        result = torch.cat([snapped.reshape(-1), err.sum().reshape(1) / err.numel()]).cpu().numpy()
+        self.last_error = float(result[-1])
+        self._print("Landmarks [Error]: ", f"{self.last_error:08.6f}", " mm")
+        return result[:-1].reshape(-1, 3)
+
+    def _predict_seams(self, file_name: Path, full_s: float):
+        self.tic()
+        image_stack, transform_stack, pd = self.renderer_3d.multiview_render(file_name)
+        self._print("Render [Total]: ", self.toc_p())
+        if self.render_image_stack:
+            self.visualize_image_stack(image_stack, file_name)
+        self.tic()
+        landmark_stack, valid = self.predictor_2d.predict_landmarks_from_images(image_stack)
+        self._print("Prediction [Total]: ", self.toc_p())
+        landmark_stack = landmark_stack[:, valid, :]
+        transform_stack = transform_stack[valid]
+        image_stack = image_stack[valid]
+        self.tic()
+        lines_s, lines_e = self.estimator_3d.estimate_landmark_lines(image_stack, landmark_stack, transform_stack)
+        self._print("Landmarks [0] - From Heatmaps: ", self.toc_p())
+        self.tic()
+        landmarks, error = self.estimator_3d.estimate_landmarks_from_lines(landmark_stack, lines_s, lines_e)
+        self._print("Landmarks [1] - From View Lines: ", self.toc_p())
+        self.tic()
+        landmarks = self.estimator_3d.project_landmarks_to_surface(pd, landmarks)
+        self._print("Landmarks [2] - Project to Surface: ", self.toc_p())
+        self.last_error = error
+        self._print("Landmarks [Error]: ", f"{error:08.6f}", " mm")
+        self._print("Landmarks 3D Total: ", self.p_time(time.time() - full_s))
+        return landmarks
+
+    # general_pipeline.py:133-146
+    def visualize_image_stack(self, image_stack: np.ndarray, file_name: Path):
+        from PIL import Image
+
+        save_folder = self.render_image_folder or file_name.parent
+        if not Path(save_folder).exists():
+            raise ValueError(f"Folder for --visualize-method flag [{save_folder}] does not exist.")
+        for i in range(self.n_views):
+            single_image = np.uint8(image_stack[i, :, :, 0:3] * 255)
+            Image.fromarray(single_image).save(Path(save_folder) / f"{file_name.stem}_{i:02d}.png")

@@ -1,0 +1,123 @@
+"""Host-side mirror of the reference's PaulsenModel / DTU3DPredictor / BU3DFEPredictor
+(src/mvlm/prediction/paulsenpredictor.py:42-243) on top of the CUDA stacked-hourglass plan
+(csrc/hourglass.cu) and the peak kernels (csrc/peaks.cu, fused arg-max in csrc/conv_umma.cu).
+
+Weights: the reference downloads `models_urls[...]` with torch.hub (:94-102).  Here, in order:
+`weights=` (a state_dict or a .pth path), `<model_dir>/<name>.pth`, `$MVLM_B200_WEIGHTS_DIR`, and
+otherwise -- only if `$MVLM_B200_RANDOM_INIT` is set or weights="random" -- a seeded random init.
+"""
+from __future__ import annotations
+
+import abc
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..weights import IMAGE_CHANNELS, seeded_state_dict
+from .predictor2d import Predictor2D
+
+__all__ = ["BU3DFEPredictor", "DTU3DPredictor", "PaulsenModel"]
+
+
+class PaulsenModel(Predictor2D):
+    def __init__(self, model_type: str, image_mode: str, n_gpus=1, batch_size=2, selection_method="simple",
+                 weights=None, seed: int = 1234, device: str = "cuda"):
+        super().__init__()
+        self.batch_size = batch_size          # kept for API compatibility; all views run as one batch
+        self.selection_method = selection_method
+        self.model_type = model_type
+        self.image_mode = image_mode
+        self.n_gpus = n_gpus
+        self.device = torch.device(device)
+        self.verbose = True
+        self._state_dict = self._load_weights(weights, seed)
+        self._nets: dict = {}
+
+    @abc.abstractmethod
+    def get_lm_count(self) -> int:
+        pass
+
+    # ------------------------------------------------------------------ weights
+    def _load_weights(self, weights, seed):
+        name = f"{self.model_type}-{self.image_mode}"
+        if isinstance(weights, dict):
+            return weights
+        if isinstance(weights, (str, Path)) and str(weights) != "random":
+            ckpt = torch.load(str(weights), map_location="cpu")
+            return ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+        if weights is None:
+            for d in (Path(__file__).parent / "models", Path(os.environ.get("MVLM_B200_WEIGHTS_DIR", "/nonexistent"))):
+                for cand in sorted(d.glob(f"{name.replace('-', '_')}*.pth")) + sorted(d.glob(f"{name}*.pth")):
+                    ckpt = torch.load(str(cand), map_location="cpu")
+                    return ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+        if weights == "random" or os.environ.get("MVLM_B200_RANDOM_INIT"):
+            return seeded_state_dict(self.get_lm_count(), self.image_mode, seed)
+        raise RuntimeError(
+            f"no weights for {name}: pass weights=<state_dict|path>, put a checkpoint in prediction/models/ or "
+            "$MVLM_B200_WEIGHTS_DIR, or set MVLM_B200_RANDOM_INIT=1 for a seeded random init (no network access)")
+
+    # ------------------------------------------------------------------ network cache
+    def network(self, n_views: int, h: int, w: int) -> ops.Hourglass:
+        key = (n_views, h, w)
+        if key not in self._nets:
+            self._nets.clear()  # one workspace at a time (22.7 GB at 100 views of 256^2)
+            self._nets[key] = ops.Hourglass(self._state_dict, self.get_lm_count(), IMAGE_CHANNELS[self.image_mode],
+                                            n_views, h, w, device=self.device)
+        return self._nets[key]
+
+    # ------------------------------------------------------------------ paulsenpredictor.py:167-217
+    def predict_landmarks_from_images(self, image_stack: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        n_views = image_stack.shape[0]
+        valid = np.ones((n_views), dtype=bool)
+        img = torch.from_numpy(np.ascontiguousarray(image_stack, dtype=np.float32)).to(self.device)
+        peaks = self.predict_landmarks_device(img)
+        return peaks.cpu().numpy(), valid
+
+    def predict_landmarks_device(self, img: torch.Tensor) -> torch.Tensor:
+        """img: (V,H,W,4) uint8 from the rasteriser or (V,H,W,C) float32 in [0,1] on the device.
+        Returns peaks (L,V,3) float32 on the device."""
+        cin = IMAGE_CHANNELS[self.image_mode]
+        if img.dtype == torch.float32 and img.shape[3] > cin:
+            img = img[..., :cin].contiguous()   # e.g. an RGB model fed the 4-channel stack
+        v, h, w = img.shape[0], img.shape[1], img.shape[2]
+        net = self.network(v, h, w)
+        if self.selection_method == "simple":
+            peaks, _ = net.forward(img, want_heatmaps=False, want_peaks=True)
+            return peaks
+        if self.selection_method == "moment":
+            _, hm = net.forward(img, want_heatmaps=True, want_peaks=False)
+            return ops.heatmap_peaks(hm, "moment")
+        # the reference leaves the coordinates at zero for unknown methods (:118,:129)
+        return torch.zeros((self.get_lm_count(), v, 3), dtype=torch.float32, device=self.device)
+
+    def find_maxima_in_batch_of_heatmaps(self, heatmaps, heatmap_maxima=None):
+        """(V,L,H,W) float32 (numpy or torch) -> (L,V,3); paulsenpredictor.py:160-165."""
+        hm = heatmaps if isinstance(heatmaps, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(heatmaps))
+        if hm.dim() != 4:
+            raise RuntimeError(f"Unexpected heatmap tensor shape: {tuple(hm.shape)}")
+        out = ops.heatmap_peaks(hm.to(self.device, torch.float32), self.selection_method).cpu().numpy()
+        if heatmap_maxima is not None:
+            heatmap_maxima[...] = out
+            return heatmap_maxima
+        return out
+
+
+class BU3DFEPredictor(PaulsenModel):
+    def __init__(self, batch_size=2, selection_method="simple", n_gpus=1, image_mode="RGB+depth", **kw):
+        super().__init__(model_type="MVLMModel_BU_3DFE", image_mode=image_mode, n_gpus=n_gpus, batch_size=batch_size,
+                         selection_method=selection_method, **kw)
+
+    def get_lm_count(self) -> int:
+        return 84
+
+
+class DTU3DPredictor(PaulsenModel):
+    def __init__(self, batch_size=2, selection_method="simple", n_gpus=1, image_mode="RGB+depth", **kw):
+        super().__init__(model_type="MVLMModel_DTU3D", image_mode=image_mode, n_gpus=n_gpus, batch_size=batch_size,
+                         selection_method=selection_method, **kw)
+
+    def get_lm_count(self) -> int:
+        return 73

@@ -1,0 +1,4 @@
+__all__ = ["ObjRenderer3D", "ObjVTKRenderer3D", "Estimator3D"]
+
+from .estimator3d import Estimator3D
+from .render3d import ObjRenderer3D, ObjVTKRenderer3D

@@ -1,0 +1,154 @@
+"""Multi-view renderer: host-side mirror of the reference's ObjVTKRenderer3D
+(src/mvlm/utils/render3d.py:12-193) on top of the CUDA rasteriser (csrc/raster.cu).
+
+Same constructor arguments, same methods and return values:
+  multiview_render(path) -> (image_stack float32 (V,H,W,4) in [0,1], transform_stack (V,6), mesh)
+where `mesh` (an io_obj.Mesh) plays the role of the reference's vtkPolyData.
+"""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..io_obj import Mesh, load_obj
+
+__all__ = ["ObjRenderer3D", "ObjVTKRenderer3D", "fixed_eight_views", "rotation_matrices"]
+
+
+def fixed_eight_views() -> np.ndarray:
+    """The n_views == 8 preset (render3d.py:93-111): (+-30, +-15/+-45, 0), float32."""
+    return np.array([[30, 15, 0, 0, 0, 0], [30, -15, 0, 0, 0, 0], [30, 45, 0, 0, 0, 0], [30, -45, 0, 0, 0, 0],
+                     [-30, 15, 0, 0, 0, 0], [-30, -15, 0, 0, 0, 0], [-30, 45, 0, 0, 0, 0], [-30, -45, 0, 0, 0, 0]],
+                    dtype=np.float32)
+
+
+def _rx(a):
+    return np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+
+
+def _ry(a):
+    return np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+
+
+def _rz(a):
+    return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+
+
+def rotation_matrices(transform_stack: np.ndarray) -> np.ndarray:
+    """(V,>=3) [rx, ry, rz] in degrees -> (V,3,3) float64, R = Ry @ Rx @ Rz.
+
+    This is both the renderer's vertex transform (vtkTransform RotateY, RotateX, RotateZ,
+    render3d.py:140-145) and the estimator's ray rotation (estimator3d.py:57).  Angles keep the dtype
+    of `transform_stack` while np.deg2rad / np.cos / np.sin are evaluated, as in the reference.
+    """
+    out = np.empty((transform_stack.shape[0], 3, 3), dtype=np.float64)
+    for i in range(transform_stack.shape[0]):
+        rx, ry, rz = transform_stack[i, :3]
+        out[i] = (_ry(np.deg2rad(ry)) @ _rx(np.deg2rad(rx))) @ _rz(np.deg2rad(rz))
+    return out
+
+
+class DeviceMesh:
+    """Device-resident copy of a Mesh (uploaded once per scan)."""
+
+    def __init__(self, mesh: Mesh, device: torch.device):
+        self.mesh = mesh
+        self.verts = torch.from_numpy(mesh.verts).to(device)
+        self.tris = torch.from_numpy(mesh.tris).to(device)
+        self.uvs = torch.from_numpy(mesh.uvs).to(device) if mesh.uvs is not None else None
+        self.tex = torch.from_numpy(mesh.texture).to(device) if mesh.texture is not None else None
+
+    @property
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.verts, self.tris, self.uvs, self.tex) if t is not None)
+
+
+class ObjRenderer3D:
+    def __init__(self, n_views: int = 8, image_size: tuple = (256, 256), offscreen: bool = True,
+                 min_x_angle: int = -40, max_x_angle: int = 40, min_y_angle: int = -80, max_y_angle: int = 80,
+                 min_z_angle: int = -20, max_z_angle: int = 20, min_scale: float = 1.4, max_scale: float = 1.9,
+                 min_tx: int = -20, max_tx: int = 20, min_ty: int = -20, max_ty: int = 20,
+                 channel_mode: str = "RGB+depth", device: str = "cuda"):
+        self.n_views = n_views
+        self.image_size = image_size
+        self.offscreen = offscreen  # kept for signature compatibility; there is no window
+        self.min_x_angle, self.max_x_angle = min_x_angle, max_x_angle
+        self.min_y_angle, self.max_y_angle = min_y_angle, max_y_angle
+        self.min_z_angle, self.max_z_angle = min_z_angle, max_z_angle
+        self.min_scale, self.max_scale = min_scale, max_scale
+        self.min_tx, self.max_tx = min_tx, max_tx
+        self.min_ty, self.max_ty = min_ty, max_ty
+        self.channel_mode = channel_mode
+        self.device = torch.device(device)
+        self.slack = 5
+        self.side_length = max([150 - (-150), 150 - (-150)]) * 1.0 / 2
+        # injected view list (tests / benchmarks); None -> generate like the reference
+        self.transforms: np.ndarray | None = None
+        self.verbose = True
+
+    # render3d.py:79-89 (GLOBAL np.random, same draw order)
+    def random_transform(self, size=1):
+        rx = np.random.randint(self.min_x_angle, self.max_x_angle, size=size)
+        ry = np.random.randint(self.min_y_angle, self.max_y_angle, size=size)
+        rz = np.random.randint(self.min_z_angle, self.max_z_angle, size=size)
+        scale = np.random.uniform(self.min_scale, self.max_scale, size=size)
+        tx = np.random.randint(self.min_tx, self.max_tx, size=size)
+        ty = np.random.randint(self.min_ty, self.max_ty, size=size)
+        return np.stack((rx, ry, rz, scale, tx, ty), axis=1)
+
+    # render3d.py:92-112
+    def generate_3d_transformations(self):
+        if self.transforms is not None:
+            return np.asarray(self.transforms)
+        if self.n_views == 8:
+            return fixed_eight_views()
+        return self.random_transform(size=self.n_views)
+
+    def upload(self, mesh: Mesh) -> DeviceMesh:
+        return DeviceMesh(mesh, self.device)
+
+    def render_device(self, dmesh: DeviceMesh, transform_stack: np.ndarray, want_f32=False, want_tri=False, want_z=False):
+        """All views in one launch pair; returns the dict of device tensors of ops.raster_multiview."""
+        rot = torch.from_numpy(rotation_matrices(transform_stack).reshape(-1, 9)).to(self.device)
+        h, w = self.image_size[0], self.image_size[1]
+        return ops.raster_multiview(dmesh.verts, dmesh.uvs, dmesh.tris, dmesh.tex, rot, h, w, self.channel_mode,
+                                    want_f32=want_f32, want_tri=want_tri, want_z=want_z)
+
+    # render3d.py:114-177
+    def render_3d_multi_rgb_geometry_depth(self, transform_stack, file_name):
+        tt = time.time()
+        mesh = file_name if isinstance(file_name, Mesh) else load_obj(file_name)
+        dmesh = self.upload(mesh)
+        if self.verbose:
+            print("Render [1] - Setup time: ", f"{time.time() - tt:08.6f} s")
+        tt = time.time()
+        out = self.render_device(dmesh, np.asarray(transform_stack), want_f32=True)
+        image_stack = out["f32"].cpu().numpy()
+        if self.verbose:
+            print("Render [2] - Render", f"{time.time() - tt:08.6f} s")
+        return image_stack, mesh
+
+    # render3d.py:179-193
+    def multiview_render(self, file_name: Path):
+        t = time.time()
+        file_name = Path(file_name)
+        if not file_name.exists():
+            raise FileNotFoundError(f"File {file_name} does not exist")
+        if not file_name.is_file():
+            raise FileNotFoundError(f"File {file_name} is not a file")
+        if not file_name.suffix == ".obj":
+            raise ValueError(f"File {file_name} is not an .obj file. Only .obj files are supported.")
+        if self.verbose:
+            print("Render [0] - Prepare", f"{time.time() - t:08.6f} s")
+        transformation_stack = self.generate_3d_transformations()
+        image_stack, mesh = self.render_3d_multi_rgb_geometry_depth(transformation_stack, file_name)
+        # the kernel already writes u8/255 in float32 (render3d.py:191)
+        return image_stack, transformation_stack, mesh
+
+
+# drop-in name of the reference class
+ObjVTKRenderer3D = ObjRenderer3D
