@@ -129,8 +129,11 @@ class HourglassOracle:
             ll2 = self.act(self.conv(h2, "conv9"), "bn3")
             x10 = self.q(self.conv(ll2, "conv10"))
             inter["x10"] = x10
-            up = F.interpolate(x10, scale_factor=2, mode="nearest")
-            hm = self.conv(up, "conv11")
+            if self.emulate:
+                hm = self._conv11_phases(x10)
+            else:
+                up = F.interpolate(x10, scale_factor=2, mode="nearest")
+                hm = self.conv(up, "conv11")
             if return_intermediates:
                 return hm, inter
             return hm
@@ -156,3 +159,22 @@ class HourglassOracle:
         o3 = self.conv(a2, f"{p}.conv3")
         y3 = self.q(o3 + skip[:, c2:])
         return torch.cat((y1, y2, y3), 1), None
+
+    def _conv11_phases(self, x10):
+        """conv3x3(nearest_up2(x)) as four 2x2 phase convolutions at low resolution, the taps that
+        read the same low-res pixel summed in fp32 and THEN rounded to bf16 (what the CUDA plan does;
+        mathematically identical to :428-429, differs only in where the weight rounding happens)."""
+        w = self.sd["conv11.weight"]
+        b = self.sd["conv11.bias"]
+        n, _, h, wd = x10.shape
+        out = torch.empty((n, w.shape[0], 2 * h, 2 * wd))
+        for a in range(2):
+            wr = torch.stack([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], 2) if a == 0 else \
+                torch.stack([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], 2)
+            for c in range(2):
+                wc = torch.stack([wr[..., 0], wr[..., 1] + wr[..., 2]], 3) if c == 0 else \
+                    torch.stack([wr[..., 0] + wr[..., 1], wr[..., 2]], 3)
+                # tap (ky,kx) reads input (y + a - 1 + ky, x + c - 1 + kx)
+                xp = F.pad(x10, (1 - c, c, 1 - a, a))
+                out[:, :, a::2, c::2] = F.conv2d(xp, self.q(wc), b)
+        return out
