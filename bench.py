@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--grid", type=int, default=224, help="mesh grid (224 -> 50 176 vertices / 99 458 triangles)")
     ap.add_argument("--hyp", type=int, default=1, help="RANSAC hypotheses per landmark (reference: 1)")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true", help="ncu mode: exact --warmup, no e2e / cpu legs")
     return ap.parse_args()
 
 
@@ -56,43 +57,54 @@ def peaks_file():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """Streams nvidia-smi clocks / throttle reasons (100 ms period) during the timed region."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self._stop = threading.Event()
+        self.proc = None
 
-    def run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        samples = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+                out = ""
+            samples = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+
+        sm = [num(s[0]) for s in samples if num(s[0]) is not None]
+        mx = [num(s[1]) for s in samples if len(s) > 1 and num(s[1]) is not None]
+        pw = [num(s[2]) for s in samples if len(s) > 2 and num(s[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s_ in samples:
             for k, n in enumerate(names):
-                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                if len(s_) > 3 + k and s_[3 + k].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(samples)}
 
 
 def make_scan(args):
@@ -245,7 +257,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if args.profile else max(args.warmup, 3)
+    for _ in range(n_warm):
         device_step()
     barrier()
     sampler = ClockSampler(local)
@@ -284,18 +297,18 @@ def run_ours(args):
     hmesh = Mesh(verts=pin(mesh.verts), tris=pin(mesh.tris), uvs=pin(mesh.uvs), texture=pin(mesh.texture))
     h2d = sum(a.nbytes for a in (hmesh.verts, hmesh.tris, hmesh.uvs, hmesh.texture)) + rot.numel() * 8 + draws.numel() * 4
     d2h = N_LANDMARKS * 3 * 8 + 8
-    for _ in range(2):
+    for _ in range(0 if args.profile else 2):
         dm.predict_mesh(hmesh)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(1 if args.profile else args.steps):
         res = dm.predict_mesh(hmesh)  # ends with a device -> host copy of the landmarks (synchronises)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / float(te.item())
+    e2e_value = world * (1 if args.profile else args.steps) / float(te.item())
     assert res.shape == (N_LANDMARKS, 3) and np.isfinite(res).all()
 
     if rank == 0:
@@ -305,7 +318,7 @@ def run_ours(args):
         peak = pk["bf16_tflops_sustained"]
         line = {
             "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": n_warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, one scan per step per GPU",
                        "n_landmarks": N_LANDMARKS, "ransac_hypotheses": args.hyp, "weights": "seeded random init",
@@ -319,7 +332,7 @@ def run_ours(args):
                          "peak_source": f"{pk_kind} bf16_tflops_sustained", "flops_per_scan": flops_scan},
             "clocks": clocks,
         }
-        if not args.skip_cpu:
+        if not args.skip_cpu and not args.profile:
             try:
                 sec, parts, cores = cpu_path_seconds_per_scan(args, mesh, 4)
                 line["cpu_baseline"] = {
