@@ -1,0 +1,125 @@
+"""CPU: C-ABI library loads and exports every declared symbol; host-side logic without a GPU."""
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from mvlm_b200 import synth
+from mvlm_b200.io_obj import load_obj
+from oracle import stages
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = (ROOT / "include" / "mvlm_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(mvlm_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/mvlm_b200.h but not exported"
+    assert lib.mvlm_version() >= 1
+    assert lib.mvlm_last_error() is not None
+    # size queries are pure host functions (no compute)
+    assert lib.mvlm_raster_workspace_bytes(100, 256, 256) == 100 * 256 * 256 * 8
+    assert lib.mvlm_hourglass_workspace_bytes(73, 4, 100, 256, 256) > 10 * 2 ** 30
+    assert lib.mvlm_consensus_workspace_bytes(84, 200, 16384) > 0
+    assert lib.mvlm_snap_workspace_bytes(73, 100000) > 0
+    assert lib.mvlm_hourglass_workspace_bytes(73, 4, 1, 100, 100) == 0  # not a multiple of 64 -> error
+    assert b"multiple of 64" in lib.mvlm_last_error()
+
+
+def test_hourglass_flops_match_survey(lib):
+    """Algorithmic FLOPs/view of the planned network == SURVEY.md 8(d) (reference census minus conv8)."""
+    for (l, cin), want in {(73, 4): 146.106, (73, 3): 146.031, (84, 4): 150.635, (84, 2): 150.484}.items():
+        assert abs(lib.mvlm_hourglass_flops_per_view(l, cin, 256, 256) / 1e9 - want) < 1.5e-3
+    assert abs(lib.mvlm_hourglass_flops_per_view(73, 4, 512, 512) / lib.mvlm_hourglass_flops_per_view(73, 4, 256, 256) - 4) < 1e-9
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the CPU oracle."""
+    for p in (ROOT / "mvlm_b200").rglob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, p
+    for p in (ROOT / "mvlm_b200" / "csrc").glob("*"):
+        assert "oracle_native" not in p.read_text().replace("oracle/csrc/oracle_native.c", ""), p
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from mvlm_b200 import _lib\n"
+            "from pathlib import Path\n"
+            "_lib.LIB_PATH = Path(%r) / 'nope.so'\n"
+            "try:\n    _lib.load()\nexcept _lib.MvlmError as e:\n    print('LOUD', e)\n") % (str(ROOT), str(tmp_path))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout
+    assert "LOUD" in out and "no CPU fallback" in out
+
+
+def test_rotation_and_views_match_oracle():
+    from mvlm_b200.utils.render3d import ObjRenderer3D, fixed_eight_views, rotation_matrices
+
+    for tr in (fixed_eight_views(), synth.random_view_transforms(9, seed=3)):
+        assert np.array_equal(rotation_matrices(tr), stages.rotation_matrices(tr))
+    r = ObjRenderer3D.__new__(ObjRenderer3D)
+    r.__dict__.update(n_views=8, transforms=None)
+    assert r.generate_3d_transformations().dtype == np.float32
+    r2 = ObjRenderer3D(n_views=5, device="cpu")
+    np.random.seed(4)
+    a = r2.generate_3d_transformations()
+    assert a.shape == (5, 6) and a.dtype == np.float64
+    assert np.array_equal(a, synth.random_view_transforms(5, seed=4))   # same draw order as render3d.py:79-89
+    assert (a[:, 0] >= -40).all() and (a[:, 0] < 40).all() and (a[:, 1] >= -80).all() and (a[:, 2] < 20).all()
+
+
+def test_obj_roundtrip_and_vertex_duplication(tmp_path):
+    v, uv, t = synth.face_mesh(grid=12, seed=0)
+    synth.write_obj(tmp_path / "a.obj", v, uv, t, synth.face_texture(32, 0))
+    m = load_obj(tmp_path / "a.obj")
+    assert m.verts.shape == v.shape and m.tris.shape == t.shape and m.texture.shape == (32, 32, 3)
+    assert np.allclose(m.verts[m.tris], v[t], atol=1e-5) and np.allclose(m.uvs[m.tris], uv[t], atol=1e-5)
+    # a position used with two different vt indices is duplicated (vtkOBJReader behaviour); quads are fanned
+    (tmp_path / "b.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvt 0.5 0.5\n"
+                                    "f 1/1 2/2 3/3 4/4\nf 1/5 3/3 2/2\n")
+    m = load_obj(tmp_path / "b.obj")
+    assert m.tris.shape == (3, 3) and m.verts.shape[0] == 5
+    (tmp_path / "c.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\nf -3 -2 -1\n")
+    m = load_obj(tmp_path / "c.obj")
+    assert m.uvs is None and m.tris.tolist() == [[0, 1, 2], [0, 1, 2]]
+    (tmp_path / "d.obj").write_text("# empty\n")
+    with pytest.raises(ValueError, match="does not contain any points"):
+        load_obj(tmp_path / "d.obj")
+
+
+def test_create_pipeline_name_handling():
+    import mvlm
+
+    with pytest.raises(ValueError, match="Unknown pipeline: nope"):
+        mvlm.pipeline.create_pipeline("NoPe")
+    with pytest.raises(ValueError, match="Unknown pipeline"):
+        mvlm.pipeline.create_pipeline("mediapipe")
+    assert mvlm.pipeline is sys.modules["mvlm.pipeline"]
+    from mvlm.prediction import BU3DFEPredictor, DTU3DPredictor, Predictor2D  # noqa: F401
+    from mvlm.utils import Estimator3D, ObjVTKRenderer3D  # noqa: F401
+
+
+def test_estimator_reference_draws_replay_global_rng():
+    from mvlm_b200.utils.estimator3d import Estimator3D
+
+    peaks, _, _, _ = synth.synthetic_rays(n_landmarks=5, n_views=20, seed=1)
+    peaks[3, :, 2] = 0.3  # all equal -> no lines -> no draw consumed
+    e = Estimator3D(device="cpu")
+    np.random.seed(11)
+    d = e.reference_draws(peaks)
+    np.random.seed(11)
+    for lm in range(5):
+        n = int(stages.line_filter_mask(peaks[lm, :, 2], "quantile", 0.5, 0.5).sum())
+        if n >= 3:
+            assert np.array_equal(d[lm, 0], np.random.choice(range(n), 8, replace=True))
+        else:
+            assert (d[lm] == 0).all()
+    e.mode = "bogus"
+    with pytest.raises(ValueError, match="Unknown mode for line matching"):
+        e.reference_draws(peaks)

@@ -1,0 +1,145 @@
+"""CPU: pins the oracle (oracle/) against golden vectors produced by the REFERENCE's own code
+(tools/make_golden.py, run in the build container where /root/reference is importable).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from mvlm_b200 import synth
+from mvlm_b200.weights import IMAGE_CHANNELS, schema, seeded_state_dict
+from oracle import native, stages
+from oracle.hourglass_ref import HourglassOracle
+
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.mark.parametrize("tag", ["dtu3d_rgbd_64", "bu3dfe_geod_64"])
+def test_cnn_oracle_matches_reference_model(tag):
+    g = np.load(GOLD / f"cnn_{tag}.npz")
+    n_lm, mode, seed = int(g["n_landmarks"]), str(g["mode"]), int(g["seed"])
+    sd = seeded_state_dict(n_lm, mode, seed)
+    x = (torch.from_numpy(g["img_u8"]).float() / 255.0).permute(0, 3, 1, 2).contiguous()
+    assert x.shape[1] == IMAGE_CHANNELS[mode]
+    hm = HourglassOracle(sd).forward(x).numpy()
+    sub = hm[:, g["channels"]]
+    assert np.abs(sub - g["heatmaps_subset"]).max() <= 2e-4 * float(g["std"])   # fp32 reassociation only
+    flat = hm.reshape(hm.shape[0], hm.shape[1], -1)
+    assert np.abs(flat.max(-1) - g["maxval"]).max() <= 2e-4 * float(g["std"])
+    assert np.abs(hm.mean((2, 3)) - g["mean"]).max() <= 2e-4 * float(g["std"])
+    assert (flat.argmax(-1) == g["argmax"]).mean() >= 0.99  # near-ties may flip under reassociation
+
+
+def test_state_dict_schema():
+    sd = seeded_state_dict(73, "RGB+depth", 1)
+    assert len(sd) == 817
+    assert sum(v.numel() for k, v in sd.items() if v.is_floating_point() and "running" not in k) == 18_507_414
+    assert len(schema(84, "RGB+depth")) == 817
+    assert sd["conv4.resample.2.weight"].shape == (256, 128, 1, 1)
+    assert sd["hg2.rb20.conv3.weight"].shape == (64, 64, 3, 3)
+    sd2 = seeded_state_dict(73, "RGB+depth", 1)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)   # deterministic
+
+
+def test_peaks_oracle_matches_reference():
+    g = np.load(GOLD / "stages.npz")
+    a = stages.heatmap_peaks(g["heatmaps"], "simple")
+    assert np.array_equal(a, g["peaks_simple"])
+    b = stages.heatmap_peaks(g["heatmaps_nan"], "simple")
+    assert np.array_equal(b[..., :2], g["peaks_simple_nan"][..., :2])
+    assert np.array_equal(np.isnan(b[..., 2]), np.isnan(g["peaks_simple_nan"][..., 2]))
+    c = stages.heatmap_peaks(g["heatmaps"], "moment")
+    assert np.array_equal(c, g["peaks_moment"])
+    assert tuple(a[0, 0, :2]) == (-1.0, -0.5)          # all-equal map -> index 0
+    assert tuple(a[1, 0, :2]) == (9.0, 4.5)            # tie -> first in row-major order
+
+
+@pytest.mark.parametrize("kind", ["f64", "f32"])
+def test_rays_oracle_matches_reference(kind):
+    g = np.load(GOLD / "stages.npz")
+    s, e = stages.landmark_lines(256, g[f"rays_{kind}_peaks"], g[f"rays_{kind}_tr"])
+    assert np.abs(s - g[f"rays_{kind}_starts"]).max() <= 1e-10
+    assert np.abs(e - g[f"rays_{kind}_ends"]).max() <= 1e-10
+
+
+def test_lsq_and_ransac_oracle_match_reference():
+    g = np.load(GOLD / "stages.npz")
+    assert np.array_equal(stages.lsq_intersection(g["lsq_pa"], g["lsq_pb"]), g["lsq_out"])
+    same = np.repeat(g["lsq_pa"][:1], 8, 0), np.repeat(g["lsq_pb"][:1], 8, 0)
+    assert np.allclose(stages.lsq_intersection(*same), g["lsq_degenerate_out"], atol=1e-9)
+    starts, ends, draws = g["ransac_starts"], g["ransac_ends"], g["ransac_draws"]
+    for lm in range(starts.shape[0]):
+        p, err = stages.ransac_intersection(starts[lm], ends[lm], stages.hypotheses_for(draws[lm], starts.shape[1]))
+        assert np.abs(p - g["ransac_points"][lm]).max() <= 1e-10
+        assert abs(err - g["ransac_errors"][lm]) <= 1e-10 * max(1.0, abs(g["ransac_errors"][lm]))
+
+
+@pytest.mark.parametrize("mode", ["quantile", "absolute"])
+def test_estimate_landmarks_from_lines_replays_reference_rng(mode):
+    """H = 1 with the reference's own np.random.choice draws (seeded global RNG) == reference output."""
+    g = np.load(GOLD / "stages.npz")
+    peaks, starts, ends = g["efl_peaks"], g["ransac_starts"], g["ransac_ends"]
+    np.random.seed(123)
+    draws = np.zeros((peaks.shape[0], 1, 8), np.uint32)
+    for lm in range(peaks.shape[0]):
+        n = int(stages.line_filter_mask(peaks[lm, :, 2], mode, 0.5, 0.5).sum())
+        if n >= 3:
+            draws[lm, 0] = np.random.choice(range(n), 8, replace=True)
+    lm_out, err, _ = stages.landmarks_from_lines(peaks, starts, ends, draws, mode=mode)
+    assert np.abs(lm_out - g[f"efl_{mode}_landmarks"]).max() <= 1e-10
+    assert abs(err - float(g[f"efl_{mode}_error"])) <= 1e-9 * max(1.0, abs(float(g[f"efl_{mode}_error"])))
+
+
+# ---------------------------------------------------------------- closed-form properties of the VTK restatements
+def test_raster_oracle_properties():
+    verts, uvs, tris = synth.face_mesh(grid=60, seed=4)
+    tex = synth.face_texture(128, seed=4)
+    rot = stages.rotation_matrices(np.zeros((1, 6)))
+    img, tri, z = native.raster_multiview(verts, uvs, tris, tex, rot, 128, 128)
+    assert img.dtype == np.float32 and img.shape == (1, 128, 128, 4)
+    bg = tri < 0
+    assert (img[bg][:, :3] == 1.0).all() and (img[bg][:, 3] == np.float32(1 / 255)).all() and (z[bg] == 1.0).all()
+    fg = ~bg
+    assert 0.2 < fg.mean() < 0.8
+    # depth byte = (256 - trunc(255 z)) mod 256 / 255, closer = larger  (render3d.py:73-77)
+    d8 = np.rint(img[..., 3] * 255).astype(int)
+    assert np.array_equal(d8[fg], (256 - np.trunc(255.0 * z[fg]).astype(int)) % 256)
+    # the frontal silhouette is the projected bounding box: 90/110 mm half extents at 128/300 px per mm
+    ys, xs = np.nonzero(fg[0])
+    sx = (verts[:, 0].max() - verts[:, 0].min()) * 128 / 300
+    assert abs((xs.max() - xs.min() + 1) - sx) <= 1.5
+    # every drawn pixel centre lies inside its winning triangle's projection (barycentric check, fp64)
+    k = 128 / 300.0
+    px = (verts[:, 0] + 150) * k
+    py = (150 - verts[:, 1]) * k
+    for y, x in list(zip(ys, xs))[::97]:
+        t = tris[tri[0, y, x]]
+        ax, ay, bx, by, cx, cy = px[t[0]], py[t[0]], px[t[1]], py[t[1]], px[t[2]], py[t[2]]
+        det = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax)
+        l1 = ((x + 0.5 - ax) * (cy - ay) - (y + 0.5 - ay) * (cx - ax)) / det
+        l2 = ((bx - ax) * (y + 0.5 - ay) - (by - ay) * (x + 0.5 - ax)) / det
+        assert l1 >= -1e-4 and l2 >= -1e-4 and l1 + l2 <= 1 + 1e-4
+    # rotating the view by rz=90 rotates the image content: same number of covered pixels
+    rot90 = stages.rotation_matrices(np.array([[0, 0, 90.0, 0, 0, 0]]))
+    _, tri90, _ = native.raster_multiview(verts, uvs, tris, tex, rot90, 128, 128)
+    assert abs(int((tri90 >= 0).sum()) - int(fg.sum())) <= 0.02 * fg.sum()
+
+
+def test_snap_oracle_properties():
+    verts, _, tris = synth.face_mesh(grid=30, seed=1)
+    rng = np.random.RandomState(0)
+    # points on the surface (random barycentric combos) snap to themselves
+    t = tris[rng.randint(0, len(tris), 50)]
+    w = rng.dirichlet([1, 1, 1], 50)
+    on = (verts[t].astype(np.float64) * w[:, :, None]).sum(1)
+    out, _ = native.snap_to_mesh(verts, tris, on)
+    assert np.abs(out - on).max() <= 1e-9
+    # brute-force check against dense sampling of the closest triangle for off-surface points
+    p = rng.uniform(-120, 120, (20, 3))
+    out, tid = native.snap_to_mesh(verts, tris, p)
+    d = np.linalg.norm(out - p, axis=1)
+    dv = np.linalg.norm(verts[None].astype(np.float64) - p[:, None], axis=2).min(1)
+    assert (d <= dv + 1e-9).all()             # at least as close as the closest vertex
+    out2, _ = native.snap_to_mesh(verts, tris, out)
+    assert np.abs(out2 - out).max() <= 1e-9   # idempotent
