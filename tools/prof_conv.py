@@ -1,0 +1,24 @@
+"""Runs a few launches of one conv shape (for `ncu --set full -k regex:conv_umma`).  GPU box only.
+usage: python tools/prof_conv.py H CIN COUT NTILE [V]"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from mvlm_b200 import build, ops  # noqa: E402
+
+build.build()
+h, cin, cout, nt = (int(x) for x in sys.argv[1:5])
+v = int(sys.argv[5]) if len(sys.argv) > 5 else 100
+x = torch.randn((v, h, h, cin), device="cuda").to(torch.bfloat16)
+w = torch.randn((cout, cin, 3, 3), device="cuda") / (cin * 9) ** 0.5
+wp = ops.pack_conv_weight(w, cout, cin)
+big = torch.zeros((v, h, h, 256), device="cuda", dtype=torch.bfloat16)
+act = torch.zeros((v, h, h, max(cout, 64)), device="cuda", dtype=torch.bfloat16)
+s = torch.ones(cout, device="cuda")
+t = torch.zeros(cout, device="cuda")
+for _ in range(3):
+    ops.conv2d_bf16(x, wp, n_tile=nt, pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
+torch.cuda.synchronize()
+print("ok")
