@@ -66,6 +66,14 @@ typedef struct mvlm_conv_args {
 
 int mvlm_conv2d_bf16(const mvlm_conv_args* args, void* stream);
 
+/* Debug aid: when dev_buf (148*8 int64, device) is non-NULL the following conv launches record per-CTA role
+ * stall cycles there: [0] producer wait A-empty, [1] producer wait B-empty, [2] MMA wait operands,
+ * [3] MMA wait accumulator-free, [4] MMA total, [5] epilogue wait accumulator-full, [6] epilogue total,
+ * [7] producer total.  NULL switches it off. */
+void mvlm_debug_conv_profile(long long* dev_buf);
+/* Debug experiment switch: 1 = tensor-pipe-only timing (no TMA loads; outputs are garbage), 0 = normal. */
+void mvlm_debug_conv_mode(int mode);
+
 /* fp32 OIHW (device) -> packed bf16 [cout_pad][kw][kh][cin_pad] (device), zero padded. */
 int mvlm_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cout_pad,
                           int cin_pad, void* out_bf16, void* stream);

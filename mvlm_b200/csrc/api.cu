@@ -54,6 +54,9 @@ long long mvlm_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+void mvlm_debug_conv_profile(long long* dev_buf) { conv_set_profile_buffer(dev_buf); }
+void mvlm_debug_conv_mode(int mode) { conv_set_debug_mode(mode); }
+
 int mvlm_conv2d_bf16(const mvlm_conv_args* a, void* stream) {
   MVLM_REQUIRE(a != nullptr, "mvlm_conv2d_bf16: null args");
   ConvShape s;

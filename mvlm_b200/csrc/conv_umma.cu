@@ -38,7 +38,7 @@ struct Cfg {
   static constexpr int kBSlotBytes = N_TILE * 128;
   static constexpr int kBSlots = (N_TILE >= 128) ? 6 : 8;
   static constexpr int kSmemBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes + 1024 /*align*/ +
-                                    256 /*barriers*/;
+                                    256 /*barriers*/ + 5 * 256 * 4 /*EpiParams*/;
   static_assert(kSmemBytes <= kSmemBudget, "shared memory budget");
   static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 128, "UMMA N");
 };
@@ -100,7 +100,35 @@ __device__ __forceinline__ void add16(const __nv_bfloat16* src, float (&f)[16]) 
   }
 }
 
-template <int N_TILE>
+// Per-output-channel epilogue parameters staged once per CTA in shared memory (LDS broadcast instead of
+// 80 global loads per 16-channel step): bias, pre scale/shift, post scale/shift for all N tiles.
+constexpr int kMaxCout = 256;
+struct EpiParams {
+  float bias[kMaxCout];
+  float pre_s[kMaxCout];
+  float pre_t[kMaxCout];
+  float post_s[kMaxCout];
+  float post_t[kMaxCout];
+};
+
+__device__ __forceinline__ void lds16(const float* src, float (&v)[16]) {
+  const float4* p = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 q = p[j];
+    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+  }
+}
+
+// role timing: wait on an mbarrier and add the stalled cycles to `acc` when profiling is on
+__device__ __forceinline__ void timed_wait(uint64_t* b, uint32_t parity, bool prof, long long& acc) {
+  if (!prof) { ptx::mbar_wait(b, parity); return; }
+  const long long t0 = clock64();
+  ptx::mbar_wait(b, parity);
+  acc += clock64() - t0;
+}
+
+template <int N_TILE, bool ARGMAX>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
   using C = Cfg<N_TILE>;
   extern __shared__ uint8_t smem_raw[];
@@ -111,15 +139,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   uint8_t* a_slots = smem;
   uint8_t* b_slots = smem + kASlots * kASlotBytes;
   Barriers* bar = reinterpret_cast<Barriers*>(b_slots + C::kBSlots * C::kBSlotBytes);
+  EpiParams* ep = reinterpret_cast<EpiParams*>(reinterpret_cast<uint8_t*>(bar) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const ConvShape& s = p.s;
+  const ConvEpilogue& e = p.e;
   const int n_chunks = (s.cin + 63) >> 6;
   const int halo_rows = kTileH + s.kh - 1;
   const uint32_t a_bytes = static_cast<uint32_t>(halo_rows) * kARowBytes;
 
+  // Tile schedule shared by the three roles.  Default: round-robin (neighbouring CTAs work on
+  // neighbouring tiles -> halo / weight reuse in L2).  ARGMAX: contiguous ranges, so that a CTA stays
+  // within one image for ~40 tiles and keeps its running arg-max in registers.
+  int t_begin, t_end, t_step;
+  if (ARGMAX) {
+    const int per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+    t_begin = blockIdx.x * per;
+    t_end = min(p.total_tiles, t_begin + per);
+    t_step = 1;
+  } else {
+    t_begin = blockIdx.x; t_end = p.total_tiles; t_step = gridDim.x;
+  }
+
+  for (int i = threadIdx.x; i < s.cout_pad; i += kThreads) {
+    ep->bias[i] = e.bias ? e.bias[i] : 0.f;
+    ep->pre_s[i] = e.out_pre ? e.pre_scale[i] : 0.f;
+    ep->pre_t[i] = e.out_pre ? e.pre_shift[i] : 0.f;
+    ep->post_s[i] = e.out_post ? e.post_scale[i] : 0.f;
+    ep->post_t[i] = e.out_post ? e.post_shift[i] : 0.f;
+  }
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&p.tm_a);
     ptx::tma_prefetch_desc(&p.tm_b);
@@ -145,13 +195,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bar->tmem_base;
+  const bool prof = p.prof != nullptr;
+  const long long t_kernel0 = clock64();
+  long long w0 = 0, w1 = 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (ptx::elect_one() && p.debug_mode != 1) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; t += t_step) {
         const int nt = t % p.n_nt;
         int r = t / p.n_nt;
         const int tx = r % p.tiles_x;
@@ -162,13 +215,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int y0 = ty * kTileH + s.y_off0;
         for (int c = 0; c < n_chunks; ++c) {
           for (int kx = 0; kx < s.kw; ++kx) {
-            ptx::mbar_wait(&bar->a_empty[sa], pa ^ 1);
+            timed_wait(&bar->a_empty[sa], pa ^ 1, prof, w0);
             ptx::mbar_expect_tx(&bar->a_full[sa], a_bytes);
             ptx::tma_load_4d(&p.tm_a, &bar->a_full[sa], a_slots + sa * kASlotBytes, c * 64, x0 + kx,
                              y0, img);
             if (++sa == kASlots) { sa = 0; pa ^= 1; }
             for (int ky = 0; ky < s.kh; ++ky) {
-              ptx::mbar_wait(&bar->b_empty[sb], pb ^ 1);
+              timed_wait(&bar->b_empty[sb], pb ^ 1, prof, w1);
               ptx::mbar_expect_tx(&bar->b_full[sb], C::kBSlotBytes);
               ptx::tma_load_2d(&p.tm_b, &bar->b_full[sb], b_slots + sb * C::kBSlotBytes,
                                (kx * s.kh + ky) * s.cin + c * 64, nt * N_TILE);
@@ -177,17 +230,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           }
         }
       }
+      if (prof) { p.prof[blockIdx.x * 8 + 0] = w0; p.prof[blockIdx.x * 8 + 1] = w1; p.prof[blockIdx.x * 8 + 7] = clock64() - t_kernel0; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): the compiler then knows a single lane is active and emits the
+    // UTCHMMA / UTCBAR uniform-datapath instructions without a per-lane serialisation loop.
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, N_TILE);
+      // descriptor = {lo: start>>4 | LBO, hi: SBO | version | SWIZZLE_128B}; only lo changes per MMA
+      constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t pacc = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        ptx::mbar_wait(&bar->t_empty[acc], pacc ^ 1);
+      for (int t = t_begin; t < t_end; t += t_step) {
+        const int ty = (t / p.n_nt / p.tiles_x) % p.tiles_y;
+        // maps of height <= 8 (hourglass levels 8^2 .. 1^2) only populate the first 128-row sub-tile
+        const int n_sub = (ty * kTileH + 8 < s.h) ? 2 : 1;
+        timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
         ptx::tc_fence_after();
         const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * 2 * N_TILE);
         uint32_t accumulate = 0;
@@ -195,36 +256,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const int rem = s.cin - c * 64;
           const int nk = rem >= 64 ? 4 : (rem >> 4);
           for (int kx = 0; kx < s.kw; ++kx) {
-            ptx::mbar_wait(&bar->a_full[sa], pa);
-            const uint32_t a_addr = ptx::smem_u32(a_slots + sa * kASlotBytes);
+            if (p.debug_mode != 1) timed_wait(&bar->a_full[sa], pa, prof, w0);
+            const uint32_t a_lo = ((ptx::smem_u32(a_slots + sa * kASlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
             for (int ky = 0; ky < s.kh; ++ky) {
-              ptx::mbar_wait(&bar->b_full[sb], pb);
+              if (p.debug_mode != 1) timed_wait(&bar->b_full[sb], pb, prof, w0);
               ptx::tc_fence_after();
-              const uint32_t b_addr = ptx::smem_u32(b_slots + sb * C::kBSlotBytes);
+              const uint32_t b_lo = ((ptx::smem_u32(b_slots + sb * C::kBSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
+              for (int sub = 0; sub < n_sub; ++sub) {
+                // vertical tap / sub-tile = whole image rows of the halo tile: (sub*8+ky) * 2048 B >> 4
+                const uint32_t a_sub = a_lo + static_cast<uint32_t>((sub * 8 + ky) * (kARowBytes >> 4));
+                const uint32_t d = d_base + sub * N_TILE;
+                if (nk == 4) {
 #pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
-                const uint32_t a_sub = a_addr + static_cast<uint32_t>((sub * 8 + ky) * kARowBytes);
-                for (int k = 0; k < nk; ++k) {
-                  ptx::umma_bf16(d_base + sub * N_TILE, ptx::umma_desc_sw128(a_sub + k * 32),
-                                 ptx::umma_desc_sw128(b_addr + k * 32), idesc,
-                                 (k == 0) ? accumulate : 1u);
+                  for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(d, (static_cast<uint64_t>(kDescHi) << 32) | (a_sub + 2 * k),
+                                   (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc,
+                                   (k == 0) ? accumulate : 1u);
+                } else {
+                  for (int k = 0; k < nk; ++k)
+                    ptx::umma_bf16(d, (static_cast<uint64_t>(kDescHi) << 32) | (a_sub + 2 * k),
+                                   (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc,
+                                   (k == 0) ? accumulate : 1u);
                 }
               }
               accumulate = 1;
-              ptx::umma_commit(&bar->b_empty[sb]);
+              if (p.debug_mode != 1) ptx::umma_commit(&bar->b_empty[sb]);
               if (++sb == C::kBSlots) { sb = 0; pb ^= 1; }
             }
-            ptx::umma_commit(&bar->a_empty[sa]);
+            if (p.debug_mode != 1) ptx::umma_commit(&bar->a_empty[sa]);
             if (++sa == kASlots) { sa = 0; pa ^= 1; }
           }
         }
         ptx::umma_commit(&bar->t_full[acc]);
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
+      if (prof) { p.prof[blockIdx.x * 8 + 2] = w0; p.prof[blockIdx.x * 8 + 3] = w1; p.prof[blockIdx.x * 8 + 4] = clock64() - t_kernel0; }
     }
   } else {
     // ===================== epilogue =====================
-    const ConvEpilogue& e = p.e;
     const int ew = warp - 2;
     const int lane_grp = warp & 3;  // TMEM lanes this warp may read: 32*(warp%4)..
     const int half = ew >> 2;
@@ -235,80 +304,123 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int m = lane_grp * 32 + lane;
     int acc = 0;
     uint32_t pacc = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    // ARGMAX: running (ordered value, ~index) per owned channel, kept across the tiles of one image
+    constexpr int kKeys = ARGMAX ? kHalf0 * 16 : 1;
+    uint32_t best_hi[kKeys], best_lo[kKeys];
+    int cur_img = -1;
+#pragma unroll
+    for (int i = 0; i < kKeys; ++i) { best_hi[i] = 0u; best_lo[i] = 0u; }
+    auto flush = [&](int img) {
+      if (!ARGMAX || img < 0) return;
+#pragma unroll
+      for (int ci = 0; ci < kHalf0; ++ci) {
+        const int ch = ch_begin + ci;
+        if (ch >= ch_end) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t hi = best_hi[ARGMAX ? ci * 16 + j : 0], lo = best_lo[ARGMAX ? ci * 16 + j : 0];
+          const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+          const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+          const int cidx = ch * 16 + j;  // N tile 0 only: arg-max convs have a single N tile
+          if (lane == 0 && cidx < e.cout_real && mhi != 0u)
+            atomicMax(e.argmax_keys + static_cast<size_t>(img) * e.cout_real + cidx,
+                      (static_cast<unsigned long long>(mhi) << 32) | mlo);
+          best_hi[ARGMAX ? ci * 16 + j : 0] = 0u;
+          best_lo[ARGMAX ? ci * 16 + j : 0] = 0u;
+        }
+      }
+    };
+    for (int t = t_begin; t < t_end; t += t_step) {
       const int nt = t % p.n_nt;
       int r = t / p.n_nt;
       const int tx = r % p.tiles_x;
       r /= p.tiles_x;
       const int ty = r % p.tiles_y;
       const int img = r / p.tiles_y;
-      ptx::mbar_wait(&bar->t_full[acc], pacc);
+      const int n_sub = (ty * kTileH + 8 < s.h) ? 2 : 1;
+      if (ARGMAX && img != cur_img) {
+        flush(cur_img);
+        cur_img = img;
+      }
+      timed_wait(&bar->t_full[acc], pacc, prof, w0);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
+      for (int sub = 0; sub < n_sub; ++sub) {
         const int y = ty * kTileH + sub * 8 + (m >> 4);
         const int x = tx * kTileW + (m & 15);
         const bool valid = (y < s.h) && (x < s.w);
         const size_t pix = (static_cast<size_t>(img) * s.h + y) * s.w + x;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                                static_cast<uint32_t>(acc * 2 * N_TILE + sub * N_TILE);
-#pragma unroll 1
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int oy = y * e.up_sy + e.up_py;
+        const int ox = x * e.up_sx + e.up_px;
+        const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
+#pragma unroll
+        for (int ci = 0; ci < kHalf0; ++ci) {
+          const int ch = ch_begin + ci;
+          if (ch >= ch_end) continue;
+          const int c0 = nt * N_TILE + ch * 16;
+          // residual loads first: their latency overlaps the TMEM load
+          uint4 r1[2], r2[2];
+          const bool has_r1 = e.res1 && valid, has_r2 = e.res2 && valid;
+          if (has_r1) {
+            const uint4* q = reinterpret_cast<const uint4*>(e.res1 + pix * e.res1_cs + e.res1_co + c0);
+            r1[0] = q[0]; r1[1] = q[1];
+          }
+          if (has_r2) {
+            const uint4* q = reinterpret_cast<const uint4*>(e.res2 + pix * e.res2_cs + e.res2_co + c0);
+            r2[0] = q[0]; r2[1] = q[1];
+          }
           uint32_t v[16];
           ptx::tmem_ld16(taddr + ch * 16, v);
+          float f[16], pb_[16];
+          lds16(ep->bias + c0, pb_);
           ptx::tmem_ld_wait();
-          const int c0 = nt * N_TILE + ch * 16;
-          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (e.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(e.bias + c0 + j);
-          }
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + pb_[j];
           if (e.out_pre && valid) {
-            float g[16];
+            float sc[16], sh[16], g[16];
+            lds16(ep->pre_s + c0, sc);
+            lds16(ep->pre_t + c0, sh);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              g[j] = fmaxf(fmaf(f[j], __ldg(e.pre_scale + c0 + j), __ldg(e.pre_shift + c0 + j)), 0.f);
+            for (int j = 0; j < 16; ++j) g[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
             store16(e.out_pre + pix * e.pre_cs + e.pre_co + c0, g);
           }
-          if (e.res1 && valid) add16(e.res1 + pix * e.res1_cs + e.res1_co + c0, f);
-          if (e.res2 && valid) add16(e.res2 + pix * e.res2_cs + e.res2_co + c0, f);
+          if (has_r1) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(r1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float2 q = __bfloat1622float2(h[j]); f[2 * j] += q.x; f[2 * j + 1] += q.y; }
+          }
+          if (has_r2) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(r2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float2 q = __bfloat1622float2(h[j]); f[2 * j] += q.x; f[2 * j + 1] += q.y; }
+          }
           if (e.out_raw && valid) store16(e.out_raw + pix * e.raw_cs + e.raw_co + c0, f);
           if (e.out_post && valid) {
-            float g[16];
+            float sc[16], sh[16], g[16];
+            lds16(ep->post_s + c0, sc);
+            lds16(ep->post_t + c0, sh);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              g[j] = fmaxf(fmaf(f[j], __ldg(e.post_scale + c0 + j), __ldg(e.post_shift + c0 + j)), 0.f);
+            for (int j = 0; j < 16; ++j) g[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
             store16(e.out_post + pix * e.post_cs + e.post_co + c0, g);
           }
-          if (e.out_f32 || e.argmax_keys) {
-            const int oy = y * e.up_sy + e.up_py;
-            const int ox = x * e.up_sx + e.up_px;
-            const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
-            if (e.out_f32 && valid) {
+          if (e.out_f32 && valid) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int c = c0 + j;
-                if (c < e.cout_real)
-                  e.out_f32[((static_cast<size_t>(img) * e.cout_real + c) * oh + oy) * ow + ox] = f[j];
-              }
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              if (c < e.cout_real)
+                e.out_f32[((static_cast<size_t>(img) * e.cout_real + c) * oh + oy) * ow + ox] = f[j];
             }
-            if (e.argmax_keys) {
-              const uint32_t inv_idx = 0xFFFFFFFFu - static_cast<uint32_t>(oy * ow + ox);
+          }
+          if (ARGMAX && valid) {
+            const uint32_t inv_idx = 0xFFFFFFFFu - static_cast<uint32_t>(oy * ow + ox);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                unsigned long long key =
-                    valid ? ((static_cast<unsigned long long>(order_f32(f[j])) << 32) | inv_idx) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                  key = other > key ? other : key;
-                }
-                const int c = c0 + j;
-                if (lane == 0 && c < e.cout_real)
-                  atomicMax(e.argmax_keys + static_cast<size_t>(img) * e.cout_real + c, key);
-              }
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t hi = order_f32(f[j]);
+              uint32_t& bh = best_hi[ARGMAX ? ci * 16 + j : 0];
+              uint32_t& bl = best_lo[ARGMAX ? ci * 16 + j : 0];
+              if (hi > bh || (hi == bh && inv_idx > bl)) { bh = hi; bl = inv_idx; }
             }
           }
         }
@@ -319,6 +431,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (lane == 0) ptx::mbar_arrive(&bar->t_empty[acc]);
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
+    flush(cur_img);
+    if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = w0; p.prof[blockIdx.x * 8 + 6] = clock64() - t_kernel0; }
   }
 
   ptx::tc_fence_before();
@@ -346,17 +460,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int N_TILE>
+template <int N_TILE, bool ARGMAX>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
   using C = Cfg<N_TILE>;
   static bool configured = false;
   if (!configured) {
-    MVLM_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<N_TILE>,
+    MVLM_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<N_TILE, ARGMAX>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv_umma_kernel<N_TILE><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  conv_umma_kernel<N_TILE, ARGMAX><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
@@ -373,6 +487,8 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
                "conv_plan: n_tile=%d unsupported", s.n_tile);
   MVLM_REQUIRE(s.cout_pad > 0 && s.cout_pad % s.n_tile == 0, "conv_plan: cout_pad=%d not a multiple of n_tile=%d",
                s.cout_pad, s.n_tile);
+  MVLM_REQUIRE(s.cout_pad <= kMaxCout, "conv_plan: cout_pad=%d exceeds %d", s.cout_pad, kMaxCout);
+  MVLM_REQUIRE(!e.argmax_keys || s.cout_pad == s.n_tile, "conv_plan: fused arg-max needs a single N tile");
   MVLM_REQUIRE(s.kh >= 1 && s.kh <= 3 && s.kw >= 1 && s.kw <= 3, "conv_plan: kernel %dx%d unsupported", s.kh, s.kw);
   MVLM_REQUIRE((reinterpret_cast<uintptr_t>(s.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(s.wpacked) & 15) == 0,
                "conv_plan: pointers must be 16-byte aligned");
@@ -421,17 +537,28 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   p.tiles_y = ceil_div(s.h, kTileH);
   p.n_nt = s.cout_pad / s.n_tile;
   p.total_tiles = s.n * p.tiles_x * p.tiles_y * p.n_nt;
+  p.prof = nullptr;
+  p.debug_mode = 0;
   *out = p;
   return MVLM_OK;
 }
 
-int conv_launch(const ConvParams& p, cudaStream_t stream) {
+static long long* g_prof_buf = nullptr;
+void conv_set_profile_buffer(long long* dev_buf) { g_prof_buf = dev_buf; }
+static int g_debug_mode = 0;
+void conv_set_debug_mode(int mode) { g_debug_mode = mode; }
+
+int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
+  ConvParams p = p_in;
+  p.prof = g_prof_buf;
+  p.debug_mode = g_debug_mode;
+  const bool am = p.e.argmax_keys != nullptr;
   switch (p.s.n_tile) {
-    case 32: return launch_t<32>(p, stream);
-    case 64: return launch_t<64>(p, stream);
-    case 80: return launch_t<80>(p, stream);
-    case 96: return launch_t<96>(p, stream);
-    case 128: return launch_t<128>(p, stream);
+    case 32: return am ? launch_t<32, true>(p, stream) : launch_t<32, false>(p, stream);
+    case 64: return am ? launch_t<64, true>(p, stream) : launch_t<64, false>(p, stream);
+    case 80: return am ? launch_t<80, true>(p, stream) : launch_t<80, false>(p, stream);
+    case 96: return am ? launch_t<96, true>(p, stream) : launch_t<96, false>(p, stream);
+    case 128: return am ? launch_t<128, true>(p, stream) : launch_t<128, false>(p, stream);
   }
   set_error("conv_launch: n_tile=%d unsupported", p.s.n_tile);
   return MVLM_E_UNSUPPORTED;

@@ -63,11 +63,17 @@ struct alignas(64) ConvParams {
   ConvShape s;
   ConvEpilogue e;
   int tiles_x, tiles_y, n_nt, total_tiles;
+  // optional per-CTA cycle counters (8 x int64 per CTA), see conv_umma.cu "role timing"
+  long long* prof;
+  int debug_mode;  // 0 normal; 1 = MMA-only experiment (no TMA loads, operand waits skipped; results garbage)
 };
 
 // Builds the tensor maps and validates the shape.  Returns MVLM_* code.
 int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out);
 // Launches the persistent kernel for a planned conv.
 int conv_launch(const ConvParams& p, cudaStream_t stream);
+// Debug: when non-null, the next conv_launch calls record role timings there (148 x 8 int64).
+void conv_set_profile_buffer(long long* dev_buf);
+void conv_set_debug_mode(int mode);
 
 }  // namespace mvlm

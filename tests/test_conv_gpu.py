@@ -72,7 +72,7 @@ def test_conv_full_epilogue(lib):
     from mvlm_b200 import ops
 
     torch.backends.cudnn.allow_tf32 = False
-    n, h, w, cin, cout, n_tile = 2, 32, 32, 128, 128, 64
+    n, h, w, cin, cout, n_tile = 2, 32, 32, 128, 128, 128
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randn((n, h, w, cin), generator=g, device="cuda").to(torch.bfloat16)
     wt = torch.randn((cout, cin, 3, 3), generator=g, device="cuda") / (cin * 9) ** 0.5

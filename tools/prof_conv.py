@@ -22,3 +22,20 @@ for _ in range(3):
     ops.conv2d_bf16(x, wp, n_tile=nt, pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
 torch.cuda.synchronize()
 print("ok")
+
+# role timing (mvlm_debug_conv_profile)
+import ctypes as C  # noqa: E402
+from mvlm_b200 import _lib  # noqa: E402
+lib = _lib.load()
+buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+lib.mvlm_debug_conv_profile.argtypes = [C.c_void_p]
+lib.mvlm_debug_conv_profile(buf.data_ptr())
+ops.conv2d_bf16(x, wp, n_tile=nt, pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
+torch.cuda.synchronize()
+lib.mvlm_debug_conv_profile(None)
+b = buf.double().mean(0).cpu().numpy()
+names = ["prod wait A-empty", "prod wait B-empty", "mma wait operands", "mma wait acc-free", "mma total", "epi wait acc-full", "epi total", "prod total"]
+for n, v in zip(names, b):
+    print(f"{n:20s} {v / 1e3:10.1f} kcycles")
+tiles = v * (h // 16) ** 2 * (cout // nt)
+print("tiles/CTA", tiles / 148)
