@@ -1,24 +1,30 @@
 // tcgen05/TMEM implicit-GEMM convolution, see conv_umma.cuh for the contract.
 //
+// GEMM orientation ("weights are the A operand"):
+//     D[cout (M=128 TMEM lanes) x pixels (N=256 TMEM columns)] += W[cout x K] * X[K x pixels]
+// A single-CTA tcgen05.mma streams its A operand (128 rows x K=16) from shared memory at ~64 B/clk,
+// i.e. >= ~75 cycles per instruction however small N is (measured: 79/84/94 cycles at N=32/64/128
+// against a 16/32/64-cycle math floor).  With the 128 output channels as A and a whole 16x16-pixel
+// tile as B (N=256) the same instruction does 128 cycles of math (measured 145), so the A stream is
+// hidden -- see tools/exp_mma_only.py and DESIGN.md section 4.
+//
 // One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer   (A: halo tile per (cin-chunk, kx); B: one
-//                               weight tile per (cin-chunk, kx, ky))
-//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma; owns TMEM)
-//   warps 2..9  epilogue       (tcgen05.ld -> bias/BN/ReLU/residual -> global)
+//   warp 0      TMA producer   X: one (16+KH-1)-row halo tile per (cin-chunk, kx);
+//                              W: one [<=128 cout][64 cin] tile per (cin-chunk, kx, ky)
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma (M=128, N=256, K=16); owns TMEM
+//   warps 2..9  epilogue       tcgen05.ld (lane = channel, 16 pixels) -> smem transpose ->
+//                              bias/BN/ReLU/residual on (pixel, 8 channels) vectors -> 16-byte stores
 //
-// A CTA tile is 16x16 output pixels (two 128-row UMMA sub-tiles of 8 image
-// rows each) x N_TILE output channels.  For a fixed input-channel chunk (64
-// channels = one 128-byte swizzle row) and a fixed horizontal tap kx the
-// producer loads ONE (16+KH-1)-row halo tile; the KH vertical taps are
-// descriptors into that tile shifted by whole image rows (2048 B, so the
-// 1024-byte swizzle-atom alignment is preserved).  A traffic is therefore
-// KW*(16+KH-1)/16 tile loads per chunk instead of KW*KH.
-// Zero padding comes from TMA out-of-bounds fill (negative / past-the-end
-// coordinates), also for feature maps smaller than the 16x16 tile.
+// For a fixed input-channel chunk (64 channels = one 128-byte swizzle row) and horizontal tap kx the
+// producer loads ONE halo tile; the KH vertical taps are B descriptors into it shifted by whole image
+// rows (16 px x 128 B = 2048 B, so the 1024-byte swizzle-atom alignment holds).  Zero padding, ragged
+// edges and maps smaller than the tile come from TMA out-of-bounds zero fill.
 //
-// Accumulators: 2 pipeline stages x 2 sub-tiles x N_TILE fp32 columns of TMEM,
-// so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Accumulators: 2 pipeline stages x 256 fp32 columns of TMEM: the epilogue of tile i overlaps the
+// MMAs of tile i+1.
 #include "conv_umma.cuh"
+
+#include <algorithm>
 
 namespace mvlm {
 
@@ -28,38 +34,45 @@ constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int kTileW = 16;
 constexpr int kTileH = 16;
-constexpr int kASlots = 3;
-constexpr int kARowBytes = kTileW * 128;               // one image row of the tile: 16 px x 64 ch bf16
-constexpr int kASlotBytes = (kTileH + 2) * kARowBytes;  // up to 18 halo rows
-constexpr int kSmemBudget = 227 * 1024;
-
-template <int N_TILE>
-struct Cfg {
-  static constexpr int kBSlotBytes = N_TILE * 128;
-  static constexpr int kBSlots = (N_TILE >= 128) ? 6 : 8;
-  static constexpr int kSmemBytes = kASlots * kASlotBytes + kBSlots * kBSlotBytes + 1024 /*align*/ +
-                                    256 /*barriers*/ + 5 * 256 * 4 /*EpiParams*/;
-  static_assert(kSmemBytes <= kSmemBudget, "shared memory budget");
-  static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 128, "UMMA N");
-};
+constexpr int kMTile = 128;                             // output channels per CTA tile (UMMA M)
+constexpr int kHSlots = 3;                              // halo (activation) ring
+constexpr int kWSlots = 5;                              // weight ring
+constexpr int kRowBytes = kTileW * 128;                 // one image row of the halo tile: 16 px x 64 ch bf16
+constexpr int kHSlotBytes = (kTileH + 2) * kRowBytes;   // up to 18 halo rows = 36 KB
+constexpr int kWSlotBytes = kMTile * 128;               // 128 cout rows x 64 cin = 16 KB
+constexpr int kStageFloats = 16 * 36;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad)
+constexpr int kMaxCout = 256;
 
 struct __align__(8) Barriers {
-  uint64_t a_full[kASlots];
-  uint64_t a_empty[kASlots];
-  uint64_t b_full[8];
-  uint64_t b_empty[8];
+  uint64_t h_full[kHSlots];
+  uint64_t h_empty[kHSlots];
+  uint64_t w_full[kWSlots];
+  uint64_t w_empty[kWSlots];
   uint64_t t_full[2];
   uint64_t t_empty[2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Barriers) <= 256, "barrier block");
 
+// Per-output-channel epilogue parameters staged once per CTA in shared memory.
+struct EpiParams {
+  float bias[kMaxCout];
+  float pre_s[kMaxCout];
+  float pre_t[kMaxCout];
+  float post_s[kMaxCout];
+  float post_t[kMaxCout];
+};
+
+constexpr int kSmemBytes = kHSlots * kHSlotBytes + kWSlots * kWSlotBytes + kEpiWarps * kStageFloats * 4 + 256 +
+                           static_cast<int>(sizeof(EpiParams)) + 1024 /*align*/;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
 __device__ __forceinline__ uint32_t order_f32(float f) {
   uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ __forceinline__ uint4 pack16_lo(const float (&f)[16]) {
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
   __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
   __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]);
@@ -71,53 +84,19 @@ __device__ __forceinline__ uint4 pack16_lo(const float (&f)[16]) {
   r.w = *reinterpret_cast<uint32_t*>(&d);
   return r;
 }
-__device__ __forceinline__ uint4 pack16_hi(const float (&f)[16]) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(f[8], f[9]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(f[10], f[11]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(f[12], f[13]);
-  __nv_bfloat162 d = __floats2bfloat162_rn(f[14], f[15]);
-  uint4 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c);
-  r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-__device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&f)[16]) {
-  uint4* p = reinterpret_cast<uint4*>(dst);
-  p[0] = pack16_lo(f);
-  p[1] = pack16_hi(f);
-}
-__device__ __forceinline__ void add16(const __nv_bfloat16* src, float (&f)[16]) {
-  const uint4* p = reinterpret_cast<const uint4*>(src);
-  uint4 q[2] = {p[0], p[1]};
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(q);
+__device__ __forceinline__ void add8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float2 t = __bfloat1622float2(h[j]);
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
     f[2 * j] += t.x;
     f[2 * j + 1] += t.y;
   }
 }
-
-// Per-output-channel epilogue parameters staged once per CTA in shared memory (LDS broadcast instead of
-// 80 global loads per 16-channel step): bias, pre scale/shift, post scale/shift for all N tiles.
-constexpr int kMaxCout = 256;
-struct EpiParams {
-  float bias[kMaxCout];
-  float pre_s[kMaxCout];
-  float pre_t[kMaxCout];
-  float post_s[kMaxCout];
-  float post_t[kMaxCout];
-};
-
-__device__ __forceinline__ void lds16(const float* src, float (&v)[16]) {
-  const float4* p = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 q = p[j];
-    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-  }
+__device__ __forceinline__ void lds8(const float* src, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(src)[0];
+  const float4 b = reinterpret_cast<const float4*>(src)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 // role timing: wait on an mbarrier and add the stalled cycles to `acc` when profiling is on
@@ -128,17 +107,35 @@ __device__ __forceinline__ void timed_wait(uint64_t* b, uint32_t parity, bool pr
   acc += clock64() - t0;
 }
 
-template <int N_TILE, bool ARGMAX>
+struct TileCoord {
+  int mt, tx, ty, img;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  c.mt = t % p.n_nt;
+  int r = t / p.n_nt;
+  c.tx = r % p.tiles_x;
+  r /= p.tiles_x;
+  c.ty = r % p.tiles_y;
+  c.img = r / p.tiles_y;
+  return c;
+}
+
+// Epilogue feature flags (template parameter F): code for a feature is only generated when its bit is set,
+// which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
+enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_HEAD = 32 /* fp32 map / arg-max */ };
+
+template <int F>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  using C = Cfg<N_TILE>;
+  constexpr bool ARGMAX = (F & F_HEAD) != 0;  // HEAD variants use the contiguous tile schedule
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment is required by SWIZZLE_128B atoms (TMA and UMMA agree on
-  // the XOR pattern only relative to 1024-byte aligned addresses).
+  // 1024-byte alignment: TMA and UMMA agree on the SWIZZLE_128B XOR pattern only relative to it
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* a_slots = smem;
-  uint8_t* b_slots = smem + kASlots * kASlotBytes;
-  Barriers* bar = reinterpret_cast<Barriers*>(b_slots + C::kBSlots * C::kBSlotBytes);
+  uint8_t* h_slots = smem;
+  uint8_t* w_slots = smem + kHSlots * kHSlotBytes;
+  float* stage_all = reinterpret_cast<float*>(w_slots + kWSlots * kWSlotBytes);
+  Barriers* bar = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(stage_all) + kEpiWarps * kStageFloats * 4);
   EpiParams* ep = reinterpret_cast<EpiParams*>(reinterpret_cast<uint8_t*>(bar) + 256);
 
   const int warp = threadIdx.x >> 5;
@@ -148,11 +145,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const ConvEpilogue& e = p.e;
   const int n_chunks = (s.cin + 63) >> 6;
   const int halo_rows = kTileH + s.kh - 1;
-  const uint32_t a_bytes = static_cast<uint32_t>(halo_rows) * kARowBytes;
+  const uint32_t h_bytes = static_cast<uint32_t>(halo_rows) * kRowBytes;
+  const int w_rows = s.cout_pad < kMTile ? s.cout_pad : kMTile;  // weight rows actually loaded per tile
+  const uint32_t w_bytes = static_cast<uint32_t>(w_rows) * 128u;
+  // cout <= 64: the weight rows are replicated `rep` times along M, so that all four TMEM lane groups (and
+  // therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows instead.
+  const int rep = s.cout_pad <= 32 ? 4 : (s.cout_pad <= 64 ? 2 : 1);
 
-  // Tile schedule shared by the three roles.  Default: round-robin (neighbouring CTAs work on
-  // neighbouring tiles -> halo / weight reuse in L2).  ARGMAX: contiguous ranges, so that a CTA stays
-  // within one image for ~40 tiles and keeps its running arg-max in registers.
+  // Tile schedule shared by the three roles.  Default: round-robin (neighbouring CTAs work on neighbouring
+  // tiles -> halo / weight reuse in L2).  ARGMAX: contiguous ranges, so that a CTA stays within one image
+  // for ~40 tiles and keeps its running arg-max in registers.
   int t_begin, t_end, t_step;
   if (ARGMAX) {
     const int per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
@@ -173,13 +175,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&p.tm_a);
     ptx::tma_prefetch_desc(&p.tm_b);
-    for (int i = 0; i < kASlots; ++i) {
-      ptx::mbar_init(&bar->a_full[i], 1);
-      ptx::mbar_init(&bar->a_empty[i], 1);
+    for (int i = 0; i < kHSlots; ++i) {
+      ptx::mbar_init(&bar->h_full[i], 1);
+      ptx::mbar_init(&bar->h_empty[i], 1);
     }
-    for (int i = 0; i < C::kBSlots; ++i) {
-      ptx::mbar_init(&bar->b_full[i], 1);
-      ptx::mbar_init(&bar->b_empty[i], 1);
+    for (int i = 0; i < kWSlots; ++i) {
+      ptx::mbar_init(&bar->w_full[i], 1);
+      ptx::mbar_init(&bar->w_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bar->t_full[i], 1);
@@ -201,31 +203,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (ptx::elect_one() && p.debug_mode != 1) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+    if (ptx::elect_one() && p.debug_mode == 0) {
+      int sh = 0, sw = 0;
+      uint32_t ph = 0, pw = 0;
       for (int t = t_begin; t < t_end; t += t_step) {
-        const int nt = t % p.n_nt;
-        int r = t / p.n_nt;
-        const int tx = r % p.tiles_x;
-        r /= p.tiles_x;
-        const int ty = r % p.tiles_y;
-        const int img = r / p.tiles_y;
-        const int x0 = tx * kTileW + s.x_off0;
-        const int y0 = ty * kTileH + s.y_off0;
+        const TileCoord tc = decode_tile(p, t);
+        const int x0 = tc.tx * kTileW + s.x_off0;
+        const int y0 = tc.ty * kTileH + s.y_off0;
         for (int c = 0; c < n_chunks; ++c) {
           for (int kx = 0; kx < s.kw; ++kx) {
-            timed_wait(&bar->a_empty[sa], pa ^ 1, prof, w0);
-            ptx::mbar_expect_tx(&bar->a_full[sa], a_bytes);
-            ptx::tma_load_4d(&p.tm_a, &bar->a_full[sa], a_slots + sa * kASlotBytes, c * 64, x0 + kx,
-                             y0, img);
-            if (++sa == kASlots) { sa = 0; pa ^= 1; }
+            timed_wait(&bar->h_empty[sh], ph ^ 1, prof, w0);
+            ptx::mbar_expect_tx(&bar->h_full[sh], h_bytes);
+            ptx::tma_load_4d(&p.tm_a, &bar->h_full[sh], h_slots + sh * kHSlotBytes, c * 64, x0 + kx, y0, tc.img);
+            if (++sh == kHSlots) { sh = 0; ph ^= 1; }
             for (int ky = 0; ky < s.kh; ++ky) {
-              timed_wait(&bar->b_empty[sb], pb ^ 1, prof, w1);
-              ptx::mbar_expect_tx(&bar->b_full[sb], C::kBSlotBytes);
-              ptx::tma_load_2d(&p.tm_b, &bar->b_full[sb], b_slots + sb * C::kBSlotBytes,
-                               (kx * s.kh + ky) * s.cin + c * 64, nt * N_TILE);
-              if (++sb == C::kBSlots) { sb = 0; pb ^= 1; }
+              timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
+              ptx::mbar_expect_tx(&bar->w_full[sw], w_bytes * rep);
+              for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
+                ptx::tma_load_2d(&p.tm_b, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * 128,
+                                 (kx * s.kh + ky) * s.cin + c * 64, tc.mt * kMTile);
+              if (++sw == kWSlots) { sw = 0; pw ^= 1; }
             }
           }
         }
@@ -237,54 +234,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // elect.sync (not `lane == 0`): the compiler then knows a single lane is active and emits the
     // UTCHMMA / UTCBAR uniform-datapath instructions without a per-lane serialisation loop.
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, N_TILE);
+      constexpr uint32_t idesc256 = ptx::umma_idesc_bf16(kMTile, 256);
+      constexpr uint32_t idesc128 = ptx::umma_idesc_bf16(kMTile, 128);
       // descriptor = {lo: start>>4 | LBO, hi: SBO | version | SWIZZLE_128B}; only lo changes per MMA
-      constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;
+      int sh = 0, sw = 0;
+      uint32_t ph = 0, pw = 0;
       int acc = 0;
       uint32_t pacc = 0;
       for (int t = t_begin; t < t_end; t += t_step) {
         const int ty = (t / p.n_nt / p.tiles_x) % p.tiles_y;
-        // maps of height <= 8 (hourglass levels 8^2 .. 1^2) only populate the first 128-row sub-tile
-        const int n_sub = (ty * kTileH + 8 < s.h) ? 2 : 1;
+        // maps of height <= 8 (hourglass levels 8^2 .. 1^2) only populate the first 8 rows: N = 128
+        const uint32_t idesc = (ty * kTileH + 8 < s.h) ? idesc256 : idesc128;
         timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
         ptx::tc_fence_after();
-        const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * 2 * N_TILE);
+        const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
         uint32_t accumulate = 0;
         for (int c = 0; c < n_chunks; ++c) {
           const int rem = s.cin - c * 64;
           const int nk = rem >= 64 ? 4 : (rem >> 4);
           for (int kx = 0; kx < s.kw; ++kx) {
-            if (p.debug_mode != 1) timed_wait(&bar->a_full[sa], pa, prof, w0);
-            const uint32_t a_lo = ((ptx::smem_u32(a_slots + sa * kASlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
+            if (p.debug_mode == 0) timed_wait(&bar->h_full[sh], ph, prof, w0);
+            const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * kHSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
             for (int ky = 0; ky < s.kh; ++ky) {
-              if (p.debug_mode != 1) timed_wait(&bar->b_full[sb], pb, prof, w0);
+              if (p.debug_mode == 0) timed_wait(&bar->w_full[sw], pw, prof, w0);
               ptx::tc_fence_after();
-              const uint32_t b_lo = ((ptx::smem_u32(b_slots + sb * C::kBSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
-              for (int sub = 0; sub < n_sub; ++sub) {
-                // vertical tap / sub-tile = whole image rows of the halo tile: (sub*8+ky) * 2048 B >> 4
-                const uint32_t a_sub = a_lo + static_cast<uint32_t>((sub * 8 + ky) * (kARowBytes >> 4));
-                const uint32_t d = d_base + sub * N_TILE;
-                if (nk == 4) {
+              const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * kWSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
+              // vertical tap = whole image rows of the halo tile: ky * 2048 B >> 4
+              const uint32_t x_lo = h_lo + static_cast<uint32_t>(ky * (kRowBytes >> 4));
+              if (nk == 4) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(d, (static_cast<uint64_t>(kDescHi) << 32) | (a_sub + 2 * k),
-                                   (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc,
-                                   (k == 0) ? accumulate : 1u);
-                } else {
-                  for (int k = 0; k < nk; ++k)
-                    ptx::umma_bf16(d, (static_cast<uint64_t>(kDescHi) << 32) | (a_sub + 2 * k),
-                                   (static_cast<uint64_t>(kDescHi) << 32) | (b_lo + 2 * k), idesc,
-                                   (k == 0) ? accumulate : 1u);
-                }
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16(d, kDescHi | (w_lo + 2 * k), kDescHi | (x_lo + 2 * k), idesc,
+                                 (k == 0) ? accumulate : 1u);
+              } else {
+                for (int k = 0; k < nk; ++k)
+                  ptx::umma_bf16(d, kDescHi | (w_lo + 2 * k), kDescHi | (x_lo + 2 * k), idesc,
+                                 (k == 0) ? accumulate : 1u);
               }
               accumulate = 1;
-              if (p.debug_mode != 1) ptx::umma_commit(&bar->b_empty[sb]);
-              if (++sb == C::kBSlots) { sb = 0; pb ^= 1; }
+              if (p.debug_mode == 0) ptx::umma_commit(&bar->w_empty[sw]);
+              if (++sw == kWSlots) { sw = 0; pw ^= 1; }
             }
-            if (p.debug_mode != 1) ptx::umma_commit(&bar->a_empty[sa]);
-            if (++sa == kASlots) { sa = 0; pa ^= 1; }
+            if (p.debug_mode == 0) ptx::umma_commit(&bar->h_empty[sh]);
+            if (++sh == kHSlots) { sh = 0; ph ^= 1; }
           }
         }
         ptx::umma_commit(&bar->t_full[acc]);
@@ -295,132 +288,127 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   } else {
     // ===================== epilogue =====================
     const int ew = warp - 2;
-    const int lane_grp = warp & 3;  // TMEM lanes this warp may read: 32*(warp%4)..
-    const int half = ew >> 2;
-    constexpr int kChunks = N_TILE / 16;
-    constexpr int kHalf0 = (kChunks + 1) / 2;
-    const int ch_begin = half == 0 ? 0 : kHalf0;
-    const int ch_end = half == 0 ? kHalf0 : kChunks;
-    const int m = lane_grp * 32 + lane;
+    const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
+    const int n_cgrp = 4 / rep;      // distinct 32-channel groups along M
+    const int cgrp = lane_grp % n_cgrp;
+    const int replica = lane_grp / n_cgrp;
+    const int rows_per_warp = 8 / rep;
+    const int row0 = (ew >> 2) * 8 + replica * rows_per_warp;  // first image row of the tile handled by this warp
+    float* stage = stage_all + ew * kStageFloats;
     int acc = 0;
     uint32_t pacc = 0;
-    // ARGMAX: running (ordered value, ~index) per owned channel, kept across the tiles of one image
-    constexpr int kKeys = ARGMAX ? kHalf0 * 16 : 1;
-    uint32_t best_hi[kKeys], best_lo[kKeys];
+    // HEAD: lane = channel -> one running (ordered value, ~index) pair per thread
+    uint32_t best_hi = 0u, best_lo = 0u;
     int cur_img = -1;
+    const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
+    // pixel-major role after the transpose: lane -> (pixel j = lane/4 (+8), channels (lane%4)*8 .. +7)
+    const int pj = lane >> 2;
+    const int cq = (lane & 3) * 8;
+    constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
+    for (int t = t_begin; t < t_end; t += t_step) {
+      const TileCoord tc = decode_tile(p, t);
+      const int m0 = tc.mt * kMTile;
+      const int c_lane = m0 + cgrp * 32 + lane;           // channel-major role: my output channel
+      const int c0 = m0 + cgrp * 32 + cq;                 // pixel-major role: first of my 8 channels
+      const bool grp_active = m0 + cgrp * 32 < s.cout_pad;
+      const int y_first = tc.ty * kTileH + row0;
+      const bool rows_active = y_first < s.h;
+      const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
+      const int xa = tc.tx * kTileW + pj;
+      const bool va = ch_ok && xa < s.w, vb = ch_ok && xa + 8 < s.w;
+      // element index of pixel (img, y_first, xa); 32-bit: pixel count x channel stride < 2^31 (checked in conv_plan)
+      const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first) * s.w + xa;
+      if ((F & F_HEAD) && e.argmax_keys && tc.img != cur_img) {
+        if (cur_img >= 0 && best_hi != 0u && c_lane < e.cout_real)
+          atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
+                    (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
+        best_hi = 0u; best_lo = 0u;
+        cur_img = tc.img;
+      }
+      // residual rows do not depend on the accumulator: fetch them while the MMAs of this tile still run
+      uint4 r1[8][2];
+      if ((F & F_RES1) && grp_active && rows_active) {
+        const __nv_bfloat16* rp = e.res1 + e.res1_co + c0;
 #pragma unroll
-    for (int i = 0; i < kKeys; ++i) { best_hi[i] = 0u; best_lo[i] = 0u; }
-    auto flush = [&](int img) {
-      if (!ARGMAX || img < 0) return;
-#pragma unroll
-      for (int ci = 0; ci < kHalf0; ++ci) {
-        const int ch = ch_begin + ci;
-        if (ch >= ch_end) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t hi = best_hi[ARGMAX ? ci * 16 + j : 0], lo = best_lo[ARGMAX ? ci * 16 + j : 0];
-          const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
-          const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-          const int cidx = ch * 16 + j;  // N tile 0 only: arg-max convs have a single N tile
-          if (lane == 0 && cidx < e.cout_real && mhi != 0u)
-            atomicMax(e.argmax_keys + static_cast<size_t>(img) * e.cout_real + cidx,
-                      (static_cast<unsigned long long>(mhi) << 32) | mlo);
-          best_hi[ARGMAX ? ci * 16 + j : 0] = 0u;
-          best_lo[ARGMAX ? ci * 16 + j : 0] = 0u;
+        for (int r = 0; r < 8; ++r) {
+          if (r < rows_per_warp && y_first + r < s.h) {
+            const uint32_t pix = pix0 + r * s.w;
+            if (va) r1[r][0] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(pix * e.res1_cs));
+            if (vb) r1[r][1] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>((pix + 8) * e.res1_cs));
+          }
         }
       }
-    };
-    for (int t = t_begin; t < t_end; t += t_step) {
-      const int nt = t % p.n_nt;
-      int r = t / p.n_nt;
-      const int tx = r % p.tiles_x;
-      r /= p.tiles_x;
-      const int ty = r % p.tiles_y;
-      const int img = r / p.tiles_y;
-      const int n_sub = (ty * kTileH + 8 < s.h) ? 2 : 1;
-      if (ARGMAX && img != cur_img) {
-        flush(cur_img);
-        cur_img = img;
-      }
+      // per-channel parameters of my 8 channels (pixel-major role) and my channel (channel-major role)
+      float pre_s[8], pre_t[8], post_s[8], post_t[8];
+      if (F & F_PRE) { lds8(ep->pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep->pre_t + (ch_ok ? c0 : 0), pre_t); }
+      if (F & F_POST) { lds8(ep->post_s + (ch_ok ? c0 : 0), post_s); lds8(ep->post_t + (ch_ok ? c0 : 0), post_t); }
+      const float bias_c = ep->bias[c_lane < kMaxCout ? c_lane : 0];
       timed_wait(&bar->t_full[acc], pacc, prof, w0);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int sub = 0; sub < n_sub; ++sub) {
-        const int y = ty * kTileH + sub * 8 + (m >> 4);
-        const int x = tx * kTileW + (m & 15);
-        const bool valid = (y < s.h) && (x < s.w);
-        const size_t pix = (static_cast<size_t>(img) * s.h + y) * s.w + x;
+      if (grp_active && rows_active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                               static_cast<uint32_t>(acc * 2 * N_TILE + sub * N_TILE);
-        const int oy = y * e.up_sy + e.up_py;
-        const int ox = x * e.up_sx + e.up_px;
-        const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
+                               static_cast<uint32_t>(acc * 256 + row0 * 16);
+        uint32_t v[2][16];
+        ptx::tmem_ld16(taddr, v[0]);
 #pragma unroll
-        for (int ci = 0; ci < kHalf0; ++ci) {
-          const int ch = ch_begin + ci;
-          if (ch >= ch_end) continue;
-          const int c0 = nt * N_TILE + ch * 16;
-          // residual loads first: their latency overlaps the TMEM load
-          uint4 r1[2], r2[2];
-          const bool has_r1 = e.res1 && valid, has_r2 = e.res2 && valid;
-          if (has_r1) {
-            const uint4* q = reinterpret_cast<const uint4*>(e.res1 + pix * e.res1_cs + e.res1_co + c0);
-            r1[0] = q[0]; r1[1] = q[1];
-          }
-          if (has_r2) {
-            const uint4* q = reinterpret_cast<const uint4*>(e.res2 + pix * e.res2_cs + e.res2_co + c0);
-            r2[0] = q[0]; r2[1] = q[1];
-          }
-          uint32_t v[16];
-          ptx::tmem_ld16(taddr + ch * 16, v);
-          float f[16], pb_[16];
-          lds16(ep->bias + c0, pb_);
-          ptx::tmem_ld_wait();
+        for (int r = 0; r < 8; ++r) {
+          if (r < rows_per_warp) {
+            const int y = y_first + r;
+            ptx::tmem_ld_wait();
+            if (r + 1 < rows_per_warp) ptx::tmem_ld16(taddr + (r + 1) * 16, v[(r + 1) & 1]);  // next row in flight
+            const uint32_t(&vr)[16] = v[r & 1];
+            if (y < s.h) {
+              if (F & F_HEAD) {
+                // channel-major consumers: lane = channel c_lane, vr[j] = pixel x0+j of row y
+                const int oy = y * e.up_sy + e.up_py;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + pb_[j];
-          if (e.out_pre && valid) {
-            float sc[16], sh[16], g[16];
-            lds16(ep->pre_s + c0, sc);
-            lds16(ep->pre_t + c0, sh);
+                for (int j = 0; j < 16; ++j) {
+                  const int x = tc.tx * kTileW + j;
+                  if (x < s.w && c_lane < e.cout_real) {
+                    const float f = __uint_as_float(vr[j]) + bias_c;
+                    const int ox = x * e.up_sx + e.up_px;
+                    if (e.out_f32) e.out_f32[((static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh + oy) * ow + ox] = f;
+                    if (e.argmax_keys) {
+                      const uint32_t hi = order_f32(f);
+                      const uint32_t lo = 0xFFFFFFFFu - static_cast<uint32_t>(oy * ow + ox);
+                      if (hi > best_hi || (hi == best_hi && lo > best_lo)) { best_hi = hi; best_lo = lo; }
+                    }
+                  }
+                }
+              }
+              if (kBf16Out) {
+                // bias in the channel-major role (one register), then transpose 16 px x 32 ch through shared
+                // memory: row = pixel, 36-float pitch (conflict-free for the STS.32 and the LDS.128)
+                __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-            store16(e.out_pre + pix * e.pre_cs + e.pre_co + c0, g);
-          }
-          if (has_r1) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(r1);
+                for (int j = 0; j < 16; ++j) stage[j * 36 + lane] = __uint_as_float(vr[j]) + bias_c;
+                __syncwarp();
+                const uint32_t pix = pix0 + r * s.w;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float2 q = __bfloat1622float2(h[j]); f[2 * j] += q.x; f[2 * j + 1] += q.y; }
-          }
-          if (has_r2) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(r2);
+                for (int i = 0; i < 2; ++i) {
+                  if (!(i == 0 ? va : vb)) continue;
+                  const uint32_t px = pix + 8 * i;
+                  float f[8];
+                  lds8(stage + (pj + 8 * i) * 36 + cq, f);
+                  if (F & F_PRE) {
+                    float g[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float2 q = __bfloat1622float2(h[j]); f[2 * j] += q.x; f[2 * j + 1] += q.y; }
-          }
-          if (e.out_raw && valid) store16(e.out_raw + pix * e.raw_cs + e.raw_co + c0, f);
-          if (e.out_post && valid) {
-            float sc[16], sh[16], g[16];
-            lds16(ep->post_s + c0, sc);
-            lds16(ep->post_t + c0, sh);
+                    for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], pre_s[j], pre_t[j]), 0.f);
+                    *reinterpret_cast<uint4*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(px * e.pre_cs)) = pack8(g);
+                  }
+                  if (F & F_RES1) add8(r1[r][i], f);
+                  if (F & F_RES2)
+                    add8(*reinterpret_cast<const uint4*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(px * e.res2_cs)), f);
+                  if (F & F_RAW)
+                    *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(px * e.raw_cs)) = pack8(f);
+                  if (F & F_POST) {
+                    float g[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-            store16(e.out_post + pix * e.post_cs + e.post_co + c0, g);
-          }
-          if (e.out_f32 && valid) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = c0 + j;
-              if (c < e.cout_real)
-                e.out_f32[((static_cast<size_t>(img) * e.cout_real + c) * oh + oy) * ow + ox] = f[j];
-            }
-          }
-          if (ARGMAX && valid) {
-            const uint32_t inv_idx = 0xFFFFFFFFu - static_cast<uint32_t>(oy * ow + ox);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t hi = order_f32(f[j]);
-              uint32_t& bh = best_hi[ARGMAX ? ci * 16 + j : 0];
-              uint32_t& bl = best_lo[ARGMAX ? ci * 16 + j : 0];
-              if (hi > bh || (hi == bh && inv_idx > bl)) { bh = hi; bl = inv_idx; }
+                    for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], post_s[j], post_t[j]), 0.f);
+                    *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(px * e.post_cs)) = pack8(g);
+                  }
+                }
+              }
             }
           }
         }
@@ -431,7 +419,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (lane == 0) ptx::mbar_arrive(&bar->t_empty[acc]);
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    flush(cur_img);
+    if ((F & F_HEAD) && e.argmax_keys && cur_img >= 0 && best_hi != 0u) {
+      const int c_lane = cgrp * 32 + lane;  // arg-max convs have a single M tile
+      if (c_lane < e.cout_real)
+        atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
+                  (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
+    }
     if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = w0; p.prof[blockIdx.x * 8 + 6] = clock64() - t_kernel0; }
   }
 
@@ -460,21 +453,22 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int N_TILE, bool ARGMAX>
+template <int F>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
-  using C = Cfg<N_TILE>;
   static bool configured = false;
   if (!configured) {
-    MVLM_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<N_TILE, ARGMAX>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MVLM_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv_umma_kernel<N_TILE, ARGMAX><<<grid, kThreads, C::kSmemBytes, stream>>>(p);
+  conv_umma_kernel<F><<<grid, kThreads, kSmemBytes, stream>>>(p);
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
 }
+
+long long* g_prof_buf = nullptr;
+int g_debug_mode = 0;
 
 }  // namespace
 
@@ -483,12 +477,18 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   MVLM_REQUIRE(s.n > 0 && s.h > 0 && s.w > 0, "conv_plan: bad image dims %d %d %d", s.n, s.h, s.w);
   MVLM_REQUIRE(s.cin >= 16 && s.cin % 16 == 0, "conv_plan: cin=%d must be a multiple of 16", s.cin);
   MVLM_REQUIRE(s.in_cs >= s.cin && s.in_cs % 8 == 0, "conv_plan: in_cs=%d invalid", s.in_cs);
-  MVLM_REQUIRE(s.n_tile == 32 || s.n_tile == 64 || s.n_tile == 80 || s.n_tile == 96 || s.n_tile == 128,
-               "conv_plan: n_tile=%d unsupported", s.n_tile);
-  MVLM_REQUIRE(s.cout_pad > 0 && s.cout_pad % s.n_tile == 0, "conv_plan: cout_pad=%d not a multiple of n_tile=%d",
-               s.cout_pad, s.n_tile);
+  MVLM_REQUIRE(s.cout_pad >= 16 && s.cout_pad % 16 == 0, "conv_plan: cout_pad=%d must be a multiple of 16", s.cout_pad);
+  MVLM_REQUIRE(s.cout_pad <= kMTile || s.cout_pad % kMTile == 0,
+               "conv_plan: cout_pad=%d must be <= 128 or a multiple of 128", s.cout_pad);
   MVLM_REQUIRE(s.cout_pad <= kMaxCout, "conv_plan: cout_pad=%d exceeds %d", s.cout_pad, kMaxCout);
-  MVLM_REQUIRE(!e.argmax_keys || s.cout_pad == s.n_tile, "conv_plan: fused arg-max needs a single N tile");
+  MVLM_REQUIRE(!e.argmax_keys || s.cout_pad <= kMTile, "conv_plan: fused arg-max needs cout_pad <= 128");
+  MVLM_REQUIRE(!((e.argmax_keys || e.out_f32) && (e.res1 || e.res2 || e.out_pre || e.out_raw || e.out_post)),
+               "conv_plan: fp32 / arg-max outputs cannot be combined with bf16 outputs or residual inputs");
+  {
+    const long long npix = 1ll * s.n * s.h * s.w;
+    const int max_cs = std::max(std::max(e.pre_cs, e.raw_cs), std::max(std::max(e.post_cs, e.res1_cs), e.res2_cs));
+    MVLM_REQUIRE(npix * std::max(max_cs, 1) < (1ll << 31), "conv_plan: tensor too large for 32-bit element offsets");
+  }
   MVLM_REQUIRE(s.kh >= 1 && s.kh <= 3 && s.kw >= 1 && s.kw <= 3, "conv_plan: kernel %dx%d unsupported", s.kh, s.kw);
   MVLM_REQUIRE((reinterpret_cast<uintptr_t>(s.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(s.wpacked) & 15) == 0,
                "conv_plan: pointers must be 16-byte aligned");
@@ -502,7 +502,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   p.s = s;
   p.e = e;
   {
-    // A: (C, W, H, N) bf16, box (64, 16, 16+KH-1, 1), 128-byte swizzle, OOB -> 0
+    // X: (C, W, H, N) bf16, box (64, 16, 16+KH-1, 1), 128-byte swizzle, OOB -> 0
     cuuint64_t gdim[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
     cuuint64_t gstr[3] = {(cuuint64_t)s.in_cs * 2, (cuuint64_t)s.in_cs * 2 * s.w,
                           (cuuint64_t)s.in_cs * 2 * s.w * s.h};
@@ -512,30 +512,30 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("conv_plan: cuTensorMapEncodeTiled(A) failed with %d (cin=%d w=%d h=%d n=%d cs=%d)", (int)r, s.cin,
+      set_error("conv_plan: cuTensorMapEncodeTiled(X) failed with %d (cin=%d w=%d h=%d n=%d cs=%d)", (int)r, s.cin,
                 s.w, s.h, s.n, s.in_cs);
       return MVLM_E_CUDA;
     }
   }
   {
-    // B: (K = KW*KH*cin, cout_pad) bf16, box (64, N_TILE)
+    // W: (K = KW*KH*cin, cout_pad) bf16, box (64, min(cout_pad,128))
     const cuuint64_t ktot = (cuuint64_t)s.kw * s.kh * s.cin;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)s.cout_pad};
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)s.n_tile};
+    cuuint32_t box[2] = {64, (cuuint32_t)(s.cout_pad < kMTile ? s.cout_pad : kMTile)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(s.wpacked), gdim,
                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("conv_plan: cuTensorMapEncodeTiled(B) failed with %d (ktot=%llu cout_pad=%d)", (int)r,
+      set_error("conv_plan: cuTensorMapEncodeTiled(W) failed with %d (ktot=%llu cout_pad=%d)", (int)r,
                 (unsigned long long)ktot, s.cout_pad);
       return MVLM_E_CUDA;
     }
   }
   p.tiles_x = ceil_div(s.w, kTileW);
   p.tiles_y = ceil_div(s.h, kTileH);
-  p.n_nt = s.cout_pad / s.n_tile;
+  p.n_nt = ceil_div(s.cout_pad, kMTile);
   p.total_tiles = s.n * p.tiles_x * p.tiles_y * p.n_nt;
   p.prof = nullptr;
   p.debug_mode = 0;
@@ -543,24 +543,30 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   return MVLM_OK;
 }
 
-static long long* g_prof_buf = nullptr;
 void conv_set_profile_buffer(long long* dev_buf) { g_prof_buf = dev_buf; }
-static int g_debug_mode = 0;
 void conv_set_debug_mode(int mode) { g_debug_mode = mode; }
 
 int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   ConvParams p = p_in;
   p.prof = g_prof_buf;
   p.debug_mode = g_debug_mode;
-  const bool am = p.e.argmax_keys != nullptr;
-  switch (p.s.n_tile) {
-    case 32: return am ? launch_t<32, true>(p, stream) : launch_t<32, false>(p, stream);
-    case 64: return am ? launch_t<64, true>(p, stream) : launch_t<64, false>(p, stream);
-    case 80: return am ? launch_t<80, true>(p, stream) : launch_t<80, false>(p, stream);
-    case 96: return am ? launch_t<96, true>(p, stream) : launch_t<96, false>(p, stream);
-    case 128: return am ? launch_t<128, true>(p, stream) : launch_t<128, false>(p, stream);
+  const ConvEpilogue& e = p.e;
+  const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
+                (e.out_post ? F_POST : 0) | ((e.out_f32 || e.argmax_keys) ? F_HEAD : 0);
+  switch (f) {
+    // the combinations the network plan uses (hourglass.cu)
+    case F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);  // RB conv1/2
+    case F_PRE | F_RES1 | F_RAW: return launch_t<F_PRE | F_RES1 | F_RAW>(p, stream);
+    case F_RES1 | F_RAW | F_POST: return launch_t<F_RES1 | F_RAW | F_POST>(p, stream);                  // RB conv3
+    case F_RES1 | F_RAW: return launch_t<F_RES1 | F_RAW>(p, stream);
+    case F_RAW: return launch_t<F_RAW>(p, stream);                                                      // resample, conv6/10
+    case F_PRE: return launch_t<F_PRE>(p, stream);                                                      // conv5, conv9
+    case F_RES1 | F_RES2 | F_RAW | F_POST: return launch_t<F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);  // conv7
+    case F_HEAD: return launch_t<F_HEAD>(p, stream);                                                    // conv11 phases
+    case F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
+      return launch_t<F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
   }
-  set_error("conv_launch: n_tile=%d unsupported", p.s.n_tile);
+  set_error("conv_launch: unsupported epilogue combination 0x%x", f);
   return MVLM_E_UNSUPPORTED;
 }
 

@@ -68,7 +68,7 @@ def test_conv_raw(lib, n, h, w, cin, cs, cout, n_tile, kh, kw):
 
 
 def test_conv_full_epilogue(lib):
-    """bias + act_pre + two residuals + raw + act_post + fp32 NCHW out + fused argmax keys."""
+    """bias + act_pre + two residuals + raw + act_post; and fp32 NCHW out + fused argmax keys."""
     from mvlm_b200 import ops
 
     torch.backends.cudnn.allow_tf32 = False
@@ -84,11 +84,8 @@ def test_conv_full_epilogue(lib):
     out_pre = torch.zeros((n, h, w, 128), device="cuda", dtype=torch.bfloat16)
     out_raw = torch.zeros((n, h, w, 256), device="cuda", dtype=torch.bfloat16)
     out_post = torch.zeros((n, h, w, 256), device="cuda", dtype=torch.bfloat16)
-    out_f32 = torch.zeros((n, cout, h, w), device="cuda")
-    keys = torch.zeros((n * cout,), device="cuda", dtype=torch.int64)
     ops.conv2d_bf16(x, wp, n_tile=n_tile, bias=bias, pre=(s1, t1, out_pre, 0), res1=(r1, 128), res2=(r2, 0),
-                    out_raw=(out_raw, 64), post=(s2, t2, out_post, 128), out_f32=out_f32, argmax_keys=keys,
-                    cout_real=cout)
+                    out_raw=(out_raw, 64), post=(s2, t2, out_post, 128))
     torch.cuda.synchronize()
     v = _ref_conv(x, wt, bias, 3, 3, -1, -1)
     scale = v.abs().max().item()
@@ -100,12 +97,23 @@ def test_conv_full_epilogue(lib):
     assert (out_raw[..., :64] == 0).all() and (out_raw[..., 192:] == 0).all()
     post_ref = torch.relu(v2 * s2 + t2)
     assert (out_post[..., 128:].float() - post_ref).abs().max().item() <= tol * s2.abs().max().item() + post_ref.abs().max().item() * 2.0 ** -8
-    assert (out_f32 - v2.permute(0, 3, 1, 2)).abs().max().item() <= tol
-    # fused argmax == argmax of the fp32 map the same kernel wrote (bit-exact, first index on ties)
-    k = keys.view(n, cout)
-    idx = 0xFFFFFFFF - (k & 0xFFFFFFFF)
-    ref_idx = out_f32.view(n, cout, -1).argmax(dim=-1)
-    assert torch.equal(idx, ref_idx)
+    # fp32 + fused arg-max path (conv11): argmax == argmax of the fp32 map the same kernel wrote
+    for co in (128, 73, 32):
+        wt2 = wt[:co]
+        cp = ((co + 15) // 16) * 16
+        wp2 = ops.pack_conv_weight(wt2, cp, cin)
+        b2 = torch.zeros(cp, device="cuda")
+        b2[:co] = bias[:co]
+        out_f32 = torch.zeros((n, co, h, w), device="cuda")
+        keys = torch.zeros((n * co,), device="cuda", dtype=torch.int64)
+        ops.conv2d_bf16(x, wp2, n_tile=cp, bias=b2, out_f32=out_f32, argmax_keys=keys, cout_real=co)
+        torch.cuda.synchronize()
+        assert (out_f32 - v[..., :co].permute(0, 3, 1, 2)).abs().max().item() <= tol
+        k = keys.view(n, co)
+        idx = 0xFFFFFFFF - (k & 0xFFFFFFFF)
+        assert torch.equal(idx, out_f32.view(n, co, -1).argmax(dim=-1))
+    with pytest.raises(Exception, match="cannot be combined"):
+        ops.conv2d_bf16(x, wp, n_tile=n_tile, res1=(r1, 0), out_f32=torch.zeros((n, cout, h, w), device="cuda"), cout_real=cout)
 
 
 def test_conv_upsample_phase(lib):

@@ -13,7 +13,7 @@ lib = _lib.load()
 lib.mvlm_debug_conv_profile.argtypes = [C.c_void_p]
 lib.mvlm_debug_conv_mode.argtypes = [C.c_int]
 v, h = 100, 128
-for cin, cout, nt in ((256, 128, 128), (256, 64, 64), (256, 96, 96), (256, 32, 32)):
+for cin, cout, nt in ((256, 128, 128),):
     x = torch.randn((v, h, h, cin), device="cuda").to(torch.bfloat16)
     w = torch.randn((cout, cin, 3, 3), device="cuda") / 48
     wp = ops.pack_conv_weight(w, cout, cin)
@@ -27,6 +27,6 @@ for cin, cout, nt in ((256, 128, 128), (256, 64, 64), (256, 96, 96), (256, 32, 3
         lib.mvlm_debug_conv_profile(None)
         lib.mvlm_debug_conv_mode(0)
         b = buf.double().mean(0).cpu().numpy()
-        n_mma = v * (h // 16) ** 2 / 148 * (cin // 64) * 9 * 2 * 4
+        n_mma = v * (h // 16) ** 2 / 148 * (cin // 64) * 9 * 4
         print(f"N={nt:3d} mode={mode}: mma total {b[4] / 1e3:8.1f} kcyc, wait operands {b[2] / 1e3:8.1f}, wait acc {b[3] / 1e3:7.1f} "
               f"-> {(b[4] - b[2] - b[3]) / n_mma:6.1f} cyc per MMA issued (floor {nt / 2:.0f})")

@@ -11,15 +11,18 @@ from mvlm_b200 import build, ops  # noqa: E402
 build.build()
 h, cin, cout, nt = (int(x) for x in sys.argv[1:5])
 v = int(sys.argv[5]) if len(sys.argv) > 5 else 100
+k = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+epi = sys.argv[7] if len(sys.argv) > 7 else "rb"
 x = torch.randn((v, h, h, cin), device="cuda").to(torch.bfloat16)
-w = torch.randn((cout, cin, 3, 3), device="cuda") / (cin * 9) ** 0.5
+w = torch.randn((cout, cin, k, k), device="cuda") / (cin * k * k) ** 0.5
 wp = ops.pack_conv_weight(w, cout, cin)
 big = torch.zeros((v, h, h, 256), device="cuda", dtype=torch.bfloat16)
 act = torch.zeros((v, h, h, max(cout, 64)), device="cuda", dtype=torch.bfloat16)
 s = torch.ones(cout, device="cuda")
 t = torch.zeros(cout, device="cuda")
+kw = dict(out_raw=(big, 0)) if epi == "raw" else dict(pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
 for _ in range(3):
-    ops.conv2d_bf16(x, wp, n_tile=nt, pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
+    ops.conv2d_bf16(x, wp, n_tile=nt, kh=k, kw=k, **kw)
 torch.cuda.synchronize()
 print("ok")
 
@@ -30,12 +33,12 @@ lib = _lib.load()
 buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
 lib.mvlm_debug_conv_profile.argtypes = [C.c_void_p]
 lib.mvlm_debug_conv_profile(buf.data_ptr())
-ops.conv2d_bf16(x, wp, n_tile=nt, pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
+ops.conv2d_bf16(x, wp, n_tile=nt, kh=k, kw=k, **kw)
 torch.cuda.synchronize()
 lib.mvlm_debug_conv_profile(None)
 b = buf.double().mean(0).cpu().numpy()
 names = ["prod wait A-empty", "prod wait B-empty", "mma wait operands", "mma wait acc-free", "mma total", "epi wait acc-full", "epi total", "prod total"]
 for n, v in zip(names, b):
     print(f"{n:20s} {v / 1e3:10.1f} kcycles")
-tiles = v * (h // 16) ** 2 * (cout // nt)
-print("tiles/CTA", tiles / 148)
+tiles = v * (h // 16) ** 2 * max(1, cout // 128)
+print("tiles/CTA", tiles / 148, "cycles/tile", b[4] / (tiles / 148))
