@@ -123,11 +123,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 
 // Epilogue feature flags (template parameter F): code for a feature is only generated when its bit is set,
 // which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
-enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_HEAD = 32 /* fp32 map / arg-max */ };
+enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64 };
+constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  constexpr bool ARGMAX = (F & F_HEAD) != 0;  // HEAD variants use the contiguous tile schedule
+  constexpr bool ARGMAX = (F & F_ARGMAX) != 0;  // arg-max variants use the contiguous tile schedule
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: TMA and UMMA agree on the SWIZZLE_128B XOR pattern only relative to it
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&p.tm_a);
     ptx::tma_prefetch_desc(&p.tm_b);
+    if (p.tail) { ptx::tma_prefetch_desc(&p.tm_a2); ptx::tma_prefetch_desc(&p.tm_b2); }
     for (int i = 0; i < kHSlots; ++i) {
       ptx::mbar_init(&bar->h_full[i], 1);
       ptx::mbar_init(&bar->h_empty[i], 1);
@@ -211,16 +213,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int x0 = tc.tx * kTileW + s.x_off0;
         const int y0 = tc.ty * kTileH + s.y_off0;
         for (int c = 0; c < n_chunks; ++c) {
+          // the last chunk may be a narrow tail (16 / 32 channels) with its own tensor maps: rows of 32 / 64 bytes
+          const bool is_tail = p.tail != 0 && c == n_chunks - 1;
+          const void* tma = is_tail ? &p.tm_a2 : &p.tm_a;
+          const void* tmb = is_tail ? &p.tm_b2 : &p.tm_b;
+          const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per pixel / weight row
+          const uint32_t hb = static_cast<uint32_t>(halo_rows) * kTileW * row_b;
+          const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
           for (int kx = 0; kx < s.kw; ++kx) {
             timed_wait(&bar->h_empty[sh], ph ^ 1, prof, w0);
-            ptx::mbar_expect_tx(&bar->h_full[sh], h_bytes);
-            ptx::tma_load_4d(&p.tm_a, &bar->h_full[sh], h_slots + sh * kHSlotBytes, c * 64, x0 + kx, y0, tc.img);
+            ptx::mbar_expect_tx(&bar->h_full[sh], hb);
+            ptx::tma_load_4d(tma, &bar->h_full[sh], h_slots + sh * kHSlotBytes, c * 64, x0 + kx, y0, tc.img);
             if (++sh == kHSlots) { sh = 0; ph ^= 1; }
             for (int ky = 0; ky < s.kh; ++ky) {
               timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
-              ptx::mbar_expect_tx(&bar->w_full[sw], w_bytes * rep);
+              ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
               for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
-                ptx::tma_load_2d(&p.tm_b, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * 128,
+                ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * row_b,
                                  (kx * s.kh + ky) * s.cin + c * 64, tc.mt * kMTile);
               if (++sw == kWSlots) { sw = 0; pw ^= 1; }
             }
@@ -253,6 +262,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         for (int c = 0; c < n_chunks; ++c) {
           const int rem = s.cin - c * 64;
           const int nk = rem >= 64 ? 4 : (rem >> 4);
+          // tail chunk: SWIZZLE_32B (16 ch: 8-row atoms of 256 B) or SWIZZLE_64B (32 ch: atoms of 512 B)
+          const bool is_tail = p.tail != 0 && c == n_chunks - 1;
+          const uint64_t desc_hi = !is_tail ? kDescHi
+                                            : (static_cast<uint64_t>((p.tail == 16 ? 16u : 32u) | (1u << 14) |
+                                                                     ((p.tail == 16 ? 6u : 4u) << 29)) << 32);
+          const uint32_t ky_step = !is_tail ? (kRowBytes >> 4) : static_cast<uint32_t>(2 * p.tail);  // one image row >> 4
           for (int kx = 0; kx < s.kw; ++kx) {
             if (p.debug_mode == 0) timed_wait(&bar->h_full[sh], ph, prof, w0);
             const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * kHSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
@@ -261,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               ptx::tc_fence_after();
               const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * kWSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
               // vertical tap = whole image rows of the halo tile: ky * 2048 B >> 4
-              const uint32_t x_lo = h_lo + static_cast<uint32_t>(ky * (kRowBytes >> 4));
+              const uint32_t x_lo = h_lo + static_cast<uint32_t>(ky) * ky_step;
               if (nk == 4) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                                  (k == 0) ? accumulate : 1u);
               } else {
                 for (int k = 0; k < nk; ++k)
-                  ptx::umma_bf16(d, kDescHi | (w_lo + 2 * k), kDescHi | (x_lo + 2 * k), idesc,
+                  ptx::umma_bf16(d, desc_hi | (w_lo + 2 * k), desc_hi | (x_lo + 2 * k), idesc,
                                  (k == 0) ? accumulate : 1u);
               }
               accumulate = 1;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const bool va = ch_ok && xa < s.w, vb = ch_ok && xa + 8 < s.w;
       // element index of pixel (img, y_first, xa); 32-bit: pixel count x channel stride < 2^31 (checked in conv_plan)
       const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first) * s.w + xa;
-      if ((F & F_HEAD) && e.argmax_keys && tc.img != cur_img) {
+      if ((F & F_ARGMAX) && tc.img != cur_img) {
         if (cur_img >= 0 && best_hi != 0u && c_lane < e.cout_real)
           atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
                     (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
@@ -360,19 +375,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             if (y < s.h) {
               if (F & F_HEAD) {
                 // channel-major consumers: lane = channel c_lane, vr[j] = pixel x0+j of row y
+                const int x0 = tc.tx * kTileW;
+                const int nvx = s.w - x0;  // >= 16 for interior tiles
                 const int oy = y * e.up_sy + e.up_py;
+                const uint32_t idx0 = static_cast<uint32_t>(oy * ow + x0 * e.up_sx + e.up_px);
+                if (c_lane < e.cout_real) {
+                  if (F & F_ARGMAX) {
+                    unsigned long long best = (static_cast<unsigned long long>(best_hi) << 32) | best_lo;
+                    uint32_t lo = 0xFFFFFFFFu - idx0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int x = tc.tx * kTileW + j;
-                  if (x < s.w && c_lane < e.cout_real) {
-                    const float f = __uint_as_float(vr[j]) + bias_c;
-                    const int ox = x * e.up_sx + e.up_px;
-                    if (e.out_f32) e.out_f32[((static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh + oy) * ow + ox] = f;
-                    if (e.argmax_keys) {
-                      const uint32_t hi = order_f32(f);
-                      const uint32_t lo = 0xFFFFFFFFu - static_cast<uint32_t>(oy * ow + ox);
-                      if (hi > best_hi || (hi == best_hi && lo > best_lo)) { best_hi = hi; best_lo = lo; }
+                    for (int j = 0; j < 16; ++j) {
+                      const unsigned long long key =
+                          (static_cast<unsigned long long>(order_f32(__uint_as_float(vr[j]) + bias_c)) << 32) | lo;
+                      if (j < nvx && key > best) best = key;
+                      lo -= static_cast<uint32_t>(e.up_sx);
                     }
+                    best_hi = static_cast<uint32_t>(best >> 32);
+                    best_lo = static_cast<uint32_t>(best);
+                  }
+                  if (F & F_F32) {
+                    float* dst = e.out_f32 + (static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh * ow + idx0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                      if (j < nvx) dst[j * e.up_sx] = __uint_as_float(vr[j]) + bias_c;
                   }
                 }
               }
@@ -419,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (lane == 0) ptx::mbar_arrive(&bar->t_empty[acc]);
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    if ((F & F_HEAD) && e.argmax_keys && cur_img >= 0 && best_hi != 0u) {
+    if ((F & F_ARGMAX) && cur_img >= 0 && best_hi != 0u) {
       const int c_lane = cgrp * 32 + lane;  // arg-max convs have a single M tile
       if (c_lane < e.cout_real)
         atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
@@ -533,6 +558,28 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
       return MVLM_E_CUDA;
     }
   }
+  p.tail = (s.cin % 64 == 16 || s.cin % 64 == 32) ? s.cin % 64 : 0;
+  if (p.tail) {
+    const CUtensorMapSwizzle sw = p.tail == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+    cuuint64_t gdim[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
+    cuuint64_t gstr[3] = {(cuuint64_t)s.in_cs * 2, (cuuint64_t)s.in_cs * 2 * s.w, (cuuint64_t)s.in_cs * 2 * s.w * s.h};
+    cuuint32_t box[4] = {(cuuint32_t)p.tail, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + s.kh - 1), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tm_a2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(s.in), gdim, gstr, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t ktot = (cuuint64_t)s.kw * s.kh * s.cin;
+    cuuint64_t gdim2[2] = {ktot, (cuuint64_t)s.cout_pad};
+    cuuint64_t gstr2[1] = {ktot * 2};
+    cuuint32_t box2[2] = {(cuuint32_t)p.tail, (cuuint32_t)(s.cout_pad < kMTile ? s.cout_pad : kMTile)};
+    CUresult r2 = enc(&p.tm_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(s.wpacked), gdim2,
+                      gstr2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+      set_error("conv_plan: cuTensorMapEncodeTiled(tail %d) failed with %d / %d", p.tail, (int)r, (int)r2);
+      return MVLM_E_CUDA;
+    }
+  }
   p.tiles_x = ceil_div(s.w, kTileW);
   p.tiles_y = ceil_div(s.h, kTileH);
   p.n_nt = ceil_div(s.cout_pad, kMTile);
@@ -552,7 +599,7 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   p.debug_mode = g_debug_mode;
   const ConvEpilogue& e = p.e;
   const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
-                (e.out_post ? F_POST : 0) | ((e.out_f32 || e.argmax_keys) ? F_HEAD : 0);
+                (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0);
   switch (f) {
     // the combinations the network plan uses (hourglass.cu)
     case F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);  // RB conv1/2
@@ -562,7 +609,9 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
     case F_RAW: return launch_t<F_RAW>(p, stream);                                                      // resample, conv6/10
     case F_PRE: return launch_t<F_PRE>(p, stream);                                                      // conv5, conv9
     case F_RES1 | F_RES2 | F_RAW | F_POST: return launch_t<F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);  // conv7
-    case F_HEAD: return launch_t<F_HEAD>(p, stream);                                                    // conv11 phases
+    case F_ARGMAX: return launch_t<F_ARGMAX>(p, stream);                                                // conv11 phases
+    case F_F32: return launch_t<F_F32>(p, stream);
+    case F_F32 | F_ARGMAX: return launch_t<F_F32 | F_ARGMAX>(p, stream);
     case F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
       return launch_t<F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
   }

@@ -58,8 +58,11 @@ struct ConvShape {
 };
 
 struct alignas(64) ConvParams {
-  CUtensorMap tm_a;
-  CUtensorMap tm_b;
+  CUtensorMap tm_a;   // activations, 64-channel chunks (SWIZZLE_128B)
+  CUtensorMap tm_b;   // weights,     64-channel chunks (SWIZZLE_128B)
+  CUtensorMap tm_a2;  // tail chunk of `tail` (16 | 32) channels: SWIZZLE_32B | SWIZZLE_64B boxes
+  CUtensorMap tm_b2;
+  int tail;           // cin % 64 if it is 16 or 32, else 0 (a 48-wide tail uses a zero-filled 64-wide box)
   ConvShape s;
   ConvEpilogue e;
   int tiles_x, tiles_y, n_nt, total_tiles;

@@ -20,7 +20,15 @@ big = torch.zeros((v, h, h, 256), device="cuda", dtype=torch.bfloat16)
 act = torch.zeros((v, h, h, max(cout, 64)), device="cuda", dtype=torch.bfloat16)
 s = torch.ones(cout, device="cuda")
 t = torch.zeros(cout, device="cuda")
-kw = dict(out_raw=(big, 0)) if epi == "raw" else dict(pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
+keys = torch.zeros((v * cout,), device="cuda", dtype=torch.int64)
+if epi == "raw":
+    kw = dict(out_raw=(big, 0))
+elif epi == "head":
+    kw = dict(argmax_keys=keys, cout_real=cout - 7, up=(2, 2, 0, 1), y_off0=-1, x_off0=0)
+elif epi == "res":
+    kw = dict(res1=(big, 0), out_raw=(big, 0))
+else:
+    kw = dict(pre=(s, t, act, 0), res1=(big, 0), out_raw=(big, 0), post=(s, t, big, 0))
 for _ in range(3):
     ops.conv2d_bf16(x, wp, n_tile=nt, kh=k, kw=k, **kw)
 torch.cuda.synchronize()
