@@ -109,13 +109,13 @@ class Pipeline(abc.ABC, TimeMixin):
         dmesh = r.upload(mesh)
         out = r.render_device(dmesh, transforms)
         peaks = p.predict_landmarks_device(out["u8"])
-        starts, ends = e.estimate_landmark_lines_device(peaks, transforms, r.image_size[0])
+        starts, ends = e.estimate_landmark_lines_device(peaks, transforms, r.image_size[0], rot=r.rotations_device(transforms))
         if e.seed is not None:
-            draws = e.seeded_draws(peaks.shape[0])
+            draws_d = e.seeded_draws_device(peaks.shape[0])
         else:
             # reference RNG replay needs the per-landmark line counts -> one small D2H of the peak values
             draws = e.reference_draws(peaks.cpu().numpy())
-        draws_d = torch.from_numpy(draws.view(np.int32)).to(self.device)
+            draws_d = torch.from_numpy(draws.view(np.int32)).to(self.device)
         lm, err, _ = e.estimate_landmarks_from_lines_device(peaks, starts, ends, draws_d)
         from .. import ops
 

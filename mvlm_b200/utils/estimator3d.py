@@ -35,9 +35,18 @@ class Estimator3D:
             transform_stack, img_size)
         return starts.cpu().numpy(), ends.cpu().numpy()
 
-    def estimate_landmark_lines_device(self, peaks: torch.Tensor, transform_stack: np.ndarray, img_size: int):
-        rot = torch.from_numpy(rotation_matrices(np.asarray(transform_stack)).reshape(-1, 9)).to(self.device)
+    def estimate_landmark_lines_device(self, peaks: torch.Tensor, transform_stack: np.ndarray, img_size: int, rot=None):
+        """`rot`: optional (V,9) float64 device tensor of the view rotations (the renderer caches it)."""
+        if rot is None:
+            rot = torch.from_numpy(rotation_matrices(np.asarray(transform_stack)).reshape(-1, 9)).to(self.device)
         return ops.rays_from_peaks(peaks, rot, img_size)
+
+    def seeded_draws_device(self, n_landmarks: int) -> torch.Tensor:
+        key = (self.seed, self.n_hypotheses, n_landmarks)
+        if getattr(self, "_draws_key", None) != key:
+            self._draws = torch.from_numpy(self.seeded_draws(n_landmarks).view(np.int32)).to(self.device)
+            self._draws_key = key
+        return self._draws
 
     # ---------------------------------------------------------------- hypothesis tables
     def _filter_counts(self, values: np.ndarray) -> np.ndarray:
