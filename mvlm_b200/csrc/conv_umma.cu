@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const ConvShape& s = p.s;
   const ConvEpilogue& e = p.e;
   const int n_chunks = (s.cin + 63) >> 6;
-  const int halo_rows = kTileH + s.kh - 1;
+  // maps of height <= 8 only ever populate 8 rows: a 10-row halo box (tensor map built accordingly)
+  const int halo_rows = (s.h <= 8 ? 8 : kTileH) + s.kh - 1;
   const uint32_t h_bytes = static_cast<uint32_t>(halo_rows) * kRowBytes;
   const int w_rows = s.cout_pad < kMTile ? s.cout_pad : kMTile;  // weight rows actually loaded per tile
   const uint32_t w_bytes = static_cast<uint32_t>(w_rows) * 128u;
@@ -341,18 +342,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         cur_img = tc.img;
       }
       // residual rows do not depend on the accumulator: fetch them while the MMAs of this tile still run
-      uint4 r1[8][2];
-      if ((F & F_RES1) && grp_active && rows_active) {
-        const __nv_bfloat16* rp = e.res1 + e.res1_co + c0;
+      // (all 8 rows when there is one residual, 4 + 4 rows when there are two: register budget)
+      constexpr int kPref = (F & F_RES2) ? 4 : 8;
+      uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2];
+      auto prefetch = [&](int r_begin) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int q = 0; q < kPref; ++q) {
+          const int r = r_begin + q;
           if (r < rows_per_warp && y_first + r < s.h) {
             const uint32_t pix = pix0 + r * s.w;
-            if (va) r1[r][0] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(pix * e.res1_cs));
-            if (vb) r1[r][1] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>((pix + 8) * e.res1_cs));
+            if (F & F_RES1) {
+              const __nv_bfloat16* rp = e.res1 + e.res1_co + c0;
+              if (va) r1[q][0] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(pix * e.res1_cs));
+              if (vb) r1[q][1] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>((pix + 8) * e.res1_cs));
+            }
+            if (F & F_RES2) {
+              const __nv_bfloat16* rp = e.res2 + e.res2_co + c0;
+              if (va) r2[q][0] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(pix * e.res2_cs));
+              if (vb) r2[q][1] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>((pix + 8) * e.res2_cs));
+            }
           }
         }
-      }
+      };
+      if ((F & (F_RES1 | F_RES2)) && grp_active && rows_active) prefetch(0);
       // per-channel parameters of my 8 channels (pixel-major role) and my channel (channel-major role)
       float pre_s[8], pre_t[8], post_s[8], post_t[8];
       if (F & F_PRE) { lds8(ep->pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep->pre_t + (ch_ok ? c0 : 0), pre_t); }
@@ -371,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             const int y = y_first + r;
             ptx::tmem_ld_wait();
             if (r + 1 < rows_per_warp) ptx::tmem_ld16(taddr + (r + 1) * 16, v[(r + 1) & 1]);  // next row in flight
+            if ((F & F_RES2) && r == kPref) prefetch(kPref);  // rows 0..3 are consumed: fetch rows 4..7
             const uint32_t(&vr)[16] = v[r & 1];
             if (y < s.h) {
               if (F & F_HEAD) {
@@ -421,9 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], pre_s[j], pre_t[j]), 0.f);
                     *reinterpret_cast<uint4*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(px * e.pre_cs)) = pack8(g);
                   }
-                  if (F & F_RES1) add8(r1[r][i], f);
-                  if (F & F_RES2)
-                    add8(*reinterpret_cast<const uint4*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(px * e.res2_cs)), f);
+                  if (F & F_RES1) add8(r1[r % kPref][i], f);
+                  if (F & F_RES2) add8(r2[r % kPref][i], f);
                   if (F & F_RAW)
                     *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(px * e.raw_cs)) = pack8(f);
                   if (F & F_POST) {
@@ -531,7 +543,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     cuuint64_t gdim[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
     cuuint64_t gstr[3] = {(cuuint64_t)s.in_cs * 2, (cuuint64_t)s.in_cs * 2 * s.w,
                           (cuuint64_t)s.in_cs * 2 * s.w * s.h};
-    cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + s.kh - 1), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)((s.h <= 8 ? 8 : kTileH) + s.kh - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(s.in), gdim, gstr,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -563,7 +575,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     const CUtensorMapSwizzle sw = p.tail == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t gdim[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
     cuuint64_t gstr[3] = {(cuuint64_t)s.in_cs * 2, (cuuint64_t)s.in_cs * 2 * s.w, (cuuint64_t)s.in_cs * 2 * s.w * s.h};
-    cuuint32_t box[4] = {(cuuint32_t)p.tail, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + s.kh - 1), 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.tail, (cuuint32_t)kTileW, (cuuint32_t)((s.h <= 8 ? 8 : kTileH) + s.kh - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tm_a2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(s.in), gdim, gstr, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
