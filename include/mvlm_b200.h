@@ -62,6 +62,8 @@ typedef struct mvlm_conv_args {
   unsigned long long* argmax_keys; /* [n*cout_real], see mvlm_peaks_from_keys */
   int cout_real;
   int up_sy, up_sx, up_py, up_px;
+  const float* mid_scale; /* optional: v = relu(v*mid_scale+mid_shift) right after the bias */
+  const float* mid_shift;
 } mvlm_conv_args;
 
 int mvlm_conv2d_bf16(const mvlm_conv_args* args, void* stream);

@@ -34,6 +34,7 @@ class ConvArgs(C.Structure):
         ("out_f32", C.c_void_p), ("argmax_keys", C.c_void_p),
         ("cout_real", C.c_int),
         ("up_sy", C.c_int), ("up_sx", C.c_int), ("up_py", C.c_int), ("up_px", C.c_int),
+        ("mid_scale", C.c_void_p), ("mid_shift", C.c_void_p),
     ]
 
 

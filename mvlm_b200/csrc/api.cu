@@ -67,6 +67,7 @@ int mvlm_conv2d_bf16(const mvlm_conv_args* a, void* stream) {
   s.y_off0 = a->y_off0; s.x_off0 = a->x_off0;
   ConvEpilogue e;
   e.bias = a->bias;
+  e.mid_scale = a->mid_scale; e.mid_shift = a->mid_shift;
   e.pre_scale = a->pre_scale; e.pre_shift = a->pre_shift;
   e.out_pre = static_cast<__nv_bfloat16*>(a->out_pre); e.pre_cs = a->pre_cs; e.pre_co = a->pre_co;
   e.res1 = static_cast<const __nv_bfloat16*>(a->res1); e.res1_cs = a->res1_cs; e.res1_co = a->res1_co;

@@ -57,6 +57,8 @@ static_assert(sizeof(Barriers) <= 256, "barrier block");
 // Per-output-channel epilogue parameters staged once per CTA in shared memory.
 struct EpiParams {
   float bias[kMaxCout];
+  float mid_s[kMaxCout];
+  float mid_t[kMaxCout];
   float pre_s[kMaxCout];
   float pre_t[kMaxCout];
   float post_s[kMaxCout];
@@ -123,7 +125,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 
 // Epilogue feature flags (template parameter F): code for a feature is only generated when its bit is set,
 // which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
-enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64 };
+enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
+              F_MID = 128 /* affine + ReLU right after the bias */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 template <int F>
@@ -169,6 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
   for (int i = threadIdx.x; i < s.cout_pad; i += kThreads) {
     ep->bias[i] = e.bias ? e.bias[i] : 0.f;
+    ep->mid_s[i] = e.mid_scale ? e.mid_scale[i] : 1.f;
+    ep->mid_t[i] = e.mid_scale ? e.mid_shift[i] : 0.f;
     ep->pre_s[i] = e.out_pre ? e.pre_scale[i] : 0.f;
     ep->pre_t[i] = e.out_pre ? e.pre_shift[i] : 0.f;
     ep->post_s[i] = e.out_post ? e.post_scale[i] : 0.f;
@@ -370,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (F & F_PRE) { lds8(ep->pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep->pre_t + (ch_ok ? c0 : 0), pre_t); }
       if (F & F_POST) { lds8(ep->post_s + (ch_ok ? c0 : 0), post_s); lds8(ep->post_t + (ch_ok ? c0 : 0), post_t); }
       const float bias_c = ep->bias[c_lane < kMaxCout ? c_lane : 0];
+      const float mid_s_c = ep->mid_s[c_lane < kMaxCout ? c_lane : 0], mid_t_c = ep->mid_t[c_lane < kMaxCout ? c_lane : 0];
       timed_wait(&bar->t_full[acc], pacc, prof, w0);
       ptx::tc_fence_after();
       if (grp_active && rows_active) {
@@ -419,7 +425,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 // memory: row = pixel, 36-float pitch (conflict-free for the STS.32 and the LDS.128)
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) stage[j * 36 + lane] = __uint_as_float(vr[j]) + bias_c;
+                for (int j = 0; j < 16; ++j) {
+                  float f = __uint_as_float(vr[j]) + bias_c;
+                  if (F & F_MID) f = fmaxf(fmaf(f, mid_s_c, mid_t_c), 0.f);
+                  stage[j * 36 + lane] = f;
+                }
                 __syncwarp();
                 const uint32_t pix = pix0 + r * s.w;
 #pragma unroll
@@ -519,6 +529,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
                "conv_plan: cout_pad=%d must be <= 128 or a multiple of 128", s.cout_pad);
   MVLM_REQUIRE(s.cout_pad <= kMaxCout, "conv_plan: cout_pad=%d exceeds %d", s.cout_pad, kMaxCout);
   MVLM_REQUIRE(!e.argmax_keys || s.cout_pad <= kMTile, "conv_plan: fused arg-max needs cout_pad <= 128");
+  MVLM_REQUIRE(!e.mid_scale || (e.mid_shift && !e.out_f32 && !e.argmax_keys), "conv_plan: mid affine needs mid_shift and bf16 outputs");
   MVLM_REQUIRE(!((e.argmax_keys || e.out_f32) && (e.res1 || e.res2 || e.out_pre || e.out_raw || e.out_post)),
                "conv_plan: fp32 / arg-max outputs cannot be combined with bf16 outputs or residual inputs");
   {
@@ -611,7 +622,8 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   p.debug_mode = g_debug_mode;
   const ConvEpilogue& e = p.e;
   const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
-                (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0);
+                (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0) |
+                (e.mid_scale ? F_MID : 0);
   switch (f) {
     // the combinations the network plan uses (hourglass.cu)
     case F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);  // RB conv1/2
@@ -624,8 +636,11 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
     case F_ARGMAX: return launch_t<F_ARGMAX>(p, stream);                                                // conv11 phases
     case F_F32: return launch_t<F_F32>(p, stream);
     case F_F32 | F_ARGMAX: return launch_t<F_F32 | F_ARGMAX>(p, stream);
+    case F_MID | F_PRE | F_POST: return launch_t<F_MID | F_PRE | F_POST>(p, stream);                    // stem (conv1)
     case F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
       return launch_t<F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
+    case F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
+      return launch_t<F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
   }
   set_error("conv_launch: unsupported epilogue combination 0x%x", f);
   return MVLM_E_UNSUPPORTED;

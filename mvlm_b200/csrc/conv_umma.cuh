@@ -19,6 +19,9 @@ namespace mvlm {
 
 struct ConvEpilogue {
   const float* bias = nullptr;  // [cout_pad] fp32, added first
+  // optional: v = relu(v*mid_scale+mid_shift) right after the bias (the stem's bn1+ReLU, paulsenpredictor.py:406-407)
+  const float* mid_scale = nullptr;
+  const float* mid_shift = nullptr;
   // act_pre = relu(v*pre_scale+pre_shift), v = acc+bias (BEFORE the residuals)
   const float* pre_scale = nullptr;
   const float* pre_shift = nullptr;

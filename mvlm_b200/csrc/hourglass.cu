@@ -75,6 +75,25 @@ __global__ void pack_phase_weight_kernel(const float* __restrict__ w, int cout, 
   }
 }
 
+// conv1.weight fp32 (co,cin,3,3) -> [co_pad][kx][ky][16] bf16 with the weights in channels 0..cin-1 (applied to
+// the hi halves of the image) and again in 4..4+cin-1 (lo halves), see stem.cu
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, int cout, int cin, int cout_pad,
+                                        __nv_bfloat16* __restrict__ out) {
+  const int total = cout_pad * 9 * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ch = i % 16;
+    int r = i / 16;
+    const int ky = r % 3;
+    r /= 3;
+    const int kx = r % 3;
+    const int co = r / 3;
+    const int ci = ch < 4 ? ch : (ch < 8 ? ch - 4 : -1);
+    float v = 0.f;
+    if (co < cout && ci >= 0 && ci < cin) v = w[((co * cin + ci) * 3 + ky) * 3 + kx];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void pad_bias_kernel(const float* b, int n, int n_pad, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) out[i] = i < n ? b[i] : 0.f;
@@ -342,30 +361,40 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
   int rc;
   const int F = 256, h2 = h / 2, w2 = w / 2;
 
-  // ---- stem (:405-407) + conv2 block at full resolution (:410)
+  // ---- stem (:405-407): image -> hi/lo bf16 staging, then conv1 on the tensor cores with the fused
+  //      bias -> bn1+ReLU -> {conv2.bn1, conv2.resample.0} BatchNorm+ReLU epilogue; conv2 block (:410)
   T a_c2 = alloc(h, w, 64), ar_c2 = alloc(h, w, 64);
+  T img16 = alloc(h, w, 16);
   {
     NetOp op;
     op.kind = NetOp::STEM;
-    StemArgs& st = op.stem;
-    st.n = V_; st.h = h; st.w = w; st.cin = cin;
-    st.out_a = a_c2.p; st.out_b = ar_c2.p;
-    if (!dry_) {
-      auto fw = sd_->find("conv1.weight"), fb = sd_->find("conv1.bias");
-      MVLM_REQUIRE(fw != sd_->end() && fb != sd_->end(), "hourglass: missing conv1.weight/bias");
-      // own copies: the caller's state_dict tensors need not outlive create()
-      float* wcopy = nullptr;
-      MVLM_CHECK_CUDA(cudaMalloc(&wcopy, sizeof(float) * (64 * cin * 9 + 64)));
-      owned_.push_back(wcopy);
-      MVLM_CHECK_CUDA(cudaMemcpy(wcopy, fw->second, sizeof(float) * 64 * cin * 9, cudaMemcpyDeviceToDevice));
-      MVLM_CHECK_CUDA(cudaMemcpy(wcopy + 64 * cin * 9, fb->second, sizeof(float) * 64, cudaMemcpyDeviceToDevice));
-      st.w_oihw = wcopy; st.bias = wcopy + 64 * cin * 9;
-      if ((rc = bn("bn1", 64, &st.s0, &st.t0))) return rc;
-      if ((rc = bn("conv2.bn1", 64, &st.sa, &st.ta))) return rc;
-      if ((rc = bn("conv2.resample.0", 64, &st.sb, &st.tb))) return rc;
-    }
-    flops_ += 2.0 * 64 * cin * 9 * h * w;
+    op.out_raw = img16.p; op.h = h; op.w = w; op.c = cin;
     ops_.push_back(op);
+    flops_ += 2.0 * 64 * cin * 9 * h * w;
+    NetOp cv;
+    cv.kind = NetOp::CONV;
+    cv.tag = "conv1";
+    if (!dry_) {
+      auto fw = sd_->find("conv1.weight");
+      MVLM_REQUIRE(fw != sd_->end(), "hourglass: missing conv1.weight");
+      __nv_bfloat16* wp = nullptr;
+      MVLM_CHECK_CUDA(cudaMalloc(&wp, sizeof(__nv_bfloat16) * 64 * 9 * 16));
+      owned_.push_back(wp);
+      pack_stem_weight_kernel<<<36, 256>>>(fw->second, 64, cin, 64, wp);
+      MVLM_CHECK_CUDA(cudaGetLastError());
+      ConvShape s;
+      s.in = img16.p; s.n = V_; s.h = h; s.w = w; s.cin = 16; s.in_cs = 16;
+      s.wpacked = wp; s.cout_pad = 64; s.n_tile = 64; s.kh = 3; s.kw = 3; s.y_off0 = -1; s.x_off0 = -1;
+      ConvEpilogue e;
+      if ((rc = bias("conv1.bias", 64, 64, &e.bias))) return rc;
+      if ((rc = bn("bn1", 64, &e.mid_scale, &e.mid_shift))) return rc;
+      if ((rc = bn("conv2.bn1", 64, &e.pre_scale, &e.pre_shift))) return rc;
+      if ((rc = bn("conv2.resample.0", 64, &e.post_scale, &e.post_shift))) return rc;
+      e.out_pre = a_c2.p; e.pre_cs = 64; e.pre_co = 0;
+      e.out_post = ar_c2.p; e.post_cs = 64; e.post_co = 0;
+      if ((rc = conv_plan(s, e, &cv.conv))) return rc;
+    }
+    ops_.push_back(cv);
   }
   T none, y2, y3, r3, a3, a4, a_h1, ar4;
   if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, nullptr, nullptr, &y2))) return rc;
@@ -488,12 +517,9 @@ int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, flo
   for (NetOp& op : ops_) {
     int rc = MVLM_OK;
     switch (op.kind) {
-      case NetOp::STEM: {
-        StemArgs st = op.stem;
-        st.img_u8 = img_u8; st.img_f32 = img_f32;
-        rc = stem_launch(st, stream);
+      case NetOp::STEM:
+        rc = image_to_hilo16(img_u8, img_f32, op.c, static_cast<size_t>(V_) * op.h * op.w, op.out_raw, stream);
         break;
-      }
       case NetOp::CONV:
         if (op.is_head) {
           ConvParams p = op.conv;

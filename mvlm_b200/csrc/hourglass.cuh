@@ -10,7 +10,7 @@
 namespace mvlm {
 
 struct NetOp {
-  enum Kind { CONV, POOL, UPADD, BNRELU, STEM, MEMSET, PEAKS } kind;
+  enum Kind { CONV, POOL, UPADD, BNRELU, STEM, MEMSET, PEAKS } kind;  // STEM = image -> hi/lo bf16 staging
   ConvParams conv;  // CONV
   // eltwise / memset
   const __nv_bfloat16* in0 = nullptr;
@@ -20,7 +20,6 @@ struct NetOp {
   const float* scale = nullptr;
   const float* shift = nullptr;
   int h = 0, w = 0, c = 0;
-  StemArgs stem;
   void* ptr = nullptr;
   size_t bytes = 0;
   bool is_head = false;  // conv11 phase: out_f32 patched per forward call

@@ -70,18 +70,8 @@ int upadd_act(const __nv_bfloat16* low, const __nv_bfloat16* skip, int n, int h,
 int bn_relu(const __nv_bfloat16* in, size_t npix, int c, const float* scale, const float* shift,
             __nv_bfloat16* out_act, cudaStream_t s);
 
-struct StemArgs {
-  const unsigned char* img_u8 = nullptr;  // (N,H,W,4) u8, value/255 -> fp32, or
-  const float* img_f32 = nullptr;         // (N,H,W,cin) fp32
-  int n = 0, h = 0, w = 0, cin = 0;
-  const float* w_oihw = nullptr;          // (64,cin,3,3) fp32
-  const float* bias = nullptr;            // (64)
-  const float* s0 = nullptr; const float* t0 = nullptr;  // bn1 (applied to conv1+bias, then ReLU)
-  const float* sa = nullptr; const float* ta = nullptr;  // consumer BN a  -> out_a
-  const float* sb = nullptr; const float* tb = nullptr;  // consumer BN b  -> out_b
-  __nv_bfloat16* out_a = nullptr;         // (N,H,W,64)
-  __nv_bfloat16* out_b = nullptr;         // (N,H,W,64)
-};
-int stem_launch(const StemArgs& a, cudaStream_t s);
+// u8 (N,H,W,4) [value/255] or fp32 (N,H,W,cin) image -> bf16 (N,H,W,16): channels 0..3 = hi, 4..7 = lo, rest 0
+int image_to_hilo16(const unsigned char* u8, const float* f32, int cin, size_t npix, __nv_bfloat16* out,
+                    cudaStream_t s);
 
 }  // namespace mvlm

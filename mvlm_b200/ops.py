@@ -25,7 +25,7 @@ def pack_conv_weight(w_oihw: torch.Tensor, cout_pad: int, cin_pad: int) -> torch
 
 def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = None, n_tile: int,
                 kh: int = 3, kw: int = 3, y_off0: int | None = None, x_off0: int | None = None,
-                bias=None, pre=None, res1=None, res2=None, out_raw=None, post=None,
+                bias=None, mid=None, pre=None, res1=None, res2=None, out_raw=None, post=None,
                 out_f32=None, argmax_keys=None, cout_real: int | None = None,
                 up=(1, 1, 0, 0)) -> None:
     """One fused conv launch.
@@ -46,6 +46,8 @@ def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = Non
     a.y_off0 = -(kh // 2) if y_off0 is None else y_off0
     a.x_off0 = -(kw // 2) if x_off0 is None else x_off0
     a.bias = ptr(bias)
+    if mid is not None:
+        a.mid_scale, a.mid_shift = ptr(mid[0]), ptr(mid[1])
     if pre is not None:
         a.pre_scale, a.pre_shift, a.out_pre = ptr(pre[0]), ptr(pre[1]), ptr(pre[2])
         a.pre_cs, a.pre_co = pre[2].shape[-1], pre[3]

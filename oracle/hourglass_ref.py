@@ -107,8 +107,9 @@ class HourglassOracle:
         sd = self.sd
         with torch.no_grad():
             inter = {}
-            # stem (:405-407) is computed in fp32 on both sides (never quantised)
-            x0 = torch.relu(self._bn_apply(F.conv2d(img_nchw.float(), sd["conv1.weight"], sd["conv1.bias"], padding=1), "bn1"))
+            # stem (:405-407): the CUDA path keeps the image to ~2^-17 (hi/lo bf16 split) and rounds only the
+            # conv1 weights to bf16, like every other layer; x0 itself is never stored
+            x0 = torch.relu(self._bn_apply(F.conv2d(img_nchw.float(), self.q(sd["conv1.weight"]), sd["conv1.bias"], padding=1), "bn1"))
             a = self.act(x0, "conv2.bn1")
             # conv2 block has a resample skip that consumes x0 through its own BN
             y2, _ = self._rb_from_fp32(x0, a, "conv2")
