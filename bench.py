@@ -239,7 +239,7 @@ def run_ours(args):
         if record:
             ev["raster"][1].record()
             ev["cnn"][0].record()
-        peaks, _ = net.forward(u8)
+        peaks, _ = net.forward(u8, graph=True)
         if record:
             ev["cnn"][1].record()
             ev["tail"][0].record()

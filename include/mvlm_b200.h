@@ -64,6 +64,7 @@ typedef struct mvlm_conv_args {
   int up_sy, up_sx, up_py, up_px;
   const float* mid_scale; /* optional: v = relu(v*mid_scale+mid_shift) right after the bias */
   const float* mid_shift;
+  int pool2;              /* 1: out_raw / out_post are the 2x2 max-pooled (half resolution) tensors */
 } mvlm_conv_args;
 
 int mvlm_conv2d_bf16(const mvlm_conv_args* args, void* stream);
@@ -115,6 +116,10 @@ int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, int
                           size_t workspace_bytes, mvlm_hourglass** out);
 int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                            float* out_heatmaps, float* out_peaks, void* stream);
+/* Same result as mvlm_hourglass_forward; the ~175 launches are captured into a CUDA graph per distinct
+ * (img, out) pointer tuple on first use and replayed afterwards (buffers must stay valid and unchanged). */
+int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
+                                 float* out_heatmaps, float* out_peaks, void* stream);
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net);
 /* layer-wise parity probes: "r3", "hg1", "sum_temp", "x10" -> NHWC bf16 tensor in the workspace */
 int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c);

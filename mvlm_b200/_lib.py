@@ -35,6 +35,7 @@ class ConvArgs(C.Structure):
         ("cout_real", C.c_int),
         ("up_sy", C.c_int), ("up_sx", C.c_int), ("up_py", C.c_int), ("up_px", C.c_int),
         ("mid_scale", C.c_void_p), ("mid_shift", C.c_void_p),
+        ("pool2", C.c_int),
     ]
 
 
@@ -71,6 +72,7 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_hourglass_create": ([C.POINTER(C.c_char_p), C.POINTER(vp), i32, i32, i32, i32, i32, i32, vp,
                                    C.c_size_t, C.POINTER(vp)], i32),
         "mvlm_hourglass_forward": ([vp, vp, vp, vp, vp, vp], i32),
+        "mvlm_hourglass_forward_graph": ([vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_num_launches": ([vp], i32),
         "mvlm_hourglass_probe": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
         "mvlm_hourglass_destroy": ([vp], None),

@@ -68,6 +68,7 @@ int mvlm_conv2d_bf16(const mvlm_conv_args* a, void* stream) {
   ConvEpilogue e;
   e.bias = a->bias;
   e.mid_scale = a->mid_scale; e.mid_shift = a->mid_shift;
+  e.pool2 = a->pool2 != 0;
   e.pre_scale = a->pre_scale; e.pre_shift = a->pre_shift;
   e.out_pre = static_cast<__nv_bfloat16*>(a->out_pre); e.pre_cs = a->pre_cs; e.pre_co = a->pre_co;
   e.res1 = static_cast<const __nv_bfloat16*>(a->res1); e.res1_cs = a->res1_cs; e.res1_co = a->res1_co;
@@ -149,6 +150,12 @@ int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const flo
                            float* out_peaks, void* stream) {
   MVLM_REQUIRE(net, "mvlm_hourglass_forward: null handle");
   return net->net.forward(img_u8, img_f32, out_heatmaps, out_peaks, static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
+                                 float* out_heatmaps, float* out_peaks, void* stream) {
+  MVLM_REQUIRE(net, "mvlm_hourglass_forward_graph: null handle");
+  return net->net.forward_graph(img_u8, img_f32, out_heatmaps, out_peaks, static_cast<cudaStream_t>(stream));
 }
 
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net) { return net ? net->net.n_ops() : 0; }

@@ -95,6 +95,15 @@ __device__ __forceinline__ void add8(const uint4& q, float (&f)[8]) {
     f[2 * j + 1] += t.y;
   }
 }
+__device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pr[j] = __hmax2(pa[j], pb[j]);
+  return r;
+}
 __device__ __forceinline__ void lds8(const float* src, float (&v)[8]) {
   const float4 a = reinterpret_cast<const float4*>(src)[0];
   const float4 b = reinterpret_cast<const float4*>(src)[1];
@@ -126,7 +135,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 // Epilogue feature flags (template parameter F): code for a feature is only generated when its bit is set,
 // which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
 enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
-              F_MID = 128 /* affine + ReLU right after the bias */ };
+              F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 template <int F>
@@ -339,6 +348,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const bool va = ch_ok && xa < s.w, vb = ch_ok && xa + 8 < s.w;
       // element index of pixel (img, y_first, xa); 32-bit: pixel count x channel stride < 2^31 (checked in conv_plan)
       const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first) * s.w + xa;
+      // F_POOL: element index of the pooled pixel of (img, y_first, xa) in the half-resolution outputs
+      const uint32_t ppix0 = (static_cast<uint32_t>(tc.img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
+      uint4 pool_prev[2];
       if ((F & F_ARGMAX) && tc.img != cur_img) {
         if (cur_img >= 0 && best_hi != 0u && c_lane < e.cout_real)
           atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
@@ -434,25 +446,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 const uint32_t pix = pix0 + r * s.w;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                  if (!(i == 0 ? va : vb)) continue;
+                  const bool valid = i == 0 ? va : vb;
                   const uint32_t px = pix + 8 * i;
-                  float f[8];
-                  lds8(stage + (pj + 8 * i) * 36 + cq, f);
-                  if (F & F_PRE) {
-                    float g[8];
+                  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  if (valid) {
+                    lds8(stage + (pj + 8 * i) * 36 + cq, f);
+                    if (F & F_PRE) {
+                      float g[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], pre_s[j], pre_t[j]), 0.f);
-                    *reinterpret_cast<uint4*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(px * e.pre_cs)) = pack8(g);
+                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], pre_s[j], pre_t[j]), 0.f);
+                      *reinterpret_cast<uint4*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(px * e.pre_cs)) = pack8(g);
+                    }
+                    if (F & F_RES1) add8(r1[r % kPref][i], f);
+                    if (F & F_RES2) add8(r2[r % kPref][i], f);
                   }
-                  if (F & F_RES1) add8(r1[r % kPref][i], f);
-                  if (F & F_RES2) add8(r2[r % kPref][i], f);
-                  if (F & F_RAW)
-                    *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(px * e.raw_cs)) = pack8(f);
-                  if (F & F_POST) {
-                    float g[8];
+                  if (F & F_POOL) {
+                    // 2x2 max-pool of the bf16-rounded values: vertical partner = previous row (same lane),
+                    // horizontal partner = lane ^ 4 (pixel j ^ 1); shuffles run on all lanes
+                    const uint4 cur = pack8(f);
+                    if ((r & 1) == 0) {
+                      pool_prev[i] = cur;
+                    } else {
+                      uint4 m = max_bf16x8(pool_prev[i], cur);
+                      uint4 o;
+                      o.x = __shfl_xor_sync(0xffffffffu, m.x, 4);
+                      o.y = __shfl_xor_sync(0xffffffffu, m.y, 4);
+                      o.z = __shfl_xor_sync(0xffffffffu, m.z, 4);
+                      o.w = __shfl_xor_sync(0xffffffffu, m.w, 4);
+                      m = max_bf16x8(m, o);
+                      if (valid && (pj & 1) == 0) {
+                        const uint32_t pp = ppix0 + (r >> 1) * (s.w >> 1) + 4 * i;
+                        if (F & F_RAW)
+                          *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(pp * e.raw_cs)) = m;
+                        if (F & F_POST) {
+                          float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                          add8(m, g);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], post_s[j], post_t[j]), 0.f);
-                    *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(px * e.post_cs)) = pack8(g);
+                          for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(g[j], post_s[j], post_t[j]), 0.f);
+                          *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(pp * e.post_cs)) = pack8(g);
+                        }
+                      }
+                    }
+                  } else if (valid) {
+                    if (F & F_RAW)
+                      *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(px * e.raw_cs)) = pack8(f);
+                    if (F & F_POST) {
+                      float g[8];
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], post_s[j], post_t[j]), 0.f);
+                      *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(px * e.post_cs)) = pack8(g);
+                    }
                   }
                 }
               }
@@ -529,6 +572,8 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
                "conv_plan: cout_pad=%d must be <= 128 or a multiple of 128", s.cout_pad);
   MVLM_REQUIRE(s.cout_pad <= kMaxCout, "conv_plan: cout_pad=%d exceeds %d", s.cout_pad, kMaxCout);
   MVLM_REQUIRE(!e.argmax_keys || s.cout_pad <= kMTile, "conv_plan: fused arg-max needs cout_pad <= 128");
+  MVLM_REQUIRE(!e.pool2 || (s.h % 2 == 0 && s.w % 2 == 0 && (e.out_raw || e.out_post) && !e.out_f32 && !e.argmax_keys),
+               "conv_plan: pool2 needs even H, W and a bf16 raw/post output");
   MVLM_REQUIRE(!e.mid_scale || (e.mid_shift && !e.out_f32 && !e.argmax_keys), "conv_plan: mid affine needs mid_shift and bf16 outputs");
   MVLM_REQUIRE(!((e.argmax_keys || e.out_f32) && (e.res1 || e.res2 || e.out_pre || e.out_raw || e.out_post)),
                "conv_plan: fp32 / arg-max outputs cannot be combined with bf16 outputs or residual inputs");
@@ -623,7 +668,7 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   const ConvEpilogue& e = p.e;
   const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
                 (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0) |
-                (e.mid_scale ? F_MID : 0);
+                (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0);
   switch (f) {
     // the combinations the network plan uses (hourglass.cu)
     case F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);  // RB conv1/2
@@ -637,6 +682,9 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
     case F_F32: return launch_t<F_F32>(p, stream);
     case F_F32 | F_ARGMAX: return launch_t<F_F32 | F_ARGMAX>(p, stream);
     case F_MID | F_PRE | F_POST: return launch_t<F_MID | F_PRE | F_POST>(p, stream);                    // stem (conv1)
+    case F_POOL | F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_POOL | F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);
+    case F_POOL | F_RES1 | F_RAW | F_POST: return launch_t<F_POOL | F_RES1 | F_RAW | F_POST>(p, stream);
+    case F_POOL | F_RAW: return launch_t<F_POOL | F_RAW>(p, stream);
     case F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
       return launch_t<F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
     case F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:

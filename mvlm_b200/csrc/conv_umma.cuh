@@ -40,6 +40,9 @@ struct ConvEpilogue {
   const float* post_shift = nullptr;
   __nv_bfloat16* out_post = nullptr;
   int post_cs = 0, post_co = 0;
+  // pool2: out_raw / out_post are written at HALF resolution: the 2x2 max-pool (F.max_pool2d(x, 2),
+  // paulsenpredictor.py:411) of the bf16-rounded raw values, and relu(post_bn(pooled)); needs even H and W
+  bool pool2 = false;
   // fp32 NCHW output (N, cout_real, H*up_sy, W*up_sx) at pixel (y*sy+py, x*sx+px)
   float* out_f32 = nullptr;
   // fused per-(image, channel) arg-max keys, see peaks.cu (atomicMax on u64)

@@ -104,6 +104,7 @@ inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
 }  // namespace
 
 HourglassNet::~HourglassNet() {
+  for (auto& g : graphs_) cudaGraphExecDestroy(g.second);
   for (void* p : owned_) cudaFree(p);
 }
 
@@ -213,7 +214,7 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
 }
 
 int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act,
-                     T* y_out) {
+                     T* y_out, T* pool_raw) {
   const int h = a_in.h, w = a_in.w;
   T y = alloc(h, w, cout);
   T skip = x;
@@ -229,8 +230,9 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
   if (post_bn) {
     rc = bn(post_bn, cout, &ps, &pt);
     if (rc) return rc;
-    *post_act = alloc(h, w, cout);
+    *post_act = pool_raw ? alloc(h / 2, w / 2, cout) : alloc(h, w, cout);
   }
+  if (pool_raw) *pool_raw = alloc(h / 2, w / 2, cout);
   const int c1 = cout / 2, c2 = cout / 4;
   T a1 = scratch(h, w, c1 < 64 ? 64 : c1, 1);
   T a2 = scratch(h, w, c2 < 64 ? 64 : c2, 2);
@@ -249,7 +251,8 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
       e.out_pre = pres[i].p; e.pre_cs = pres[i].c; e.pre_co = 0;
     }
     e.res1 = skip.p; e.res1_cs = skip.c; e.res1_co = offs[i];
-    e.out_raw = y.p; e.raw_cs = cout; e.raw_co = offs[i];
+    e.out_raw = pool_raw ? pool_raw->p : y.p; e.raw_cs = cout; e.raw_co = offs[i];
+    e.pool2 = pool_raw != nullptr;
     if (post_bn) {
       e.post_scale = dry_ ? nullptr : ps + offs[i];
       e.post_shift = dry_ ? nullptr : pt + offs[i];
@@ -397,11 +400,9 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
     ops_.push_back(cv);
   }
   T none, y2, y3, r3, a3, a4, a_h1, ar4;
-  if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, nullptr, nullptr, &y2))) return rc;
-  // ---- maxpool (:411), conv3, conv4 (:412-413)
-  T x1 = alloc(h2, w2, 128);
-  a3 = alloc(h2, w2, 128);
-  if ((rc = emit_pool(y2, x1, "conv3.bn1", a3))) return rc;
+  // conv2 block: its output is only consumed through the max-pool (:411) -> pooled outputs straight from the epilogues
+  T x1;
+  if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, "conv3.bn1", &a3, &y2, &x1))) return rc;
   if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3))) return rc;
   ar4 = alloc(h2, w2, 128);
   {
@@ -548,6 +549,44 @@ int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, flo
     if (rc != MVLM_OK) return rc;
   }
   return MVLM_OK;
+}
+
+int HourglassNet::forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps,
+                                float* out_peaks, cudaStream_t stream) {
+  for (auto& g : graphs_) {
+    if (g.first.a == img_u8 && g.first.b == img_f32 && g.first.c == out_heatmaps && g.first.d == out_peaks) {
+      MVLM_CHECK_CUDA(cudaGraphLaunch(g.second, stream));
+      count_launch(static_cast<int>(ops_.size()));
+      return MVLM_OK;
+    }
+  }
+  // first call with these buffers: warm every kernel attribute outside capture, then capture
+  int rc = forward(img_u8, img_f32, out_heatmaps, out_peaks, stream);
+  if (rc != MVLM_OK) return rc;
+  if (graphs_.size() >= 8) return MVLM_OK;  // too many distinct buffer sets: stay on plain launches
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return MVLM_OK;
+  }
+  rc = forward(img_u8, img_f32, out_heatmaps, out_peaks, stream);
+  const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+  if (rc != MVLM_OK || ce != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess && exec) {
+    graphs_.push_back({GraphKey{img_u8, img_f32, out_heatmaps, out_peaks}, exec});
+    // the captured pass did not execute: run it once through the graph so that this call has its result
+    MVLM_CHECK_CUDA(cudaGraphLaunch(exec, stream));
+  } else {
+    cudaGetLastError();
+    rc = forward(img_u8, img_f32, out_heatmaps, out_peaks, stream);
+  }
+  cudaGraphDestroy(graph);
+  return rc;
 }
 
 }  // namespace mvlm

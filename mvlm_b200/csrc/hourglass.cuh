@@ -35,6 +35,10 @@ class HourglassNet {
             void* workspace, size_t workspace_bytes, bool dry);
   int forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
               cudaStream_t stream);
+  // Captures the launch sequence of forward() into a CUDA graph per distinct argument tuple and replays it
+  // (the plan is static: ~175 launches per call).  Falls back to plain launches if capture is unavailable.
+  int forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
+                    cudaStream_t stream);
 
   size_t workspace_needed() const { return ws_off_; }
   int n_views() const { return V_; }
@@ -58,7 +62,10 @@ class HourglassNet {
   int bias(const std::string& name, int cout, int cout_pad, const float** out);
   int emit_conv(const char* tag, T in, int cin, const std::string& wname, int cout, int cout_pad, int n_tile, int k,
                 ConvEpilogue e, bool with_bias);
-  int rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act, T* y_out);
+  // pool_raw != nullptr: the block output is only consumed through a 2x2 max-pool (conv2 block, :410-411):
+  // the three convs write the pooled raw tensor and relu(post_bn(pooled)) directly; no full-resolution output
+  int rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act, T* y_out,
+         T* pool_raw = nullptr);
   int hourglass(const std::string& p, T x, T a_x, T* out);
   int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
   int emit_upadd(T low, T skip, T out_raw, const char* bn_name, T out_act);
@@ -74,6 +81,8 @@ class HourglassNet {
   std::vector<NetOp> ops_;
   unsigned long long* keys_ = nullptr;
   double flops_ = 0.0;
+  struct GraphKey { const void* a; const void* b; const void* c; const void* d; };
+  std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs_;
 };
 
 }  // namespace mvlm

@@ -27,7 +27,7 @@ def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = Non
                 kh: int = 3, kw: int = 3, y_off0: int | None = None, x_off0: int | None = None,
                 bias=None, mid=None, pre=None, res1=None, res2=None, out_raw=None, post=None,
                 out_f32=None, argmax_keys=None, cout_real: int | None = None,
-                up=(1, 1, 0, 0)) -> None:
+                up=(1, 1, 0, 0), pool2: bool = False) -> None:
     """One fused conv launch.
 
     x          : (N,H,W,Cs) bf16; the first `cin` channels are read.
@@ -64,6 +64,7 @@ def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = Non
     a.argmax_keys = ptr(argmax_keys)
     a.cout_real = cout_real if cout_real is not None else wpacked.shape[0]
     a.up_sy, a.up_sx, a.up_py, a.up_px = up
+    a.pool2 = 1 if pool2 else 0
     check(lib.mvlm_conv2d_bf16(C.byref(a), cur_stream()), "mvlm_conv2d_bf16")
 
 
@@ -120,8 +121,10 @@ class Hourglass:
         self.flops_per_view = lib.mvlm_hourglass_flops_per_view(n_landmarks, cin, h, w)
         self.num_launches = lib.mvlm_hourglass_num_launches(handle)
 
-    def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True):
-        """img: (V,H,W,4) uint8 (rasteriser output) or (V,H,W,cin) float32; returns (peaks (L,V,3) f32, heatmaps|None)."""
+    def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False):
+        """img: (V,H,W,4) uint8 (rasteriser output) or (V,H,W,cin) float32; returns (peaks (L,V,3) f32, heatmaps|None).
+        graph=True replays a CUDA graph of the launch sequence; the returned peaks tensor is then a persistent
+        buffer owned by this object (overwritten by the next call)."""
         lib = _lib.load()
         assert img.shape[0] == self.n_views and img.shape[1] == self.h and img.shape[2] == self.w
         u8 = img if img.dtype == torch.uint8 else None
@@ -130,6 +133,12 @@ class Hourglass:
             raise TypeError("img must be uint8 (V,H,W,4) or float32 (V,H,W,cin)")
         if f32 is not None and f32.shape[3] != self.cin:
             raise ValueError(f"expected {self.cin} channels, got {f32.shape[3]}")
+        if graph and want_peaks and not want_heatmaps:
+            if getattr(self, "_peaks_buf", None) is None:
+                self._peaks_buf = torch.empty((self.n_landmarks, self.n_views, 3), dtype=torch.float32, device=self.device)
+            check(lib.mvlm_hourglass_forward_graph(self._h, ptr(u8), ptr(f32), None, ptr(self._peaks_buf), cur_stream()),
+                  "mvlm_hourglass_forward_graph")
+            return self._peaks_buf, None
         peaks = torch.empty((self.n_landmarks, self.n_views, 3), dtype=torch.float32, device=self.device) if want_peaks else None
         hm = torch.empty((self.n_views, self.n_landmarks, self.h, self.w), dtype=torch.float32, device=self.device) \
             if want_heatmaps else None

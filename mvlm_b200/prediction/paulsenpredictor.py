@@ -85,7 +85,8 @@ class PaulsenModel(Predictor2D):
         v, h, w = img.shape[0], img.shape[1], img.shape[2]
         net = self.network(v, h, w)
         if self.selection_method == "simple":
-            peaks, _ = net.forward(img, want_heatmaps=False, want_peaks=True)
+            # the rasteriser's persistent u8 image has a stable address: replay the captured CUDA graph
+            peaks, _ = net.forward(img, want_heatmaps=False, want_peaks=True, graph=img.dtype == torch.uint8)
             return peaks
         if self.selection_method == "moment":
             _, hm = net.forward(img, want_heatmaps=True, want_peaks=False)

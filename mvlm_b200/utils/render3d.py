@@ -124,8 +124,15 @@ class ObjRenderer3D:
         """All views in one launch pair; returns the dict of device tensors of ops.raster_multiview."""
         rot = self.rotations_device(np.asarray(transform_stack))
         h, w = self.image_size[0], self.image_size[1]
+        # persistent z-buffer / u8 image (overwritten by the next render): stable pointers let the CNN replay
+        # its CUDA graph, and no allocation happens per scan
+        key = (rot.shape[0], h, w)
+        if getattr(self, "_buf_key", None) != key:
+            self._zbuf = torch.empty((rot.shape[0], h, w), dtype=torch.int64, device=self.device)
+            self._u8 = torch.empty((rot.shape[0], h, w, 4), dtype=torch.uint8, device=self.device)
+            self._buf_key = key
         return ops.raster_multiview(dmesh.verts, dmesh.uvs, dmesh.tris, dmesh.tex, rot, h, w, self.channel_mode,
-                                    want_f32=want_f32, want_tri=want_tri, want_z=want_z)
+                                    want_f32=want_f32, want_tri=want_tri, want_z=want_z, zbuf=self._zbuf, out_u8=self._u8)
 
     # render3d.py:114-177
     def render_3d_multi_rgb_geometry_depth(self, transform_stack, file_name):

@@ -147,3 +147,28 @@ def test_conv_upsample_phase(lib):
     scale = ref.abs().max().item()
     # combined phase weights are rounded to bf16 after summation -> bf16-level difference
     assert (out - ref).abs().max().item() <= 1.5e-2 * scale
+
+
+def test_conv_fused_maxpool(lib):
+    """pool2 epilogue == F.max_pool2d of the bf16 raw output (+ BN+ReLU of the pooled values)."""
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    for (n, h, w, cin, cout) in ((2, 32, 32, 64, 64), (1, 48, 32, 64, 32), (2, 16, 32, 128, 128)):
+        g = torch.Generator(device="cuda").manual_seed(3 + cout)
+        x = torch.randn((n, h, w, cin), generator=g, device="cuda").to(torch.bfloat16)
+        wt = torch.randn((cout, cin, 3, 3), generator=g, device="cuda") / (cin * 9) ** 0.5
+        s2, t2 = (torch.randn((cout,), generator=g, device="cuda") for _ in range(2))
+        res = torch.randn((n, h, w, 256), generator=g, device="cuda").to(torch.bfloat16)
+        wp = ops.pack_conv_weight(wt, cout, cin)
+        full = torch.zeros((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+        ops.conv2d_bf16(x, wp, n_tile=cout, res1=(res, 16), out_raw=(full, 0))
+        praw = torch.zeros((n, h // 2, w // 2, 256), device="cuda", dtype=torch.bfloat16)
+        pact = torch.zeros((n, h // 2, w // 2, 256), device="cuda", dtype=torch.bfloat16)
+        ops.conv2d_bf16(x, wp, n_tile=cout, res1=(res, 16), out_raw=(praw, 32), post=(s2, t2, pact, 32), pool2=True)
+        torch.cuda.synchronize()
+        ref = F.max_pool2d(full.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        assert torch.equal(praw[..., 32:32 + cout].float(), ref)          # bit-exact: max of the same bf16 values
+        act = torch.relu(ref * s2 + t2).to(torch.bfloat16).float()
+        assert (pact[..., 32:32 + cout].float() - act).abs().max().item() <= act.abs().max().item() * 2.0 ** -7
+        assert (praw[..., :32] == 0).all() and (praw[..., 32 + cout:] == 0).all()
