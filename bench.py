@@ -32,6 +32,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_LANDMARKS = 73
+CNN_DRAM_BYTES_PER_STEP = 54.9e9  # measured with ncu, see profiles/r1_dram_per_launch.csv
 IMAGE_MODE = "RGB+depth"
 
 
@@ -184,7 +185,7 @@ def run_reference(args):
         "impl": "reference", "metric": "scans/sec", "value": val, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": len(secs), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, one scan",
+        "config": {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, one scan per step per GPU",
                    "n_landmarks": N_LANDMARKS, "ransac_hypotheses": args.hyp},
         "cpu_baseline": {"value": val, "unit": "scans/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} of {args.views} views for raster/CNN/peaks (scaled linearly), full size for rays/consensus/snap; "
@@ -328,7 +329,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "stages_ms": stage_ms,
             "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (CNN stage incl. its stem/pool/upsample glue launches)",
-                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum summed over the 164 CNN launches of one step
+                         # (ncu capture of this command, profiles/r1_dram_per_launch.csv: 32.5 GB read + 22.4 GB written)
+                         "traffic": CNN_DRAM_BYTES_PER_STEP if (args.views, args.size) == (100, 256) else None,
+                         "traffic_note": "bytes per step over all CNN launches; = %.0f%% of measured HBM peak at this step time" % (
+                             100 * CNN_DRAM_BYTES_PER_STEP / (stage_ms["cnn"] / 1e3) / 1e9 / pk["hbm_gbs"]),
                          "peak_source": f"{pk_kind} bf16_tflops_sustained", "flops_per_scan": flops_scan},
             "clocks": clocks,
         }
