@@ -16,9 +16,10 @@
 //   consensus_prepare     one block per landmark: np.quantile('linear', float32) threshold, strict
 //                         `>` mask, order-preserving compaction, per-line normal-equation terms
 //                         M_i = n n^T - I and M_i a_i, LSQ over all kept lines (the fallback).
-//   consensus_hypotheses  grid (L, splits): lines of the landmark staged in shared memory, one warp
-//                         per hypothesis (8-line LSQ -> distances to all lines -> ballot/popc inlier
-//                         count -> inlier refit -> score), warp-shuffle reductions throughout.
+//   consensus_hypotheses  grid (L, splits): lines of the landmark staged in shared memory, one THREAD
+//                         per hypothesis (8-line LSQ -> one pass over all lines: inlier test + count +
+//                         normal-equation sums -> inlier refit -> score pass), warp-shuffle + shared
+//                         memory reduction of the lexicographic (error, hypothesis) minimum.
 //   consensus_finalize    lexicographic (error, hypothesis) minimum over splits, fallbacks.
 #include "common.cuh"
 #include "stages.cuh"
@@ -27,7 +28,7 @@ namespace mvlm {
 
 namespace {
 
-constexpr int kLineDoubles = 15;  // a[3] b[3] M[6]={xx,yy,zz,xy,xz,yz} Ma[3]
+constexpr int kLineDoubles = 16;  // a[3] b[3] M[6]={xx,yy,zz,xy,xz,yz} Ma[3] |b-a|
 constexpr int kMaxViews = 1024;
 constexpr int kPartDoubles = 5;   // err, hyp, p[3]
 constexpr double kNoFit = 100000000.0;  // estimator3d.py:95
@@ -39,7 +40,8 @@ __device__ void sym3_pinv_solve(const double* S6, const double* c, double* p) {
   double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   for (int sweep = 0; sweep < 12; ++sweep) {
     const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-    if (off == 0.0) break;
+    const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-34 * diag) break;  // eigenvalues converged far below double rounding
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int pi = k == 2 ? 1 : 0;
@@ -88,10 +90,8 @@ __device__ __forceinline__ double line_sqdist(const double* p, const double* ln)
   const double ax = p[0] - ln[0], ay = p[1] - ln[1], az = p[2] - ln[2];
   const double bx = p[0] - ln[3], by = p[1] - ln[4], bz = p[2] - ln[5];
   const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-  const double dx = ln[3] - ln[0], dy = ln[4] - ln[1], dz = ln[5] - ln[2];
   const double top = sqrt((cx * cx + cy * cy) + cz * cz);
-  const double bot = sqrt((dx * dx + dy * dy) + dz * dz);
-  const double d = top / bot;
+  const double d = top / ln[15];  // |b-a| = np.linalg.norm(bottom), precomputed per line
   return d * d;
 }
 
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(256) consensus_prepare_kernel(ConsensusArgs g,
     ln[12] = (a[0] * mxx + a[1] * mxy) + a[2] * mxz;
     ln[13] = (a[0] * mxy + a[1] * myy) + a[2] * myz;
     ln[14] = (a[0] * mxz + a[1] * myz) + a[2] * mzz;
+    ln[15] = nrm;
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] += ln[6 + k];
   }
@@ -214,8 +215,11 @@ __global__ void __launch_bounds__(256) consensus_prepare_kernel(ConsensusArgs g,
   }
 }
 
+// One THREAD per hypothesis (the lines of the landmark are broadcast reads from shared memory):
+//   8-line LSQ -> one pass over all lines (inlier test, count, normal-equation sums of the inliers)
+//   -> if count > n/3: refit, second pass (mean squared distance of the inliers to the refit point).
 __global__ void __launch_bounds__(256) consensus_hyp_kernel(ConsensusArgs g, Layout ws, int splits, int chunk) {
-  extern __shared__ double sl[];  // n * 15
+  extern __shared__ double sl[];  // n * 16
   __shared__ double wbest[8][kPartDoubles];
   const int l = blockIdx.x, split = blockIdx.y;
   const int n = ws.nl[l];
@@ -231,53 +235,56 @@ __global__ void __launch_bounds__(256) consensus_hyp_kernel(ConsensusArgs g, Lay
   const int h_begin = split * chunk;
   const int h_end = min(g.n_hyp, h_begin + chunk);
   const double need = static_cast<double>(n) / 3.0;  // d = n_lines / 3, :100
+  const double thres = g.dist_thres;
   double best_err = kNoFit, best_h = -1.0, bp0 = 0.0, bp1 = 0.0, bp2 = 0.0;
-  for (int h = h_begin + warp; h < h_end; h += 8) {
+  for (int h = h_begin + tid; h < h_end; h += blockDim.x) {
     // --- 8-line LSQ (:105-107)
-    double s9[9];
-    {
-      const double* ln = nullptr;
-      if (lane < 8) {
-        const unsigned int draw = g.draws[(static_cast<size_t>(l) * g.n_hyp + h) * 8 + lane];
-        ln = sl + static_cast<size_t>(draw % static_cast<unsigned int>(n)) * kLineDoubles;
-      }
+    double s9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const uint4* dr = reinterpret_cast<const uint4*>(g.draws + (static_cast<size_t>(l) * g.n_hyp + h) * 8);
+    const uint4 d0 = __ldg(dr), d1 = __ldg(dr + 1);
+    const unsigned int draws[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-      for (int k = 0; k < 9; ++k) s9[k] = warp_sum(ln ? ln[6 + k] : 0.0);
+    for (int q = 0; q < 8; ++q) {
+      const double* ln = sl + static_cast<size_t>(draws[q] % static_cast<unsigned int>(n)) * kLineDoubles;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s9[k] += ln[6 + k];
     }
     double p[3];
     sym3_pinv_solve(s9, s9 + 6, p);
-    // --- inliers (:109-114)
-    unsigned int mask = 0;
+    // --- inliers (:109-114) and their normal-equation sums in one pass
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (int i = lane, k = 0; i < n; i += 32, ++k) {
-      const bool in = line_sqdist(p, sl + static_cast<size_t>(i) * kLineDoubles) < g.dist_thres;
-      mask |= (in ? 1u : 0u) << k;
-      cnt += in ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+      const double* ln = sl + static_cast<size_t>(i) * kLineDoubles;
+      if (line_sqdist(p, ln) < thres) {
+        ++cnt;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] += ln[6 + k];
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (static_cast<double>(cnt) > need) {
       // --- refit on the inliers and score (:116-125)
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int i = lane, k = 0; i < n; i += 32, ++k) {
-        if ((mask >> k) & 1u) {
-          const double* ln = sl + static_cast<size_t>(i) * kLineDoubles;
-#pragma unroll
-          for (int q = 0; q < 9; ++q) acc[q] += ln[6 + q];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 9; ++q) acc[q] = warp_sum(acc[q]);
       double p2[3];
       sym3_pinv_solve(acc, acc + 6, p2);
       double ds = 0.0;
-      for (int i = lane, k = 0; i < n; i += 32, ++k)
-        if ((mask >> k) & 1u) ds += line_sqdist(p2, sl + static_cast<size_t>(i) * kLineDoubles);
-      ds = warp_sum(ds);
+      for (int i = 0; i < n; ++i) {
+        const double* ln = sl + static_cast<size_t>(i) * kLineDoubles;
+        if (line_sqdist(p, ln) < thres) ds += line_sqdist(p2, ln);
+      }
       const double err = ds / static_cast<double>(cnt);
       if (err < best_err) {  // strict <, hypotheses visited in increasing order
         best_err = err; best_h = h; bp0 = p2[0]; bp1 = p2[1]; bp2 = p2[2];
       }
     }
+  }
+  // block reduction: lexicographic (error, hypothesis) minimum -> first strict minimum over the whole range
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oe = __shfl_xor_sync(0xffffffffu, best_err, o), oh = __shfl_xor_sync(0xffffffffu, best_h, o);
+    const double o0 = __shfl_xor_sync(0xffffffffu, bp0, o), o1 = __shfl_xor_sync(0xffffffffu, bp1, o);
+    const double o2 = __shfl_xor_sync(0xffffffffu, bp2, o);
+    const bool take = oh >= 0.0 && (best_h < 0.0 || oe < best_err || (oe == best_err && oh < best_h));
+    if (take) { best_err = oe; best_h = oh; bp0 = o0; bp1 = o1; bp2 = o2; }
   }
   if (lane == 0) {
     wbest[warp][0] = best_err; wbest[warp][1] = best_h; wbest[warp][2] = bp0; wbest[warp][3] = bp1; wbest[warp][4] = bp2;
@@ -324,7 +331,7 @@ __global__ void consensus_finalize_kernel(ConsensusArgs g, Layout ws, int splits
 
 int pick_splits(int l, int n_hyp) {
   int splits = ceil_div(2 * kNumSMs, l);
-  const int max_splits = ceil_div(n_hyp, 8);  // at least one hypothesis per warp
+  const int max_splits = ceil_div(n_hyp, 256);  // at least one hypothesis per thread
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   return splits;
