@@ -121,6 +121,12 @@ int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const flo
 int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                                  float* out_heatmaps, float* out_peaks, void* stream);
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net);
+/* Debug aids: per-op mean milliseconds over `reps` passes (ms_out[num_launches], host memory; out_peaks (L,V,3)
+ * device), optionally the conv kernel's per-role stall cycles (roles_out[num_launches*8] host doubles, layout of
+ * mvlm_debug_conv_profile, mean over CTAs), and a one-line description of op `op`. */
+int mvlm_debug_hourglass_profile(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
+                                 float* out_peaks, int reps, float* ms_out, double* roles_out, void* stream);
+int mvlm_debug_hourglass_describe(const mvlm_hourglass* net, int op, char* buf, int buf_len);
 /* layer-wise parity probes: "r3", "hg1", "sum_temp", "x10" -> NHWC bf16 tensor in the workspace */
 int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c);
 void mvlm_hourglass_destroy(mvlm_hourglass* net);

@@ -158,6 +158,18 @@ int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, con
   return net->net.forward_graph(img_u8, img_f32, out_heatmaps, out_peaks, static_cast<cudaStream_t>(stream));
 }
 
+int mvlm_debug_hourglass_profile(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, float* out_peaks,
+                                 int reps, float* ms_out, double* roles_out, void* stream) {
+  MVLM_REQUIRE(net, "mvlm_debug_hourglass_profile: null handle");
+  return net->net.profile_ops(img_u8, img_f32, out_peaks, reps, ms_out, roles_out, static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_debug_hourglass_describe(const mvlm_hourglass* net, int op, char* buf, int buf_len) {
+  MVLM_REQUIRE(net && buf && buf_len > 0, "mvlm_debug_hourglass_describe: null pointer");
+  snprintf(buf, buf_len, "%s", net->net.describe_op(op).c_str());
+  return MVLM_OK;
+}
+
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net) { return net ? net->net.n_ops() : 0; }
 
 int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c) {

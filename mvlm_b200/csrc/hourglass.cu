@@ -511,44 +511,118 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
   return MVLM_OK;
 }
 
+int HourglassNet::run_op(NetOp& op, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps,
+                         float* out_peaks, cudaStream_t stream) {
+  switch (op.kind) {
+    case NetOp::STEM:
+      return image_to_hilo16(img_u8, img_f32, op.c, static_cast<size_t>(V_) * op.h * op.w, op.out_raw, stream);
+    case NetOp::CONV:
+      if (op.is_head) {
+        ConvParams p = op.conv;
+        p.e.out_f32 = out_heatmaps;
+        return conv_launch(p, stream);
+      }
+      return conv_launch(op.conv, stream);
+    case NetOp::POOL:
+      return pool2_act(op.in0, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
+    case NetOp::UPADD:
+      return upadd_act(op.in0, op.in1, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
+    case NetOp::BNRELU:
+      return bn_relu(op.in0, static_cast<size_t>(V_) * op.h * op.w, op.c, op.scale, op.shift, op.out_act, stream);
+    case NetOp::MEMSET:
+      MVLM_CHECK_CUDA(cudaMemsetAsync(op.ptr, 0, op.bytes, stream));
+      return MVLM_OK;
+    case NetOp::PEAKS:
+      if (out_peaks) return peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
+      return MVLM_OK;
+  }
+  return MVLM_OK;
+}
+
 int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
                           cudaStream_t stream) {
   MVLM_REQUIRE(!dry_, "hourglass: forward on a dry plan");
   MVLM_REQUIRE(out_peaks || out_heatmaps, "hourglass: no output requested");
   for (NetOp& op : ops_) {
-    int rc = MVLM_OK;
-    switch (op.kind) {
-      case NetOp::STEM:
-        rc = image_to_hilo16(img_u8, img_f32, op.c, static_cast<size_t>(V_) * op.h * op.w, op.out_raw, stream);
-        break;
-      case NetOp::CONV:
-        if (op.is_head) {
-          ConvParams p = op.conv;
-          p.e.out_f32 = out_heatmaps;
-          rc = conv_launch(p, stream);
-        } else {
-          rc = conv_launch(op.conv, stream);
-        }
-        break;
-      case NetOp::POOL:
-        rc = pool2_act(op.in0, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
-        break;
-      case NetOp::UPADD:
-        rc = upadd_act(op.in0, op.in1, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
-        break;
-      case NetOp::BNRELU:
-        rc = bn_relu(op.in0, static_cast<size_t>(V_) * op.h * op.w, op.c, op.scale, op.shift, op.out_act, stream);
-        break;
-      case NetOp::MEMSET:
-        MVLM_CHECK_CUDA(cudaMemsetAsync(op.ptr, 0, op.bytes, stream));
-        break;
-      case NetOp::PEAKS:
-        if (out_peaks) rc = peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
-        break;
-    }
+    const int rc = run_op(op, img_u8, img_f32, out_heatmaps, out_peaks, stream);
     if (rc != MVLM_OK) return rc;
   }
   return MVLM_OK;
+}
+
+int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32, float* out_peaks, int reps,
+                              float* ms_out, double* roles_out, cudaStream_t stream) {
+  MVLM_REQUIRE(!dry_ && out_peaks && ms_out && reps > 0, "hourglass: bad profile_ops arguments");
+  const size_t n = ops_.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) MVLM_CHECK_CUDA(cudaEventCreate(&e));
+  for (size_t i = 0; i < n; ++i) ms_out[i] = 0.f;
+  int rc = forward(img_u8, img_f32, nullptr, out_peaks, stream);  // warm-up
+  for (int r = 0; r < reps && rc == MVLM_OK; ++r) {
+    MVLM_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+    for (size_t i = 0; i < n && rc == MVLM_OK; ++i) {
+      rc = run_op(ops_[i], img_u8, img_f32, nullptr, out_peaks, stream);
+      MVLM_CHECK_CUDA(cudaEventRecord(ev[i + 1], stream));
+    }
+    MVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      MVLM_CHECK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      ms_out[i] += ms / reps;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (roles_out && rc == MVLM_OK) {
+    // one more pass with the conv kernel's role counters on: mean over the CTAs that ran (see conv_umma.cu)
+    long long* dev = nullptr;
+    MVLM_CHECK_CUDA(cudaMalloc(&dev, sizeof(long long) * kNumSMs * 8));
+    std::vector<long long> host(kNumSMs * 8);
+    for (size_t i = 0; i < n && rc == MVLM_OK; ++i) {
+      for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] = 0.0;
+      if (ops_[i].kind == NetOp::CONV) {
+        MVLM_CHECK_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * kNumSMs * 8, stream));
+        conv_set_profile_buffer(dev);
+      }
+      rc = run_op(ops_[i], img_u8, img_f32, nullptr, out_peaks, stream);
+      conv_set_profile_buffer(nullptr);
+      if (ops_[i].kind == NetOp::CONV && rc == MVLM_OK) {
+        MVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
+        MVLM_CHECK_CUDA(cudaMemcpy(host.data(), dev, sizeof(long long) * kNumSMs * 8, cudaMemcpyDeviceToHost));
+        int ctas = 0;
+        for (int c = 0; c < kNumSMs; ++c) {
+          if (host[c * 8 + 4] == 0) continue;
+          ++ctas;
+          for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] += static_cast<double>(host[c * 8 + k]);
+        }
+        for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] /= ctas > 0 ? ctas : 1;
+      }
+    }
+    cudaFree(dev);
+  }
+  return rc;
+}
+
+std::string HourglassNet::describe_op(int i) const {
+  if (i < 0 || i >= static_cast<int>(ops_.size())) return "";
+  const NetOp& op = ops_[i];
+  char buf[256];
+  switch (op.kind) {
+    case NetOp::CONV: {
+      const ConvShape& s = op.conv.s;
+      const ConvEpilogue& e = op.conv.e;
+      snprintf(buf, sizeof(buf), "conv %s %dx%d %d->%d k%d%s%s%s%s%s%s%s", op.tag, s.h, s.w, s.cin, s.cout_pad, s.kh,
+               e.out_pre ? " pre" : "", e.res1 ? " res1" : "", e.res2 ? " res2" : "", e.out_raw ? " raw" : "",
+               e.out_post ? " post" : "", e.pool2 ? " pool" : "", e.argmax_keys ? " argmax" : "");
+      break;
+    }
+    case NetOp::POOL: snprintf(buf, sizeof(buf), "pool %dx%dx%d", op.h, op.w, op.c); break;
+    case NetOp::UPADD: snprintf(buf, sizeof(buf), "upadd %dx%dx%d%s", op.h, op.w, op.c, op.out_act ? " act" : ""); break;
+    case NetOp::BNRELU: snprintf(buf, sizeof(buf), "bnrelu %dx%dx%d", op.h, op.w, op.c); break;
+    case NetOp::STEM: snprintf(buf, sizeof(buf), "stem-stage %dx%dx%d", op.h, op.w, op.c); break;
+    case NetOp::MEMSET: snprintf(buf, sizeof(buf), "memset %zu", op.bytes); break;
+    case NetOp::PEAKS: snprintf(buf, sizeof(buf), "peaks"); break;
+  }
+  return buf;
 }
 
 int HourglassNet::forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps,

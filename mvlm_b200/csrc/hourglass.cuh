@@ -35,10 +35,19 @@ class HourglassNet {
             void* workspace, size_t workspace_bytes, bool dry);
   int forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
               cudaStream_t stream);
+  int run_op(NetOp& op, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
+             cudaStream_t stream);
   // Captures the launch sequence of forward() into a CUDA graph per distinct argument tuple and replays it
   // (the plan is static: ~175 launches per call).  Falls back to plain launches if capture is unavailable.
   int forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
                     cudaStream_t stream);
+
+  // Debug aid: runs the plan `reps` times with a CUDA event pair around every op; ms_out[n_ops()] = mean ms per op.
+  // roles_out (optional, n_ops() x 8 doubles): mean per-CTA role stall cycles of every conv op (conv_umma.cu).
+  int profile_ops(const unsigned char* img_u8, const float* img_f32, float* out_peaks, int reps, float* ms_out,
+                  double* roles_out, cudaStream_t stream);
+  // one-line description of op i ("conv rb.conv 128x128 256->128 k3 F=0x1b", "upadd 64x64x256", ...)
+  std::string describe_op(int i) const;
 
   size_t workspace_needed() const { return ws_off_; }
   int n_views() const { return V_; }
