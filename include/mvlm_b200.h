@@ -65,6 +65,8 @@ typedef struct mvlm_conv_args {
   const float* mid_scale; /* optional: v = relu(v*mid_scale+mid_shift) right after the bias */
   const float* mid_shift;
   int pool2;              /* 1: out_raw / out_post are the 2x2 max-pooled (half resolution) tensors */
+  const void* res_up;     /* optional bf16 (n, h/2, w/2, up_cs): v += nearest-x2 up-sampled res_up (with res1/res2) */
+  int up_cs, up_co;
 } mvlm_conv_args;
 
 int mvlm_conv2d_bf16(const mvlm_conv_args* args, void* stream);

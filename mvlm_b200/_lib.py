@@ -36,6 +36,7 @@ class ConvArgs(C.Structure):
         ("up_sy", C.c_int), ("up_sx", C.c_int), ("up_py", C.c_int), ("up_px", C.c_int),
         ("mid_scale", C.c_void_p), ("mid_shift", C.c_void_p),
         ("pool2", C.c_int),
+        ("res_up", C.c_void_p), ("up_cs", C.c_int), ("up_co", C.c_int),
     ]
 
 

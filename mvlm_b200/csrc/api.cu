@@ -73,6 +73,7 @@ int mvlm_conv2d_bf16(const mvlm_conv_args* a, void* stream) {
   e.out_pre = static_cast<__nv_bfloat16*>(a->out_pre); e.pre_cs = a->pre_cs; e.pre_co = a->pre_co;
   e.res1 = static_cast<const __nv_bfloat16*>(a->res1); e.res1_cs = a->res1_cs; e.res1_co = a->res1_co;
   e.res2 = static_cast<const __nv_bfloat16*>(a->res2); e.res2_cs = a->res2_cs; e.res2_co = a->res2_co;
+  e.res_up = static_cast<const __nv_bfloat16*>(a->res_up); e.up_cs = a->up_cs; e.up_co = a->up_co;
   e.out_raw = static_cast<__nv_bfloat16*>(a->out_raw); e.raw_cs = a->raw_cs; e.raw_co = a->raw_co;
   e.post_scale = a->post_scale; e.post_shift = a->post_shift;
   e.out_post = static_cast<__nv_bfloat16*>(a->out_post); e.post_cs = a->post_cs; e.post_co = a->post_co;

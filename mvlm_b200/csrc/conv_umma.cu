@@ -4,25 +4,33 @@
 //     D[cout (M=128 TMEM lanes) x pixels (N=256 TMEM columns)] += W[cout x K] * X[K x pixels]
 // A single-CTA tcgen05.mma streams its A operand (128 rows x K=16) from shared memory at ~64 B/clk,
 // i.e. >= ~75 cycles per instruction however small N is (measured: 79/84/94 cycles at N=32/64/128
-// against a 16/32/64-cycle math floor).  With the 128 output channels as A and a whole 16x16-pixel
+// against a 16/32/64-cycle math floor).  With the 128 output channels as A and a whole 256-pixel
 // tile as B (N=256) the same instruction does 128 cycles of math (measured 145), so the A stream is
 // hidden -- see tools/exp_mma_only.py and DESIGN.md section 4.
 //
 // One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer   X: one (16+KH-1)-row halo tile per (cin-chunk, kx);
+//   warp 0      TMA producer   X: ONE halo tile (8+KW-1 px x 32+KH-1 rows x 64 ch) per cin-chunk;
 //                              W: one [<=128 cout][64 cin] tile per (cin-chunk, kx, ky)
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma (M=128, N=256, K=16); owns TMEM
 //   warps 2..9  epilogue       tcgen05.ld (lane = channel, 16 pixels) -> smem transpose ->
 //                              bias/BN/ReLU/residual on (pixel, 8 channels) vectors -> 16-byte stores
 //
-// For a fixed input-channel chunk (64 channels = one 128-byte swizzle row) and horizontal tap kx the
-// producer loads ONE halo tile; the KH vertical taps are B descriptors into it shifted by whole image
-// rows (16 px x 128 B = 2048 B, so the 1024-byte swizzle-atom alignment holds).  Zero padding, ragged
-// edges and maps smaller than the tile come from TMA out-of-bounds zero fill.
+// Output tile = 8 px x 32 rows (N = 256; 16/8/4 rows for maps lower than 32).  The halo tile of a
+// 64-channel chunk is stored pixel-major (128-byte rows, SWIZZLE_128B); the B operand of tap (kx, ky)
+// is a descriptor into that SAME tile: start address shifted by (ky*(8+KW-1) + kx) rows of 128 bytes,
+// stride between 8-row groups (SBO) = one halo row of (8+KW-1)*128 bytes.  Neither is a multiple of
+// the 1024-byte swizzle atom: the hardware applies the swizzle XOR to the absolute shared-memory
+// address (measured, tools/exp_swizzle_shift.cu: all taps / all swizzle widths bit-exact with base
+// offset 0), so one TMA load serves all KW*KH taps -- 1.33x the tile's own pixels instead of 3.4x
+// (one load per horizontal tap), which matters because the L2 -> SM fabric is the binding resource
+// (10 TB/s on the 256->128 layers before this change).  Zero padding, ragged edges and maps smaller
+// than the tile come from TMA out-of-bounds zero fill.
 //
 // Accumulators: 2 pipeline stages x 256 fp32 columns of TMEM: the epilogue of tile i overlaps the
 // MMAs of tile i+1.
 #include "conv_umma.cuh"
+
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -32,22 +40,21 @@ namespace {
 
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
-constexpr int kTileW = 16;
-constexpr int kTileH = 16;
+constexpr int kTileW = 8;                               // output tile: 8 px wide ...
+constexpr int kMaxTileH = 32;                           // ... and up to 32 rows high (N = 256)
 constexpr int kMTile = 128;                             // output channels per CTA tile (UMMA M)
-constexpr int kHSlots = 3;                              // halo (activation) ring
-constexpr int kWSlots = 5;                              // weight ring
-constexpr int kRowBytes = kTileW * 128;                 // one image row of the halo tile: 16 px x 64 ch bf16
-constexpr int kHSlotBytes = (kTileH + 2) * kRowBytes;   // up to 18 halo rows = 36 KB
+constexpr int kMaxHSlots = 4;                           // halo (activation) ring, depth chosen per layer
+constexpr int kMaxWSlots = 8;                           // weight ring
 constexpr int kWSlotBytes = kMTile * 128;               // 128 cout rows x 64 cin = 16 KB
+constexpr int kPoolBytes = 200 * 1024;                  // both rings
 constexpr int kStageFloats = 16 * 36;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad)
 constexpr int kMaxCout = 256;
 
 struct __align__(8) Barriers {
-  uint64_t h_full[kHSlots];
-  uint64_t h_empty[kHSlots];
-  uint64_t w_full[kWSlots];
-  uint64_t w_empty[kWSlots];
+  uint64_t h_full[kMaxHSlots];
+  uint64_t h_empty[kMaxHSlots];
+  uint64_t w_full[kMaxWSlots];
+  uint64_t w_empty[kMaxWSlots];
   uint64_t t_full[2];
   uint64_t t_empty[2];
   uint32_t tmem_base;
@@ -65,8 +72,8 @@ struct EpiParams {
   float post_t[kMaxCout];
 };
 
-constexpr int kSmemBytes = kHSlots * kHSlotBytes + kWSlots * kWSlotBytes + kEpiWarps * kStageFloats * 4 + 256 +
-                           static_cast<int>(sizeof(EpiParams)) + 1024 /*align*/;
+constexpr int kSmemBytes = kPoolBytes + kEpiWarps * kStageFloats * 4 + 256 + static_cast<int>(sizeof(EpiParams)) +
+                           1024 /*align*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t order_f32(float f) {
@@ -135,19 +142,20 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 // Epilogue feature flags (template parameter F): code for a feature is only generated when its bit is set,
 // which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
 enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
-              F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */ };
+              F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */,
+              F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool ARGMAX = (F & F_ARGMAX) != 0;  // arg-max variants use the contiguous tile schedule
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment: TMA and UMMA agree on the SWIZZLE_128B XOR pattern only relative to it
+  // 1024-byte alignment: TMA and UMMA agree on the SWIZZLE_128B XOR pattern through the absolute address
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* h_slots = smem;
-  uint8_t* w_slots = smem + kHSlots * kHSlotBytes;
-  float* stage_all = reinterpret_cast<float*>(w_slots + kWSlots * kWSlotBytes);
+  uint8_t* w_slots = smem + p.n_hslots * p.h_slot_bytes;
+  float* stage_all = reinterpret_cast<float*>(smem + kPoolBytes);
   Barriers* bar = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(stage_all) + kEpiWarps * kStageFloats * 4);
   EpiParams* ep = reinterpret_cast<EpiParams*>(reinterpret_cast<uint8_t*>(bar) + 256);
 
@@ -157,11 +165,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const ConvShape& s = p.s;
   const ConvEpilogue& e = p.e;
   const int n_chunks = (s.cin + 63) >> 6;
-  // maps of height <= 8 only ever populate 8 rows: a 10-row halo box (tensor map built accordingly)
-  const int halo_rows = (s.h <= 8 ? 8 : kTileH) + s.kh - 1;
-  const uint32_t h_bytes = static_cast<uint32_t>(halo_rows) * kRowBytes;
+  const int n_hslots = p.n_hslots, n_wslots = p.n_wslots;
+  const int halo_px = kTileW + s.kw - 1;            // pixels per halo row
+  const int halo_rows = p.tile_h + s.kh - 1;
   const int w_rows = s.cout_pad < kMTile ? s.cout_pad : kMTile;  // weight rows actually loaded per tile
-  const uint32_t w_bytes = static_cast<uint32_t>(w_rows) * 128u;
   // cout <= 64: the weight rows are replicated `rep` times along M, so that all four TMEM lane groups (and
   // therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows instead.
   const int rep = s.cout_pad <= 32 ? 4 : (s.cout_pad <= 64 ? 2 : 1);
@@ -192,11 +199,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     ptx::tma_prefetch_desc(&p.tm_a);
     ptx::tma_prefetch_desc(&p.tm_b);
     if (p.tail) { ptx::tma_prefetch_desc(&p.tm_a2); ptx::tma_prefetch_desc(&p.tm_b2); }
-    for (int i = 0; i < kHSlots; ++i) {
+    for (int i = 0; i < n_hslots; ++i) {
       ptx::mbar_init(&bar->h_full[i], 1);
       ptx::mbar_init(&bar->h_empty[i], 1);
     }
-    for (int i = 0; i < kWSlots; ++i) {
+    for (int i = 0; i < n_wslots; ++i) {
       ptx::mbar_init(&bar->w_full[i], 1);
       ptx::mbar_init(&bar->w_empty[i], 1);
     }
@@ -226,27 +233,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       for (int t = t_begin; t < t_end; t += t_step) {
         const TileCoord tc = decode_tile(p, t);
         const int x0 = tc.tx * kTileW + s.x_off0;
-        const int y0 = tc.ty * kTileH + s.y_off0;
+        const int y0 = tc.ty * p.tile_h + s.y_off0;
         for (int c = 0; c < n_chunks; ++c) {
           // the last chunk may be a narrow tail (16 / 32 channels) with its own tensor maps: rows of 32 / 64 bytes
           const bool is_tail = p.tail != 0 && c == n_chunks - 1;
           const void* tma = is_tail ? &p.tm_a2 : &p.tm_a;
           const void* tmb = is_tail ? &p.tm_b2 : &p.tm_b;
           const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per pixel / weight row
-          const uint32_t hb = static_cast<uint32_t>(halo_rows) * kTileW * row_b;
+          const uint32_t hb = static_cast<uint32_t>(halo_rows * halo_px) * row_b;
           const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
+          // one halo tile for all KW x KH taps of this chunk
+          timed_wait(&bar->h_empty[sh], ph ^ 1, prof, w0);
+          ptx::mbar_expect_tx(&bar->h_full[sh], hb);
+          ptx::tma_load_4d(tma, &bar->h_full[sh], h_slots + sh * p.h_slot_bytes, c * 64, x0, y0, tc.img);
+          if (++sh == n_hslots) { sh = 0; ph ^= 1; }
           for (int kx = 0; kx < s.kw; ++kx) {
-            timed_wait(&bar->h_empty[sh], ph ^ 1, prof, w0);
-            ptx::mbar_expect_tx(&bar->h_full[sh], hb);
-            ptx::tma_load_4d(tma, &bar->h_full[sh], h_slots + sh * kHSlotBytes, c * 64, x0 + kx, y0, tc.img);
-            if (++sh == kHSlots) { sh = 0; ph ^= 1; }
             for (int ky = 0; ky < s.kh; ++ky) {
               timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
               ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
               for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
                 ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * row_b,
                                  (kx * s.kh + ky) * s.cin + c * 64, tc.mt * kMTile);
-              if (++sw == kWSlots) { sw = 0; pw ^= 1; }
+              if (++sw == n_wslots) { sw = 0; pw ^= 1; }
             }
           }
         }
@@ -258,18 +266,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // elect.sync (not `lane == 0`): the compiler then knows a single lane is active and emits the
     // UTCHMMA / UTCBAR uniform-datapath instructions without a per-lane serialisation loop.
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc256 = ptx::umma_idesc_bf16(kMTile, 256);
-      constexpr uint32_t idesc128 = ptx::umma_idesc_bf16(kMTile, 128);
-      // descriptor = {lo: start>>4 | LBO, hi: SBO | version | SWIZZLE_128B}; only lo changes per MMA
-      constexpr uint64_t kDescHi = static_cast<uint64_t>(64u | (1u << 14) | (2u << 29)) << 32;
+      const uint32_t idesc = ptx::umma_idesc_bf16(kMTile, p.tile_h * kTileW);
+      // descriptor = {lo: start>>4 | LBO, hi: SBO | version | swizzle}; only lo changes per MMA.
+      //   A (weights): 8-row groups 8 rows apart.  B (halo tile): 8-row group = the 8 pixels of one image row,
+      //   groups one halo row (halo_px pixels) apart.
       int sh = 0, sw = 0;
       uint32_t ph = 0, pw = 0;
       int acc = 0;
       uint32_t pacc = 0;
       for (int t = t_begin; t < t_end; t += t_step) {
-        const int ty = (t / p.n_nt / p.tiles_x) % p.tiles_y;
-        // maps of height <= 8 (hourglass levels 8^2 .. 1^2) only populate the first 8 rows: N = 128
-        const uint32_t idesc = (ty * kTileH + 8 < s.h) ? idesc256 : idesc128;
         timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -277,38 +282,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         for (int c = 0; c < n_chunks; ++c) {
           const int rem = s.cin - c * 64;
           const int nk = rem >= 64 ? 4 : (rem >> 4);
-          // tail chunk: SWIZZLE_32B (16 ch: 8-row atoms of 256 B) or SWIZZLE_64B (32 ch: atoms of 512 B)
+          // tail chunk: SWIZZLE_32B (16 ch: 32-byte rows) or SWIZZLE_64B (32 ch: 64-byte rows)
           const bool is_tail = p.tail != 0 && c == n_chunks - 1;
-          const uint64_t desc_hi = !is_tail ? kDescHi
-                                            : (static_cast<uint64_t>((p.tail == 16 ? 16u : 32u) | (1u << 14) |
-                                                                     ((p.tail == 16 ? 6u : 4u) << 29)) << 32);
-          const uint32_t ky_step = !is_tail ? (kRowBytes >> 4) : static_cast<uint32_t>(2 * p.tail);  // one image row >> 4
+          const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;
+          const uint32_t swz = !is_tail ? 2u : (p.tail == 16 ? 6u : 4u);
+          const uint64_t a_hi = static_cast<uint64_t>(((8u * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
+          const uint64_t b_hi = static_cast<uint64_t>(((static_cast<uint32_t>(halo_px) * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
+          if (p.debug_mode == 0) timed_wait(&bar->h_full[sh], ph, prof, w0);
+          const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * p.h_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
           for (int kx = 0; kx < s.kw; ++kx) {
-            if (p.debug_mode == 0) timed_wait(&bar->h_full[sh], ph, prof, w0);
-            const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * kHSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
             for (int ky = 0; ky < s.kh; ++ky) {
               if (p.debug_mode == 0) timed_wait(&bar->w_full[sw], pw, prof, w0);
               ptx::tc_fence_after();
               const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * kWSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
-              // vertical tap = whole image rows of the halo tile: ky * 2048 B >> 4
-              const uint32_t x_lo = h_lo + static_cast<uint32_t>(ky) * ky_step;
+              // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
+              const uint32_t x_lo = h_lo + ((static_cast<uint32_t>(ky * halo_px + kx) * row_b) >> 4);
               if (nk == 4) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(d, kDescHi | (w_lo + 2 * k), kDescHi | (x_lo + 2 * k), idesc,
-                                 (k == 0) ? accumulate : 1u);
+                  ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
               } else {
                 for (int k = 0; k < nk; ++k)
-                  ptx::umma_bf16(d, desc_hi | (w_lo + 2 * k), desc_hi | (x_lo + 2 * k), idesc,
-                                 (k == 0) ? accumulate : 1u);
+                  ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
               }
               accumulate = 1;
               if (p.debug_mode == 0) ptx::umma_commit(&bar->w_empty[sw]);
-              if (++sw == kWSlots) { sw = 0; pw ^= 1; }
+              if (++sw == n_wslots) { sw = 0; pw ^= 1; }
             }
-            if (p.debug_mode == 0) ptx::umma_commit(&bar->h_empty[sh]);
-            if (++sh == kHSlots) { sh = 0; ph ^= 1; }
           }
+          if (p.debug_mode == 0) ptx::umma_commit(&bar->h_empty[sh]);
+          if (++sh == n_hslots) { sh = 0; ph ^= 1; }
         }
         ptx::umma_commit(&bar->t_full[acc]);
         if (++acc == 2) { acc = 0; pacc ^= 1; }
@@ -317,13 +320,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
   } else {
     // ===================== epilogue =====================
+    // Accumulator column n = 8 * (row in tile) + (pixel in row).  One "unit" = 16 columns = 2 image rows x 8 px.
     const int ew = warp - 2;
     const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
     const int n_cgrp = 4 / rep;      // distinct 32-channel groups along M
     const int cgrp = lane_grp % n_cgrp;
     const int replica = lane_grp / n_cgrp;
-    const int rows_per_warp = 8 / rep;
-    const int row0 = (ew >> 2) * 8 + replica * rows_per_warp;  // first image row of the tile handled by this warp
+    const int n_units = p.tile_h >> 1;
+    const int upw = max(1, n_units / (2 * rep));              // units per warp
+    const int u_begin = ((ew >> 2) * rep + replica) * upw;    // first unit handled by this warp
     float* stage = stage_all + ew * kStageFloats;
     int acc = 0;
     uint32_t pacc = 0;
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     uint32_t best_hi = 0u, best_lo = 0u;
     int cur_img = -1;
     const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
-    // pixel-major role after the transpose: lane -> (pixel j = lane/4 (+8), channels (lane%4)*8 .. +7)
+    // pixel-major role after the transpose: lane -> (pixel column pj = lane/4, row parity i, channels (lane%4)*8 .. +7)
     const int pj = lane >> 2;
     const int cq = (lane & 3) * 8;
     constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
@@ -341,16 +346,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const int c_lane = m0 + cgrp * 32 + lane;           // channel-major role: my output channel
       const int c0 = m0 + cgrp * 32 + cq;                 // pixel-major role: first of my 8 channels
       const bool grp_active = m0 + cgrp * 32 < s.cout_pad;
-      const int y_first = tc.ty * kTileH + row0;
-      const bool rows_active = y_first < s.h;
+      const int y_first = tc.ty * p.tile_h + 2 * u_begin;  // first image row handled by this warp
+      const bool rows_active = u_begin < n_units && y_first < s.h;
       const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
       const int xa = tc.tx * kTileW + pj;
-      const bool va = ch_ok && xa < s.w, vb = ch_ok && xa + 8 < s.w;
+      const bool vx = ch_ok && xa < s.w;
       // element index of pixel (img, y_first, xa); 32-bit: pixel count x channel stride < 2^31 (checked in conv_plan)
       const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first) * s.w + xa;
       // F_POOL: element index of the pooled pixel of (img, y_first, xa) in the half-resolution outputs
       const uint32_t ppix0 = (static_cast<uint32_t>(tc.img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
-      uint4 pool_prev[2];
       if ((F & F_ARGMAX) && tc.img != cur_img) {
         if (cur_img >= 0 && best_hi != 0u && c_lane < e.cout_real)
           atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
@@ -358,30 +362,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         best_hi = 0u; best_lo = 0u;
         cur_img = tc.img;
       }
-      // residual rows do not depend on the accumulator: fetch them while the MMAs of this tile still run
-      // (all 8 rows when there is one residual, 4 + 4 rows when there are two: register budget)
-      constexpr int kPref = (F & F_RES2) ? 4 : 8;
-      uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2];
-      auto prefetch = [&](int r_begin) {
+      // residual rows do not depend on the accumulator: the first kPref units are fetched while the MMAs of this
+      // tile still run, unit r + kPref is fetched as soon as unit r has been consumed (rolling window)
+      constexpr int kPref = (F & (F_RES2 | F_UP)) ? 4 : 8;
+      uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1];
+      auto prefetch_unit = [&](int u) {  // u: compile-time after unrolling
+        if (u < upw) {
+          const int q = u % kPref;
 #pragma unroll
-        for (int q = 0; q < kPref; ++q) {
-          const int r = r_begin + q;
-          if (r < rows_per_warp && y_first + r < s.h) {
-            const uint32_t pix = pix0 + r * s.w;
-            if (F & F_RES1) {
-              const __nv_bfloat16* rp = e.res1 + e.res1_co + c0;
-              if (va) r1[q][0] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(pix * e.res1_cs));
-              if (vb) r1[q][1] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>((pix + 8) * e.res1_cs));
-            }
-            if (F & F_RES2) {
-              const __nv_bfloat16* rp = e.res2 + e.res2_co + c0;
-              if (va) r2[q][0] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(pix * e.res2_cs));
-              if (vb) r2[q][1] = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>((pix + 8) * e.res2_cs));
+          for (int i = 0; i < 2; ++i) {
+            if (vx && y_first + 2 * u + i < s.h) {
+              const uint32_t pix = pix0 + (2 * u + i) * s.w;
+              if (F & F_RES1)
+                r1[q][i] = *reinterpret_cast<const uint4*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix * e.res1_cs));
+              if (F & F_RES2)
+                r2[q][i] = *reinterpret_cast<const uint4*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix * e.res2_cs));
             }
           }
+          // nearest x2: rows y, y+1 and columns xa, xa^1 all read low-res pixel (y/2, xa/2)
+          if ((F & F_UP) && vx && y_first + 2 * u < s.h)
+            ru[q] = *reinterpret_cast<const uint4*>(e.res_up + e.up_co + c0 + static_cast<size_t>((ppix0 + u * (s.w >> 1)) * e.up_cs));
         }
       };
-      if ((F & (F_RES1 | F_RES2)) && grp_active && rows_active) prefetch(0);
+      if ((F & (F_RES1 | F_RES2 | F_UP)) && grp_active && rows_active) {
+#pragma unroll
+        for (int q = 0; q < kPref; ++q) prefetch_unit(q);
+      }
       // per-channel parameters of my 8 channels (pixel-major role) and my channel (channel-major role)
       float pre_s[8], pre_t[8], post_s[8], post_t[8];
       if (F & F_PRE) { lds8(ep->pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep->pre_t + (ch_ok ? c0 : 0), pre_t); }
@@ -392,43 +398,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       ptx::tc_fence_after();
       if (grp_active && rows_active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                               static_cast<uint32_t>(acc * 256 + row0 * 16);
+                               static_cast<uint32_t>(acc * 256 + u_begin * 16);
         uint32_t v[2][16];
         ptx::tmem_ld16(taddr, v[0]);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          if (r < rows_per_warp) {
-            const int y = y_first + r;
+          if (r < upw) {
+            const int y = y_first + 2 * r;  // image rows y (columns 0..7 of the unit) and y+1 (columns 8..15)
             ptx::tmem_ld_wait();
-            if (r + 1 < rows_per_warp) ptx::tmem_ld16(taddr + (r + 1) * 16, v[(r + 1) & 1]);  // next row in flight
-            if ((F & F_RES2) && r == kPref) prefetch(kPref);  // rows 0..3 are consumed: fetch rows 4..7
+            if (r + 1 < upw) ptx::tmem_ld16(taddr + (r + 1) * 16, v[(r + 1) & 1]);  // next unit in flight
             const uint32_t(&vr)[16] = v[r & 1];
             if (y < s.h) {
               if (F & F_HEAD) {
-                // channel-major consumers: lane = channel c_lane, vr[j] = pixel x0+j of row y
+                // channel-major consumers: lane = channel c_lane, vr[j] = pixel (y + j/8, x0 + j%8)
                 const int x0 = tc.tx * kTileW;
-                const int nvx = s.w - x0;  // >= 16 for interior tiles
-                const int oy = y * e.up_sy + e.up_py;
-                const uint32_t idx0 = static_cast<uint32_t>(oy * ow + x0 * e.up_sx + e.up_px);
+                const int nvx = s.w - x0;  // >= 8 for interior tiles
                 if (c_lane < e.cout_real) {
-                  if (F & F_ARGMAX) {
-                    unsigned long long best = (static_cast<unsigned long long>(best_hi) << 32) | best_lo;
-                    uint32_t lo = 0xFFFFFFFFu - idx0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                      const unsigned long long key =
-                          (static_cast<unsigned long long>(order_f32(__uint_as_float(vr[j]) + bias_c)) << 32) | lo;
-                      if (j < nvx && key > best) best = key;
-                      lo -= static_cast<uint32_t>(e.up_sx);
+                  for (int i = 0; i < 2; ++i) {
+                    if (y + i < s.h) {
+                      const int oy = (y + i) * e.up_sy + e.up_py;
+                      const uint32_t idx0 = static_cast<uint32_t>(oy * ow + x0 * e.up_sx + e.up_px);
+                      if (F & F_ARGMAX) {
+                        unsigned long long best = (static_cast<unsigned long long>(best_hi) << 32) | best_lo;
+                        uint32_t lo = 0xFFFFFFFFu - idx0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                          const unsigned long long key =
+                              (static_cast<unsigned long long>(order_f32(__uint_as_float(vr[8 * i + j]) + bias_c)) << 32) | lo;
+                          if (j < nvx && key > best) best = key;
+                          lo -= static_cast<uint32_t>(e.up_sx);
+                        }
+                        best_hi = static_cast<uint32_t>(best >> 32);
+                        best_lo = static_cast<uint32_t>(best);
+                      }
+                      if (F & F_F32) {
+                        float* dst = e.out_f32 + (static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh * ow + idx0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                          if (j < nvx) dst[j * e.up_sx] = __uint_as_float(vr[8 * i + j]) + bias_c;
+                      }
                     }
-                    best_hi = static_cast<uint32_t>(best >> 32);
-                    best_lo = static_cast<uint32_t>(best);
-                  }
-                  if (F & F_F32) {
-                    float* dst = e.out_f32 + (static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh * ow + idx0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                      if (j < nvx) dst[j * e.up_sx] = __uint_as_float(vr[j]) + bias_c;
                   }
                 }
               }
@@ -443,11 +453,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   stage[j * 36 + lane] = f;
                 }
                 __syncwarp();
-                const uint32_t pix = pix0 + r * s.w;
+                uint4 pool_cur[2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                  const bool valid = i == 0 ? va : vb;
-                  const uint32_t px = pix + 8 * i;
+                  const bool valid = vx && y + i < s.h;
+                  const uint32_t px = pix0 + (2 * r + i) * s.w;
                   float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                   if (valid) {
                     lds8(stage + (pj + 8 * i) * 36 + cq, f);
@@ -459,34 +469,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     }
                     if (F & F_RES1) add8(r1[r % kPref][i], f);
                     if (F & F_RES2) add8(r2[r % kPref][i], f);
+                    if (F & F_UP) add8(ru[r % kPref], f);
                   }
                   if (F & F_POOL) {
-                    // 2x2 max-pool of the bf16-rounded values: vertical partner = previous row (same lane),
-                    // horizontal partner = lane ^ 4 (pixel j ^ 1); shuffles run on all lanes
-                    const uint4 cur = pack8(f);
-                    if ((r & 1) == 0) {
-                      pool_prev[i] = cur;
-                    } else {
-                      uint4 m = max_bf16x8(pool_prev[i], cur);
-                      uint4 o;
-                      o.x = __shfl_xor_sync(0xffffffffu, m.x, 4);
-                      o.y = __shfl_xor_sync(0xffffffffu, m.y, 4);
-                      o.z = __shfl_xor_sync(0xffffffffu, m.z, 4);
-                      o.w = __shfl_xor_sync(0xffffffffu, m.w, 4);
-                      m = max_bf16x8(m, o);
-                      if (valid && (pj & 1) == 0) {
-                        const uint32_t pp = ppix0 + (r >> 1) * (s.w >> 1) + 4 * i;
-                        if (F & F_RAW)
-                          *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(pp * e.raw_cs)) = m;
-                        if (F & F_POST) {
-                          float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                          add8(m, g);
-#pragma unroll
-                          for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(g[j], post_s[j], post_t[j]), 0.f);
-                          *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(pp * e.post_cs)) = pack8(g);
-                        }
-                      }
-                    }
+                    pool_cur[i] = pack8(f);
                   } else if (valid) {
                     if (F & F_RAW)
                       *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(px * e.raw_cs)) = pack8(f);
@@ -495,6 +481,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                       for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], post_s[j], post_t[j]), 0.f);
                       *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(px * e.post_cs)) = pack8(g);
+                    }
+                  }
+                }
+                if ((F & (F_RES1 | F_RES2 | F_UP)) && r + kPref < 8) prefetch_unit(r + kPref);
+                if (F & F_POOL) {
+                  // 2x2 max-pool of the bf16-rounded values: vertical partner = the unit's other row (same lane),
+                  // horizontal partner = lane ^ 4 (pixel column pj ^ 1); shuffles run on all lanes
+                  uint4 m = max_bf16x8(pool_cur[0], pool_cur[1]);
+                  uint4 o;
+                  o.x = __shfl_xor_sync(0xffffffffu, m.x, 4);
+                  o.y = __shfl_xor_sync(0xffffffffu, m.y, 4);
+                  o.z = __shfl_xor_sync(0xffffffffu, m.z, 4);
+                  o.w = __shfl_xor_sync(0xffffffffu, m.w, 4);
+                  m = max_bf16x8(m, o);
+                  if (vx && (pj & 1) == 0) {  // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
+                    const uint32_t pp = ppix0 + r * (s.w >> 1);
+                    if (F & F_RAW)
+                      *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(pp * e.raw_cs)) = m;
+                    if (F & F_POST) {
+                      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                      add8(m, g);
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(g[j], post_s[j], post_t[j]), 0.f);
+                      *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(pp * e.post_cs)) = pack8(g);
                     }
                   }
                 }
@@ -574,12 +584,14 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   MVLM_REQUIRE(!e.argmax_keys || s.cout_pad <= kMTile, "conv_plan: fused arg-max needs cout_pad <= 128");
   MVLM_REQUIRE(!e.pool2 || (s.h % 2 == 0 && s.w % 2 == 0 && (e.out_raw || e.out_post) && !e.out_f32 && !e.argmax_keys),
                "conv_plan: pool2 needs even H, W and a bf16 raw/post output");
+  MVLM_REQUIRE(!e.res_up || (s.h % 2 == 0 && s.w % 2 == 0 && !e.pool2 && !e.out_f32 && !e.argmax_keys),
+               "conv_plan: res_up needs even H, W and bf16 outputs");
   MVLM_REQUIRE(!e.mid_scale || (e.mid_shift && !e.out_f32 && !e.argmax_keys), "conv_plan: mid affine needs mid_shift and bf16 outputs");
   MVLM_REQUIRE(!((e.argmax_keys || e.out_f32) && (e.res1 || e.res2 || e.out_pre || e.out_raw || e.out_post)),
                "conv_plan: fp32 / arg-max outputs cannot be combined with bf16 outputs or residual inputs");
   {
     const long long npix = 1ll * s.n * s.h * s.w;
-    const int max_cs = std::max(std::max(e.pre_cs, e.raw_cs), std::max(std::max(e.post_cs, e.res1_cs), e.res2_cs));
+    const int max_cs = std::max(std::max(std::max(e.pre_cs, e.raw_cs), std::max(std::max(e.post_cs, e.res1_cs), e.res2_cs)), e.up_cs);
     MVLM_REQUIRE(npix * std::max(max_cs, 1) < (1ll << 31), "conv_plan: tensor too large for 32-bit element offsets");
   }
   MVLM_REQUIRE(s.kh >= 1 && s.kh <= 3 && s.kw >= 1 && s.kw <= 3, "conv_plan: kernel %dx%d unsupported", s.kh, s.kw);
@@ -594,12 +606,30 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   memset(&p, 0, sizeof(p));
   p.s = s;
   p.e = e;
+  // output tile: 8 px x tile_h rows (N = 8 * tile_h columns), tile_h = 32 unless the map is lower
+  const int tile_h = s.h >= 32 ? kMaxTileH : (s.h >= 16 ? 16 : (s.h >= 8 ? 8 : 4));
+  p.tile_h = tile_h;
   {
-    // X: (C, W, H, N) bf16, box (64, 16, 16+KH-1, 1), 128-byte swizzle, OOB -> 0
+    // ring depths: the halo slot holds the whole (8+KW-1) x (tile_h+KH-1) pixel tile of one 64-channel chunk
+    const int hbytes = (kTileW + s.kw - 1) * (tile_h + s.kh - 1) * 128;
+    p.h_slot_bytes = (hbytes + 1023) & ~1023;
+    int nh = s.kh * s.kw == 1 ? 3 : 2, nw = s.kh * s.kw == 1 ? 6 : 7;
+    if (const char* env = getenv("MVLM_CONV_RING")) {  // experiment knob: "halo_slots,weight_slots"
+      int a = 0, b = 0;
+      if (sscanf(env, "%d,%d", &a, &b) == 2 && a >= 2 && a <= kMaxHSlots && b >= 2 && b <= kMaxWSlots) { nh = a; nw = b; }
+    }
+    while (nh * p.h_slot_bytes + nw * kWSlotBytes > kPoolBytes && nw > 2) --nw;
+    while (nh * p.h_slot_bytes + nw * kWSlotBytes > kPoolBytes && nh > 2) --nh;
+    MVLM_REQUIRE(nh * p.h_slot_bytes + nw * kWSlotBytes <= kPoolBytes, "conv_plan: operand rings do not fit");
+    p.n_hslots = nh;
+    p.n_wslots = nw;
+  }
+  {
+    // X: (C, W, H, N) bf16, box (64, 8+KW-1, tile_h+KH-1, 1), 128-byte swizzle, OOB -> 0
     cuuint64_t gdim[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
     cuuint64_t gstr[3] = {(cuuint64_t)s.in_cs * 2, (cuuint64_t)s.in_cs * 2 * s.w,
                           (cuuint64_t)s.in_cs * 2 * s.w * s.h};
-    cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)((s.h <= 8 ? 8 : kTileH) + s.kh - 1), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(kTileW + s.kw - 1), (cuuint32_t)(tile_h + s.kh - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(s.in), gdim, gstr,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -631,7 +661,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     const CUtensorMapSwizzle sw = p.tail == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t gdim[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.w, (cuuint64_t)s.h, (cuuint64_t)s.n};
     cuuint64_t gstr[3] = {(cuuint64_t)s.in_cs * 2, (cuuint64_t)s.in_cs * 2 * s.w, (cuuint64_t)s.in_cs * 2 * s.w * s.h};
-    cuuint32_t box[4] = {(cuuint32_t)p.tail, (cuuint32_t)kTileW, (cuuint32_t)((s.h <= 8 ? 8 : kTileH) + s.kh - 1), 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.tail, (cuuint32_t)(kTileW + s.kw - 1), (cuuint32_t)(tile_h + s.kh - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tm_a2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(s.in), gdim, gstr, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -649,7 +679,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     }
   }
   p.tiles_x = ceil_div(s.w, kTileW);
-  p.tiles_y = ceil_div(s.h, kTileH);
+  p.tiles_y = ceil_div(s.h, tile_h);
   p.n_nt = ceil_div(s.cout_pad, kMTile);
   p.total_tiles = s.n * p.tiles_x * p.tiles_y * p.n_nt;
   p.prof = nullptr;
@@ -668,7 +698,7 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   const ConvEpilogue& e = p.e;
   const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
                 (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0) |
-                (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0);
+                (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0) | (e.res_up ? F_UP : 0);
   switch (f) {
     // the combinations the network plan uses (hourglass.cu)
     case F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);  // RB conv1/2
@@ -687,6 +717,11 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
     case F_POOL | F_RAW: return launch_t<F_POOL | F_RAW>(p, stream);
     case F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
       return launch_t<F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
+    // skip-branch ResidualBlocks with the up-sampled low path added in the epilogue (hourglass up path)
+    case F_UP | F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_UP | F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);
+    case F_UP | F_PRE | F_RES1 | F_RAW: return launch_t<F_UP | F_PRE | F_RES1 | F_RAW>(p, stream);
+    case F_UP | F_RES1 | F_RAW | F_POST: return launch_t<F_UP | F_RES1 | F_RAW | F_POST>(p, stream);
+    case F_UP | F_RES1 | F_RAW: return launch_t<F_UP | F_RES1 | F_RAW>(p, stream);
     case F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
       return launch_t<F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
   }

@@ -10,8 +10,8 @@
 //                 base pointer.
 //   weights     : packed bf16 [cout_pad][KW][KH][cin]  (K-major rows; one row
 //                 per output channel; rows >= cout_real are zero).
-//   GEMM view   : M = output pixels (128-row sub-tiles of 8 image rows x 16
-//                 px), N = output channels (N_TILE per CTA), K = KW*KH*cin.
+//   GEMM view   : M = output channels (128 per CTA tile), N = output pixels (8 px x 32
+//                 rows per CTA tile), K = KW*KH*cin.
 #pragma once
 #include "common.cuh"
 
@@ -32,6 +32,10 @@ struct ConvEpilogue {
   int res1_cs = 0, res1_co = 0;
   const __nv_bfloat16* res2 = nullptr;
   int res2_cs = 0, res2_co = 0;
+  // v += res_up[(y/2, x/2)]: a half-resolution tensor added with nearest x2 up-sampling
+  // (F.interpolate(scale_factor=2, mode="nearest") + skip, paulsenpredictor.py:334-359)
+  const __nv_bfloat16* res_up = nullptr;
+  int up_cs = 0, up_co = 0;
   // raw output (after residuals)
   __nv_bfloat16* out_raw = nullptr;
   int raw_cs = 0, raw_co = 0;
@@ -72,6 +76,8 @@ struct alignas(64) ConvParams {
   ConvShape s;
   ConvEpilogue e;
   int tiles_x, tiles_y, n_nt, total_tiles;
+  int tile_h;                             // rows of the 8-px-wide output tile: 32 (N = 256), 16, 8 or 4 for low maps
+  int h_slot_bytes, n_hslots, n_wslots;   // operand ring geometry (conv_plan)
   // optional per-CTA cycle counters (8 x int64 per CTA), see conv_umma.cu "role timing"
   long long* prof;
   int debug_mode;  // 0 normal; 1 = MMA-only experiment (no TMA loads, operand waits skipped; results garbage)

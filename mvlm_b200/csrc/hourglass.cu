@@ -214,7 +214,7 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
 }
 
 int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act,
-                     T* y_out, T* pool_raw) {
+                     T* y_out, T* pool_raw, const T* up_low) {
   const int h = a_in.h, w = a_in.w;
   T y = alloc(h, w, cout);
   T skip = x;
@@ -251,6 +251,7 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
       e.out_pre = pres[i].p; e.pre_cs = pres[i].c; e.pre_co = 0;
     }
     e.res1 = skip.p; e.res1_cs = skip.c; e.res1_co = offs[i];
+    if (up_low) { e.res_up = up_low->p; e.up_cs = up_low->c; e.up_co = offs[i]; }
     e.out_raw = pool_raw ? pool_raw->p : y.p; e.raw_cs = cout; e.raw_co = offs[i];
     e.pool2 = pool_raw != nullptr;
     if (post_bn) {
@@ -293,13 +294,14 @@ int HourglassNet::emit_upadd(T low, T skip, T out_raw, const char* bn_name, T ou
 }
 
 int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
+  // HourGlassModule.forward (:301-361).  The skip-branch blocks (rb1, rb3, rb5, rb7, rb9) are scheduled on the way
+  // UP, after the low path of their level has returned, so that `F.interpolate(low, 2) + skip` (:334-359) is one
+  // more residual of their epilogues instead of a separate elementwise pass over both tensors.
   const int F = 256;
   int rc;
-  T skips[5];
   T none;
-  rc = rb(p + ".rb1", x, a_x, none, F, F, nullptr, nullptr, &skips[0]);
-  if (rc) return rc;
-  T cur = x, a_low;
+  T lows[5], a_lows[5];
+  T cur = x;
   const int low_blocks[5] = {2, 4, 6, 8, 10};
   const int skip_blocks[4] = {3, 5, 7, 9};
   for (int lvl = 0; lvl < 5; ++lvl) {
@@ -309,28 +311,23 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
     if (rc) return rc;
     const int nxt = lvl < 4 ? skip_blocks[lvl] : 11;
     const std::string post = p + ".rb" + std::to_string(nxt) + ".bn1";
-    T low;
-    rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_low, &low);
+    rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_lows[lvl], &lows[lvl]);
     if (rc) return rc;
-    if (lvl < 4) {
-      rc = rb(p + ".rb" + std::to_string(skip_blocks[lvl]), low, a_low, none, F, F, nullptr, nullptr, &skips[lvl + 1]);
-      if (rc) return rc;
-    }
-    cur = low;
+    cur = lows[lvl];
   }
   T low2, a2, low3;
-  rc = rb(p + ".rb11", cur, a_low, none, F, F, (p + ".rb12.bn1").c_str(), &a2, &low2);
+  rc = rb(p + ".rb11", cur, a_lows[4], none, F, F, (p + ".rb12.bn1").c_str(), &a2, &low2);
   if (rc) return rc;
   rc = rb(p + ".rb12", low2, a2, none, F, F, nullptr, nullptr, &low3);
   if (rc) return rc;
   cur = low3;
   const int ups[4][2] = {{13, 14}, {15, 16}, {17, 18}, {19, 20}};
   for (int lvl = 0; lvl < 4; ++lvl) {
-    T skip = skips[4 - lvl];
-    T s = alloc(skip.h, skip.w, F), a = alloc(skip.h, skip.w, F);
+    const std::string sb = p + ".rb" + std::to_string(skip_blocks[3 - lvl]);
     const std::string b1 = p + ".rb" + std::to_string(ups[lvl][0]);
     const std::string b2 = p + ".rb" + std::to_string(ups[lvl][1]);
-    rc = emit_upadd(cur, skip, s, (b1 + ".bn1").c_str(), a);
+    T s, a;
+    rc = rb(sb, lows[3 - lvl], a_lows[3 - lvl], none, F, F, (b1 + ".bn1").c_str(), &a, &s, nullptr, &cur);
     if (rc) return rc;
     T l1, a1, l2;
     rc = rb(b1, s, a, none, F, F, (b2 + ".bn1").c_str(), &a1, &l1);
@@ -339,8 +336,8 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
     if (rc) return rc;
     cur = l2;
   }
-  T add5 = alloc(skips[0].h, skips[0].w, F);
-  rc = emit_upadd(cur, skips[0], add5, nullptr, T());
+  T add5;
+  rc = rb(p + ".rb1", x, a_x, none, F, F, nullptr, nullptr, &add5, nullptr, &cur);
   if (rc) return rc;
   *out = add5;
   return MVLM_OK;

@@ -73,8 +73,10 @@ class HourglassNet {
                 ConvEpilogue e, bool with_bias);
   // pool_raw != nullptr: the block output is only consumed through a 2x2 max-pool (conv2 block, :410-411):
   // the three convs write the pooled raw tensor and relu(post_bn(pooled)) directly; no full-resolution output
+  // up_low != nullptr: the nearest-x2 up-sampled half-resolution tensor is added to the block output
+  // (hourglass up path, :334-359)
   int rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act, T* y_out,
-         T* pool_raw = nullptr);
+         T* pool_raw = nullptr, const T* up_low = nullptr);
   int hourglass(const std::string& p, T x, T a_x, T* out);
   int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
   int emit_upadd(T low, T skip, T out_raw, const char* bn_name, T out_act);

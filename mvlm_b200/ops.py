@@ -27,12 +27,13 @@ def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = Non
                 kh: int = 3, kw: int = 3, y_off0: int | None = None, x_off0: int | None = None,
                 bias=None, mid=None, pre=None, res1=None, res2=None, out_raw=None, post=None,
                 out_f32=None, argmax_keys=None, cout_real: int | None = None,
-                up=(1, 1, 0, 0), pool2: bool = False) -> None:
+                up=(1, 1, 0, 0), pool2: bool = False, res_up=None) -> None:
     """One fused conv launch.
 
     x          : (N,H,W,Cs) bf16; the first `cin` channels are read.
     pre / post : (scale f32[cout_pad], shift f32[cout_pad], out bf16 (N,H,W,Cs'), channel offset)
     res1/res2  : (tensor bf16 (N,H,W,Cs'), channel offset)
+    res_up     : (tensor bf16 (N,H/2,W/2,Cs'), channel offset), added with nearest x2 up-sampling
     out_raw    : (tensor bf16 (N,H,W,Cs'), channel offset)
     """
     lib = _lib.load()
@@ -65,6 +66,8 @@ def conv2d_bf16(x: torch.Tensor, wpacked: torch.Tensor, *, cin: int | None = Non
     a.cout_real = cout_real if cout_real is not None else wpacked.shape[0]
     a.up_sy, a.up_sx, a.up_py, a.up_px = up
     a.pool2 = 1 if pool2 else 0
+    if res_up is not None:
+        a.res_up, a.up_cs, a.up_co = ptr(res_up[0]), res_up[0].shape[-1], res_up[1]
     check(lib.mvlm_conv2d_bf16(C.byref(a), cur_stream()), "mvlm_conv2d_bf16")
 
 

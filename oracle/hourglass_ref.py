@@ -51,9 +51,10 @@ class HourglassOracle:
         b = self.sd.get(f"{name}.bias")
         return F.conv2d(x, w, b, padding=w.shape[-1] // 2)
 
-    def rb(self, x_raw, a_in, p, post=None):
+    def rb(self, x_raw, a_in, p, post=None, up_low=None):
         """ResidualBlock (:267-273).  x_raw: stored block input, a_in = relu(bn1(x)) stored.
-        Returns (y stored, relu(post_bn(y)) stored or None)."""
+        up_low: half-resolution tensor added nearest-x2 up-sampled (:334-359), like the CUDA plan's epilogue
+        before the block output is rounded.  Returns (y stored, relu(post_bn(y)) stored or None)."""
         sd = self.sd
         if f"{p}.resample.2.weight" in sd:
             ar = self.act(x_raw, f"{p}.resample.0")
@@ -66,40 +67,38 @@ class HourglassOracle:
         a2 = self.act(o2, f"{p}.bn3")
         o3 = self.conv(a2, f"{p}.conv3")
         y = torch.cat((o1, o2, o3), 1) + skip
+        if up_low is not None:
+            y = y + F.interpolate(up_low, scale_factor=2, mode="nearest")
         post_act = self.act(y, post) if post is not None else None  # from the un-rounded sum
         return self.q(y), post_act
 
     def hourglass(self, x, a_x, p):
-        """HourGlassModule.forward (:301-361). x stored raw input, a_x = relu(rb1.bn1(x))."""
-        up1, _ = self.rb(x, a_x, f"{p}.rb1")
-        skips = [up1]
+        """HourGlassModule.forward (:301-361). x stored raw input, a_x = relu(rb1.bn1(x)).
+        Same schedule as the CUDA plan: the skip-branch blocks (rb1,3,5,7,9) run on the way up with
+        `interpolate(low) + skip` folded into their output (one rounding instead of two)."""
         cur = x
-        # down path: pool -> rb(even) ; the odd blocks are the skip branches
         low_blocks = [2, 4, 6, 8, 10]
         skip_blocks = [3, 5, 7, 9]
+        lows, a_lows = [], []
         for lvl, lb in enumerate(low_blocks):
             pooled = F.max_pool2d(cur, 2)
             a = self.act(pooled, f"{p}.rb{lb}.bn1")
             nxt = skip_blocks[lvl] if lvl < 4 else 11
             low, a_low = self.rb(pooled, a, f"{p}.rb{lb}", post=f"{p}.rb{nxt}.bn1")
-            if lvl < 4:
-                up, _ = self.rb(low, a_low, f"{p}.rb{skip_blocks[lvl]}")
-                skips.append(up)
+            lows.append(low)
+            a_lows.append(a_low)
             cur = low
         # bottleneck (:332-334)
-        low2, a2 = self.rb(cur, a_low, f"{p}.rb11", post=f"{p}.rb12.bn1")
+        low2, a2 = self.rb(cur, a_lows[4], f"{p}.rb11", post=f"{p}.rb12.bn1")
         low3, _ = self.rb(low2, a2, f"{p}.rb12")
         cur = low3
         # up path (:335-359)
         for lvl, (b1, b2) in enumerate([(13, 14), (15, 16), (17, 18), (19, 20)]):
-            skip = skips[4 - lvl]
-            s = F.interpolate(cur, scale_factor=2, mode="nearest") + skip
-            a = self.act(s, f"{p}.rb{b1}.bn1")
-            s = self.q(s)
+            s, a = self.rb(lows[3 - lvl], a_lows[3 - lvl], f"{p}.rb{skip_blocks[3 - lvl]}", post=f"{p}.rb{b1}.bn1", up_low=cur)
             l1, a1 = self.rb(s, a, f"{p}.rb{b1}", post=f"{p}.rb{b2}.bn1")
             cur, _ = self.rb(l1, a1, f"{p}.rb{b2}")
-        add5 = F.interpolate(cur, scale_factor=2, mode="nearest") + skips[0]
-        return self.q(add5)
+        add5, _ = self.rb(x, a_x, f"{p}.rb1", up_low=cur)
+        return add5
 
     # -- full forward ---------------------------------------------------------
     def forward(self, img_nchw: torch.Tensor, return_intermediates: bool = False):

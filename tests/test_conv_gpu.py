@@ -34,9 +34,11 @@ CASES = [
     (2, 32, 32, 256, 256, 73, 80, 3, 3),     # cout 73 padded to 80
     (1, 32, 32, 96, 96, 84, 96, 3, 3),
     (2, 32, 32, 64, 64, 128, 128, 1, 1),     # 1x1 resample conv
-    (5, 8, 8, 256, 256, 128, 128, 3, 3),     # map smaller than the 16x16 tile
+    (5, 8, 8, 256, 256, 128, 128, 3, 3),     # map smaller than the 8x32 tile
     (5, 4, 4, 128, 128, 64, 64, 3, 3),
-    (2, 24, 40, 64, 64, 64, 64, 3, 3),       # ragged: not a multiple of 16
+    (2, 24, 40, 64, 64, 64, 64, 3, 3),       # ragged: rows not a multiple of the tile height
+    (2, 80, 20, 64, 64, 64, 64, 3, 3),       # ragged: width not a multiple of 8, 2.5 tiles high
+    (3, 2, 2, 256, 256, 128, 128, 3, 3),     # 2x2 map (hourglass bottom of a 64^2 image)
 ]
 
 
@@ -172,3 +174,38 @@ def test_conv_fused_maxpool(lib):
         act = torch.relu(ref * s2 + t2).to(torch.bfloat16).float()
         assert (pact[..., 32:32 + cout].float() - act).abs().max().item() <= act.abs().max().item() * 2.0 ** -7
         assert (praw[..., :32] == 0).all() and (praw[..., 32 + cout:] == 0).all()
+
+
+def test_conv_upsampled_residual(lib):
+    """res_up epilogue: out = conv + res1 + nearest_up2(low) (hourglass up path, paulsenpredictor.py:334-359),
+    with the pre / post activations around it; ragged map so that partial tiles are covered."""
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    for (n, h, w, cin, cout, with_pre, with_post) in ((2, 32, 32, 128, 128, True, True), (1, 48, 24, 64, 64, False, True),
+                                                       (3, 8, 8, 256, 128, True, False), (2, 64, 64, 64, 32, False, False)):
+        g = torch.Generator(device="cuda").manual_seed(17 + cout + h)
+        x = torch.randn((n, h, w, cin), generator=g, device="cuda").to(torch.bfloat16)
+        wt = torch.randn((cout, cin, 3, 3), generator=g, device="cuda") / (cin * 9) ** 0.5
+        s1, t1, s2, t2 = (torch.randn((cout,), generator=g, device="cuda") for _ in range(4))
+        res = torch.randn((n, h, w, 256), generator=g, device="cuda").to(torch.bfloat16)
+        low = torch.randn((n, h // 2, w // 2, 256), generator=g, device="cuda").to(torch.bfloat16)
+        wp = ops.pack_conv_weight(wt, cout, cin)
+        out_pre = torch.zeros((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+        out_raw = torch.zeros((n, h, w, 256), device="cuda", dtype=torch.bfloat16)
+        out_post = torch.zeros((n, h, w, 256), device="cuda", dtype=torch.bfloat16)
+        ops.conv2d_bf16(x, wp, n_tile=cout, pre=(s1, t1, out_pre, 0) if with_pre else None, res1=(res, 64),
+                        res_up=(low, 96), out_raw=(out_raw, 32), post=(s2, t2, out_post, 32) if with_post else None)
+        torch.cuda.synchronize()
+        v = _ref_conv(x, wt, None, 3, 3, -1, -1)
+        tol = 2e-3 * v.abs().max().item()
+        if with_pre:
+            pre_ref = torch.relu(v * s1 + t1)
+            assert (out_pre.float() - pre_ref).abs().max().item() <= tol * s1.abs().max().item() + pre_ref.abs().max().item() * 2.0 ** -8
+        up = F.interpolate(low[..., 96:96 + cout].float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+        v2 = v + res[..., 64:64 + cout].float() + up
+        assert (out_raw[..., 32:32 + cout].float() - v2).abs().max().item() <= tol + v2.abs().max().item() * 2.0 ** -8
+        assert (out_raw[..., :32] == 0).all() and (out_raw[..., 32 + cout:] == 0).all()
+        if with_post:
+            post_ref = torch.relu(v2 * s2 + t2)
+            assert (out_post[..., 32:32 + cout].float() - post_ref).abs().max().item() <= tol * s2.abs().max().item() + post_ref.abs().max().item() * 2.0 ** -8
