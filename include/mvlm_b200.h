@@ -71,11 +71,13 @@ typedef struct mvlm_conv_args {
 
 int mvlm_conv2d_bf16(const mvlm_conv_args* args, void* stream);
 
-/* Debug aid: when dev_buf (148*8 int64, device) is non-NULL the following conv launches record per-CTA role
+/* Debug aid: when dev_buf (mvlm_debug_conv_profile_ints() int64, device) is non-NULL the following conv launches record per-CTA role
  * stall cycles there: [0] producer wait A-empty, [1] producer wait B-empty, [2] MMA wait operands,
  * [3] MMA wait accumulator-free, [4] MMA total, [5] epilogue wait accumulator-full, [6] epilogue total,
  * [7] producer total.  NULL switches it off. */
 void mvlm_debug_conv_profile(long long* dev_buf);
+/* number of int64 the buffer given to mvlm_debug_conv_profile must hold (role counters + CTA-0 tile timeline) */
+int mvlm_debug_conv_profile_ints(void);
 /* Debug experiment switch: 1 = tensor-pipe-only timing (no TMA loads; outputs are garbage), 0 = normal. */
 void mvlm_debug_conv_mode(int mode);
 
@@ -127,7 +129,9 @@ int mvlm_hourglass_num_launches(const mvlm_hourglass* net);
  * device), optionally the conv kernel's per-role stall cycles (roles_out[num_launches*8] host doubles, layout of
  * mvlm_debug_conv_profile, mean over CTAs), and a one-line description of op `op`. */
 int mvlm_debug_hourglass_profile(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
-                                 float* out_peaks, int reps, float* ms_out, double* roles_out, void* stream);
+                                 float* out_peaks, int reps, float* ms_out, double* roles_out, int trace_op,
+                                 long long* trace_out /* 64 x 16 int64 timeline of CTA 0 of conv op trace_op, or NULL */,
+                                 void* stream);
 int mvlm_debug_hourglass_describe(const mvlm_hourglass* net, int op, char* buf, int buf_len);
 /* layer-wise parity probes: "r3", "hg1", "sum_temp", "x10" -> NHWC bf16 tensor in the workspace */
 int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c);

@@ -75,7 +75,9 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_hourglass_forward": ([vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_forward_graph": ([vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_num_launches": ([vp], i32),
-        "mvlm_debug_hourglass_profile": ([vp, vp, vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_double), vp], i32),
+        "mvlm_debug_hourglass_profile": ([vp, vp, vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_double), i32,
+                                         C.POINTER(C.c_longlong), vp], i32),
+        "mvlm_debug_conv_profile_ints": ([], i32),
         "mvlm_debug_hourglass_describe": ([vp, i32, C.c_char_p, i32], i32),
         "mvlm_hourglass_probe": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
         "mvlm_hourglass_destroy": ([vp], None),

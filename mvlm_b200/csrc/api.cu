@@ -55,6 +55,7 @@ long long mvlm_launch_count(int reset) {
 }
 
 void mvlm_debug_conv_profile(long long* dev_buf) { conv_set_profile_buffer(dev_buf); }
+int mvlm_debug_conv_profile_ints(void) { return kConvProfInts; }
 void mvlm_debug_conv_mode(int mode) { conv_set_debug_mode(mode); }
 
 int mvlm_conv2d_bf16(const mvlm_conv_args* a, void* stream) {
@@ -160,9 +161,11 @@ int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, con
 }
 
 int mvlm_debug_hourglass_profile(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, float* out_peaks,
-                                 int reps, float* ms_out, double* roles_out, void* stream) {
+                                 int reps, float* ms_out, double* roles_out, int trace_op, long long* trace_out,
+                                 void* stream) {
   MVLM_REQUIRE(net, "mvlm_debug_hourglass_profile: null handle");
-  return net->net.profile_ops(img_u8, img_f32, out_peaks, reps, ms_out, roles_out, static_cast<cudaStream_t>(stream));
+  return net->net.profile_ops(img_u8, img_f32, out_peaks, reps, ms_out, roles_out, trace_op, trace_out,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int mvlm_debug_hourglass_describe(const mvlm_hourglass* net, int op, char* buf, int buf_len) {

@@ -8,9 +8,9 @@
 // tile as B (N=256) the same instruction does 128 cycles of math (measured 145), so the A stream is
 // hidden -- see tools/exp_mma_only.py and DESIGN.md section 4.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer   X: ONE halo tile (8+KW-1 px x 32+KH-1 rows x 64 ch) per cin-chunk;
-//                              W: one [<=128 cout][64 cin] tile per (cin-chunk, kx, ky)
+// One persistent CTA per SM, 11 warps:
+//   warp 0      TMA producer   X: ONE halo tile (8+KW-1 px x 32+KH-1 rows x 64 ch) per cin-chunk
+//   warp 10     TMA producer   W: one [<=128 cout][64 cin] tile per (cin-chunk, kx, ky)
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma (M=128, N=256, K=16); owns TMEM
 //   warps 2..9  epilogue       tcgen05.ld (lane = channel, 16 pixels) -> smem transpose ->
 //                              bias/BN/ReLU/residual on (pixel, 8 channels) vectors -> 16-byte stores
@@ -38,7 +38,7 @@ namespace mvlm {
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;                          // warps: 0 halo TMA, 1 MMA, 2..9 epilogue, 10 weight TMA
 constexpr int kEpiWarps = 8;
 constexpr int kTileW = 8;                               // output tile: 8 px wide ...
 constexpr int kMaxTileH = 32;                           // ... and up to 32 rows high (N = 256)
@@ -49,6 +49,7 @@ constexpr int kWSlotBytes = kMTile * 128;               // 128 cout rows x 64 ci
 constexpr int kPoolBytes = 200 * 1024;                  // both rings
 constexpr int kStageFloats = 16 * 36;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad)
 constexpr int kMaxCout = 256;
+constexpr int kTraceTiles = 64;                        // debug timeline: tiles traced on CTA 0
 
 struct __align__(8) Barriers {
   uint64_t h_full[kMaxHSlots];
@@ -91,6 +92,21 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   r.y = *reinterpret_cast<uint32_t*>(&b);
   r.z = *reinterpret_cast<uint32_t*>(&c);
   r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+// relu + round to bf16 in one instruction per pair (cvt.rn.relu.bf16x2.f32: first source -> upper half)
+__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// relu(f * s + t) -> bf16 x 8
+__device__ __forceinline__ uint4 affine_relu_pack8(const float (&f)[8], const float (&sc)[8], const float (&sh)[8]) {
+  uint4 r;
+  r.x = relu_bf16x2(fmaf(f[0], sc[0], sh[0]), fmaf(f[1], sc[1], sh[1]));
+  r.y = relu_bf16x2(fmaf(f[2], sc[2], sh[2]), fmaf(f[3], sc[3], sh[3]));
+  r.z = relu_bf16x2(fmaf(f[4], sc[4], sh[4]), fmaf(f[5], sc[5], sh[5]));
+  r.w = relu_bf16x2(fmaf(f[6], sc[6], sh[6]), fmaf(f[7], sc[7], sh[7]));
   return r;
 }
 __device__ __forceinline__ void add8(const uint4& q, float (&f)[8]) {
@@ -224,42 +240,71 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const bool prof = p.prof != nullptr;
   const long long t_kernel0 = clock64();
   long long w0 = 0, w1 = 0;
+  // per-tile timeline of CTA 0 (first kTraceTiles tiles), cycles since kernel start:
+  //   [0] producer: halo load of chunk 0 issued   [1] producer: last weight load issued
+  //   [2] MMA: accumulator stage acquired         [3] MMA: first halo tile landed      [4] MMA: all MMAs issued
+  //   [5] epilogue warp 2: accumulator ready      [6] epilogue warp 2: stage released
+  //   epilogue warp 2, unit r = 0 / 1: [8 + 4r] accumulator columns in registers, [9 + 4r] transposed to shared
+  //   memory, [10 + 4r] outputs computed and stores issued, [11 + 4r] unit done (rolling prefetch issued)
+  long long* const trace = (prof && blockIdx.x == 0) ? p.prof + kNumSMs * 8 : nullptr;
+  int trace_i = 0;
+#define MVLM_TRACE(slot)                                                                  \
+  do {                                                                                    \
+    if (trace && trace_i < kTraceTiles) trace[trace_i * 16 + (slot)] = clock64() - t_kernel0; \
+  } while (0)
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: activations =====================
+    // Its own thread, so that the halo prefetch runs n_hslots chunks ahead of the MMAs whatever the state of the
+    // weight ring (measured: behind the weight loads in one queue the next halo tile was issued ~4k cycles before
+    // it was needed, about the DRAM + queueing latency of the load, and the tensor pipe waited for it every tile).
     if (ptx::elect_one() && p.debug_mode == 0) {
-      int sh = 0, sw = 0;
-      uint32_t ph = 0, pw = 0;
+      int sh = 0;
+      uint32_t ph = 0;
       for (int t = t_begin; t < t_end; t += t_step) {
         const TileCoord tc = decode_tile(p, t);
         const int x0 = tc.tx * kTileW + s.x_off0;
         const int y0 = tc.ty * p.tile_h + s.y_off0;
         for (int c = 0; c < n_chunks; ++c) {
-          // the last chunk may be a narrow tail (16 / 32 channels) with its own tensor maps: rows of 32 / 64 bytes
+          // the last chunk may be a narrow tail (16 / 32 channels) with its own tensor map: rows of 32 / 64 bytes
           const bool is_tail = p.tail != 0 && c == n_chunks - 1;
-          const void* tma = is_tail ? &p.tm_a2 : &p.tm_a;
-          const void* tmb = is_tail ? &p.tm_b2 : &p.tm_b;
-          const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per pixel / weight row
-          const uint32_t hb = static_cast<uint32_t>(halo_rows * halo_px) * row_b;
-          const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
-          // one halo tile for all KW x KH taps of this chunk
+          const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per pixel
           timed_wait(&bar->h_empty[sh], ph ^ 1, prof, w0);
-          ptx::mbar_expect_tx(&bar->h_full[sh], hb);
-          ptx::tma_load_4d(tma, &bar->h_full[sh], h_slots + sh * p.h_slot_bytes, c * 64, x0, y0, tc.img);
+          ptx::mbar_expect_tx(&bar->h_full[sh], static_cast<uint32_t>(halo_rows * halo_px) * row_b);
+          // one halo tile for all KW x KH taps of this chunk
+          ptx::tma_load_4d(is_tail ? &p.tm_a2 : &p.tm_a, &bar->h_full[sh], h_slots + sh * p.h_slot_bytes, c * 64, x0, y0, tc.img);
+          if (c == 0) MVLM_TRACE(0);
           if (++sh == n_hslots) { sh = 0; ph ^= 1; }
-          for (int kx = 0; kx < s.kw; ++kx) {
-            for (int ky = 0; ky < s.kh; ++ky) {
-              timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
-              ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
-              for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
-                ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * row_b,
-                                 (kx * s.kh + ky) * s.cin + c * 64, tc.mt * kMTile);
-              if (++sw == n_wslots) { sw = 0; pw ^= 1; }
-            }
+        }
+        ++trace_i;
+      }
+      if (prof) { p.prof[blockIdx.x * 8 + 0] = w0; p.prof[blockIdx.x * 8 + 7] = clock64() - t_kernel0; }
+    }
+  } else if (warp == 10) {
+    // ===================== TMA producer: weights =====================
+    if (ptx::elect_one() && p.debug_mode == 0) {
+      int sw = 0;
+      uint32_t pw = 0;
+      for (int t = t_begin; t < t_end; t += t_step) {
+        const int mt = t % p.n_nt;
+        for (int c = 0; c < n_chunks; ++c) {
+          const bool is_tail = p.tail != 0 && c == n_chunks - 1;
+          const void* tmb = is_tail ? &p.tm_b2 : &p.tm_b;
+          const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per weight row
+          const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
+          for (int tap = 0; tap < s.kw * s.kh; ++tap) {  // tap = kx * KH + ky
+            timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
+            ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
+            for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
+              ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * row_b,
+                               tap * s.cin + c * 64, mt * kMTile);
+            if (++sw == n_wslots) { sw = 0; pw ^= 1; }
           }
         }
+        MVLM_TRACE(1);
+        ++trace_i;
       }
-      if (prof) { p.prof[blockIdx.x * 8 + 0] = w0; p.prof[blockIdx.x * 8 + 1] = w1; p.prof[blockIdx.x * 8 + 7] = clock64() - t_kernel0; }
+      if (prof) p.prof[blockIdx.x * 8 + 1] = w1;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -277,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       for (int t = t_begin; t < t_end; t += t_step) {
         timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
         ptx::tc_fence_after();
+        MVLM_TRACE(2);
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
         uint32_t accumulate = 0;
         for (int c = 0; c < n_chunks; ++c) {
@@ -289,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const uint64_t a_hi = static_cast<uint64_t>(((8u * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
           const uint64_t b_hi = static_cast<uint64_t>(((static_cast<uint32_t>(halo_px) * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
           if (p.debug_mode == 0) timed_wait(&bar->h_full[sh], ph, prof, w0);
+          if (c == 0) MVLM_TRACE(3);
           const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * p.h_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
           for (int kx = 0; kx < s.kw; ++kx) {
             for (int ky = 0; ky < s.kh; ++ky) {
@@ -314,6 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           if (++sh == n_hslots) { sh = 0; ph ^= 1; }
         }
         ptx::umma_commit(&bar->t_full[acc]);
+        MVLM_TRACE(4);
+        ++trace_i;
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
       if (prof) { p.prof[blockIdx.x * 8 + 2] = w0; p.prof[blockIdx.x * 8 + 3] = w1; p.prof[blockIdx.x * 8 + 4] = clock64() - t_kernel0; }
@@ -340,6 +389,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int pj = lane >> 2;
     const int cq = (lane & 3) * 8;
     constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
+    // byte strides of one image row in every tensor the epilogue touches: an access of unit r, row i is then
+    // (per-tile base pointer) + (2r + i) * stride with a compile-time (2r + i)
+    const uint32_t rs_pre = static_cast<uint32_t>(s.w * e.pre_cs) * 2u, rs_res1 = static_cast<uint32_t>(s.w * e.res1_cs) * 2u;
+    const uint32_t rs_res2 = static_cast<uint32_t>(s.w * e.res2_cs) * 2u;
+    const uint32_t rs_up = static_cast<uint32_t>((s.w >> 1) * e.up_cs) * 2u;
+    // F_POOL: raw / post live at half resolution, one pooled row per unit
+    const uint32_t rs_raw = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.raw_cs) * 2u;
+    const uint32_t rs_post = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.post_cs) * 2u;
     for (int t = t_begin; t < t_end; t += t_step) {
       const TileCoord tc = decode_tile(p, t);
       const int m0 = tc.mt * kMTile;
@@ -366,22 +423,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       // tile still run, unit r + kPref is fetched as soon as unit r has been consumed (rolling window)
       constexpr int kPref = (F & (F_RES2 | F_UP)) ? 4 : 8;
       uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1];
+      // per-tile base pointers of my (pixel column, 8 channels) at the first row of my first unit
+      const uint32_t opix0 = (F & F_POOL) ? ppix0 : pix0;
+      uint8_t* const b_pre = (F & F_PRE) ? reinterpret_cast<uint8_t*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(pix0) * e.pre_cs) : nullptr;
+      uint8_t* const b_raw = (F & F_RAW) ? reinterpret_cast<uint8_t*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(opix0) * e.raw_cs) : nullptr;
+      uint8_t* const b_post = (F & F_POST) ? reinterpret_cast<uint8_t*>(e.out_post + e.post_co + c0 + static_cast<size_t>(opix0) * e.post_cs) : nullptr;
+      const uint8_t* const b_res1 = (F & F_RES1) ? reinterpret_cast<const uint8_t*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix0) * e.res1_cs) : nullptr;
+      const uint8_t* const b_res2 = (F & F_RES2) ? reinterpret_cast<const uint8_t*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix0) * e.res2_cs) : nullptr;
+      const uint8_t* const b_up = (F & F_UP) ? reinterpret_cast<const uint8_t*>(e.res_up + e.up_co + c0 + static_cast<size_t>(ppix0) * e.up_cs) : nullptr;
+      // rows of this warp's part of the tile that exist in the image (0 when my pixel column / channels do not)
+      const int n_rows_ok = vx ? s.h - y_first : 0;
       auto prefetch_unit = [&](int u) {  // u: compile-time after unrolling
         if (u < upw) {
           const int q = u % kPref;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            if (vx && y_first + 2 * u + i < s.h) {
-              const uint32_t pix = pix0 + (2 * u + i) * s.w;
-              if (F & F_RES1)
-                r1[q][i] = *reinterpret_cast<const uint4*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix * e.res1_cs));
-              if (F & F_RES2)
-                r2[q][i] = *reinterpret_cast<const uint4*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix * e.res2_cs));
+            if (2 * u + i < n_rows_ok) {
+              if (F & F_RES1) r1[q][i] = *reinterpret_cast<const uint4*>(b_res1 + static_cast<size_t>((2 * u + i) * rs_res1));
+              if (F & F_RES2) r2[q][i] = *reinterpret_cast<const uint4*>(b_res2 + static_cast<size_t>((2 * u + i) * rs_res2));
             }
           }
           // nearest x2: rows y, y+1 and columns xa, xa^1 all read low-res pixel (y/2, xa/2)
-          if ((F & F_UP) && vx && y_first + 2 * u < s.h)
-            ru[q] = *reinterpret_cast<const uint4*>(e.res_up + e.up_co + c0 + static_cast<size_t>((ppix0 + u * (s.w >> 1)) * e.up_cs));
+          if ((F & F_UP) && 2 * u < n_rows_ok) ru[q] = *reinterpret_cast<const uint4*>(b_up + static_cast<size_t>(u * rs_up));
         }
       };
       if ((F & (F_RES1 | F_RES2 | F_UP)) && grp_active && rows_active) {
@@ -396,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const float mid_s_c = ep->mid_s[c_lane < kMaxCout ? c_lane : 0], mid_t_c = ep->mid_t[c_lane < kMaxCout ? c_lane : 0];
       timed_wait(&bar->t_full[acc], pacc, prof, w0);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0) MVLM_TRACE(5);
       if (grp_active && rows_active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                                static_cast<uint32_t>(acc * 256 + u_begin * 16);
@@ -406,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           if (r < upw) {
             const int y = y_first + 2 * r;  // image rows y (columns 0..7 of the unit) and y+1 (columns 8..15)
             ptx::tmem_ld_wait();
+            if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(8 + 4 * r);
             if (r + 1 < upw) ptx::tmem_ld16(taddr + (r + 1) * 16, v[(r + 1) & 1]);  // next unit in flight
             const uint32_t(&vr)[16] = v[r & 1];
             if (y < s.h) {
@@ -453,20 +518,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   stage[j * 36 + lane] = f;
                 }
                 __syncwarp();
+                if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(9 + 4 * r);
                 uint4 pool_cur[2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                  const bool valid = vx && y + i < s.h;
-                  const uint32_t px = pix0 + (2 * r + i) * s.w;
+                  const bool valid = 2 * r + i < n_rows_ok;
                   float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                   if (valid) {
                     lds8(stage + (pj + 8 * i) * 36 + cq, f);
-                    if (F & F_PRE) {
-                      float g[8];
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], pre_s[j], pre_t[j]), 0.f);
-                      *reinterpret_cast<uint4*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(px * e.pre_cs)) = pack8(g);
-                    }
+                    if (F & F_PRE)
+                      *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>((2 * r + i) * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
                     if (F & F_RES1) add8(r1[r % kPref][i], f);
                     if (F & F_RES2) add8(r2[r % kPref][i], f);
                     if (F & F_UP) add8(ru[r % kPref], f);
@@ -474,16 +535,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   if (F & F_POOL) {
                     pool_cur[i] = pack8(f);
                   } else if (valid) {
-                    if (F & F_RAW)
-                      *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(px * e.raw_cs)) = pack8(f);
-                    if (F & F_POST) {
-                      float g[8];
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(f[j], post_s[j], post_t[j]), 0.f);
-                      *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(px * e.post_cs)) = pack8(g);
-                    }
+                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>((2 * r + i) * rs_raw)) = pack8(f);
+                    if (F & F_POST)
+                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>((2 * r + i) * rs_post)) = affine_relu_pack8(f, post_s, post_t);
                   }
                 }
+                if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(10 + 4 * r);
                 if ((F & (F_RES1 | F_RES2 | F_UP)) && r + kPref < 8) prefetch_unit(r + kPref);
                 if (F & F_POOL) {
                   // 2x2 max-pool of the bf16-rounded values: vertical partner = the unit's other row (same lane),
@@ -495,19 +552,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   o.z = __shfl_xor_sync(0xffffffffu, m.z, 4);
                   o.w = __shfl_xor_sync(0xffffffffu, m.w, 4);
                   m = max_bf16x8(m, o);
-                  if (vx && (pj & 1) == 0) {  // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
-                    const uint32_t pp = ppix0 + r * (s.w >> 1);
-                    if (F & F_RAW)
-                      *reinterpret_cast<uint4*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(pp * e.raw_cs)) = m;
+                  if (2 * r < n_rows_ok && (pj & 1) == 0) {  // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
+                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(r * rs_raw)) = m;
                     if (F & F_POST) {
                       float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                       add8(m, g);
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) g[j] = fmaxf(fmaf(g[j], post_s[j], post_t[j]), 0.f);
-                      *reinterpret_cast<uint4*>(e.out_post + e.post_co + c0 + static_cast<size_t>(pp * e.post_cs)) = pack8(g);
+                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(r * rs_post)) = affine_relu_pack8(g, post_s, post_t);
                     }
                   }
                 }
+                if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(11 + 4 * r);
               }
             }
           }
@@ -517,6 +571,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar->t_empty[acc]);
+      if (warp == 2 && lane == 0) MVLM_TRACE(6);
+      ++trace_i;
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
     if ((F & F_ARGMAX) && cur_img >= 0 && best_hi != 0u) {
@@ -528,6 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = w0; p.prof[blockIdx.x * 8 + 6] = clock64() - t_kernel0; }
   }
 
+#undef MVLM_TRACE
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {

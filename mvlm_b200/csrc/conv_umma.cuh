@@ -87,7 +87,10 @@ struct alignas(64) ConvParams {
 int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out);
 // Launches the persistent kernel for a planned conv.
 int conv_launch(const ConvParams& p, cudaStream_t stream);
-// Debug: when non-null, the next conv_launch calls record role timings there (148 x 8 int64).
+// Debug: when non-null, the next conv_launch calls record role timings there (148 x 8 int64) followed by the
+// per-tile timeline of CTA 0 (kConvTraceTiles x 16 int64, see conv_umma.cu).
+constexpr int kConvTraceTiles = 64;
+constexpr int kConvProfInts = 148 * 8 + kConvTraceTiles * 16;
 void conv_set_profile_buffer(long long* dev_buf);
 void conv_set_debug_mode(int mode);
 

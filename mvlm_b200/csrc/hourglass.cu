@@ -400,7 +400,9 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
   // conv2 block: its output is only consumed through the max-pool (:411) -> pooled outputs straight from the epilogues
   T x1;
   if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, "conv3.bn1", &a3, &y2, &x1))) return rc;
+  probes["x1"] = {x1.p, x1.h, x1.w, x1.c};
   if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3))) return rc;
+  probes["y3"] = {y3.p, y3.h, y3.w, y3.c};
   ar4 = alloc(h2, w2, 128);
   {
     NetOp op;
@@ -548,7 +550,8 @@ int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, flo
 }
 
 int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32, float* out_peaks, int reps,
-                              float* ms_out, double* roles_out, cudaStream_t stream) {
+                              float* ms_out, double* roles_out, int trace_op, long long* trace_out,
+                              cudaStream_t stream) {
   MVLM_REQUIRE(!dry_ && out_peaks && ms_out && reps > 0, "hourglass: bad profile_ops arguments");
   const size_t n = ops_.size();
   std::vector<cudaEvent_t> ev(n + 1);
@@ -572,19 +575,21 @@ int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32,
   if (roles_out && rc == MVLM_OK) {
     // one more pass with the conv kernel's role counters on: mean over the CTAs that ran (see conv_umma.cu)
     long long* dev = nullptr;
-    MVLM_CHECK_CUDA(cudaMalloc(&dev, sizeof(long long) * kNumSMs * 8));
-    std::vector<long long> host(kNumSMs * 8);
+    MVLM_CHECK_CUDA(cudaMalloc(&dev, sizeof(long long) * kConvProfInts));
+    std::vector<long long> host(kConvProfInts);
     for (size_t i = 0; i < n && rc == MVLM_OK; ++i) {
       for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] = 0.0;
       if (ops_[i].kind == NetOp::CONV) {
-        MVLM_CHECK_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * kNumSMs * 8, stream));
+        MVLM_CHECK_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * kConvProfInts, stream));
         conv_set_profile_buffer(dev);
       }
       rc = run_op(ops_[i], img_u8, img_f32, nullptr, out_peaks, stream);
       conv_set_profile_buffer(nullptr);
       if (ops_[i].kind == NetOp::CONV && rc == MVLM_OK) {
         MVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
-        MVLM_CHECK_CUDA(cudaMemcpy(host.data(), dev, sizeof(long long) * kNumSMs * 8, cudaMemcpyDeviceToHost));
+        MVLM_CHECK_CUDA(cudaMemcpy(host.data(), dev, sizeof(long long) * kConvProfInts, cudaMemcpyDeviceToHost));
+        if (trace_out && static_cast<int>(i) == trace_op)
+          for (int k = 0; k < kConvTraceTiles * 16; ++k) trace_out[k] = host[kNumSMs * 8 + k];
         int ctas = 0;
         for (int c = 0; c < kNumSMs; ++c) {
           if (host[c * 8 + 4] == 0) continue;
@@ -607,8 +612,8 @@ std::string HourglassNet::describe_op(int i) const {
     case NetOp::CONV: {
       const ConvShape& s = op.conv.s;
       const ConvEpilogue& e = op.conv.e;
-      snprintf(buf, sizeof(buf), "conv %s %dx%d %d->%d k%d%s%s%s%s%s%s%s", op.tag, s.h, s.w, s.cin, s.cout_pad, s.kh,
-               e.out_pre ? " pre" : "", e.res1 ? " res1" : "", e.res2 ? " res2" : "", e.out_raw ? " raw" : "",
+      snprintf(buf, sizeof(buf), "conv %s %dx%d %d->%d k%d%s%s%s%s%s%s%s%s", op.tag, s.h, s.w, s.cin, s.cout_pad, s.kh,
+               e.out_pre ? " pre" : "", e.res1 ? " res1" : "", e.res2 ? " res2" : "", e.res_up ? " up" : "", e.out_raw ? " raw" : "",
                e.out_post ? " post" : "", e.pool2 ? " pool" : "", e.argmax_keys ? " argmax" : "");
       break;
     }

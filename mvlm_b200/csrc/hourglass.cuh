@@ -44,8 +44,9 @@ class HourglassNet {
 
   // Debug aid: runs the plan `reps` times with a CUDA event pair around every op; ms_out[n_ops()] = mean ms per op.
   // roles_out (optional, n_ops() x 8 doubles): mean per-CTA role stall cycles of every conv op (conv_umma.cu).
+  // trace_out (optional, kConvTraceTiles x 8 int64): per-tile timeline of CTA 0 of conv op `trace_op`.
   int profile_ops(const unsigned char* img_u8, const float* img_f32, float* out_peaks, int reps, float* ms_out,
-                  double* roles_out, cudaStream_t stream);
+                  double* roles_out, int trace_op, long long* trace_out, cudaStream_t stream);
   // one-line description of op i ("conv rb.conv 128x128 256->128 k3 F=0x1b", "upadd 64x64x256", ...)
   std::string describe_op(int i) const;
 

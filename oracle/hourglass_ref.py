@@ -113,8 +113,10 @@ class HourglassOracle:
             # conv2 block has a resample skip that consumes x0 through its own BN
             y2, _ = self._rb_from_fp32(x0, a, "conv2")
             x1 = F.max_pool2d(y2, 2)
+            inter["x1"] = x1
             a = self.act(x1, "conv3.bn1")
             y3, a4 = self.rb(x1, a, "conv3", post="conv4.bn1")
+            inter["y3"] = y3
             r3, a_h1 = self.rb(y3, a4, "conv4", post="hg1.rb1.bn1")
             inter["r3"] = r3
             h1 = self.hourglass(r3, a_h1, "hg1")

@@ -51,14 +51,14 @@ def test_hourglass_matches_oracle(lib, n_landmarks, mode, size, views):
     std = ref32.std().item()
     assert torch.isfinite(hm).all()
     # layer-wise probes first (localises a failure)
-    for name in ("r3", "hg1", "sum_temp", "x10"):
+    for name in ("x1", "y3", "r3", "hg1", "sum_temp", "x10"):
         got = _nchw(net.probe(name))[:, : inter[name].shape[1]]
         s = inter32[name].std().item()
         e_emu = (got - inter[name]).abs().mean().item() / s
         e_32 = (got - inter32[name]).abs()
         ideal = (inter[name] - inter32[name]).abs().mean().item() / s
         print(f"{name}: cuda-emu {e_emu:.5f} cuda-fp32 {e_32.mean().item() / s:.5f} emu-fp32 {ideal:.5f} (fractions of std)")
-        if name == "r3":
+        if name in ("x1", "y3", "r3"):
             assert e_emu <= 2e-3, (name, e_emu)
         assert e_32.mean().item() / s <= 0.012 and e_32.max().item() / s <= 0.12, (name, e_32.mean().item() / s, e_32.max().item() / s)
         assert e_32.mean().item() / s <= 1.25 * ideal + 1e-4, (name, e_32.mean().item() / s, ideal)

@@ -1,0 +1,147 @@
+// Experiment (GPU box): tcgen05.mma cta_group::1 with M=64: (a) which TMEM lanes hold the 64 output rows,
+// (b) cycles per instruction against M=128 at N=256, K=16 (operands resident in shared memory, no TMA traffic).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -I mvlm_b200/csrc tools/exp_m64.cu -o tools/_bin/exp_m64 -lcuda
+#include <cstdio>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace mvlm;
+
+struct Args {
+  CUtensorMap tm_a, tm_x;
+  float* out;  // [128][256]
+  long long* cycles;
+  int m, n_mma;
+};
+
+__global__ void __launch_bounds__(128, 1) k(const __grid_constant__ Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* sA = smem;          // 128 x 128 B
+  uint8_t* sX = smem + 16384;  // 256 x 128 B
+  __shared__ uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar_full, 1);
+    ptx::mbar_init(&bar_done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_base_s, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::mbar_expect_tx(&bar_full, 16384 + 32768);
+    ptx::tma_load_2d(&a.tm_a, &bar_full, sA, 0, 0);
+    ptx::tma_load_2d(&a.tm_x, &bar_full, sX, 0, 0);
+    ptx::mbar_wait(&bar_full, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::umma_idesc_bf16(a.m, 256);
+    const long long t0 = clock64();
+    for (int i = 0; i < a.n_mma; ++i) {
+      const int kk = i & 3;
+      ptx::umma_bf16(tmem, ptx::umma_desc_sw128(ptx::smem_u32(sA) + kk * 32), ptx::umma_desc_sw128(ptx::smem_u32(sX) + kk * 32),
+                     idesc, i > 0 ? 1u : 0u);
+    }
+    ptx::umma_commit(&bar_done);
+    ptx::mbar_wait(&bar_done, 0);
+    a.cycles[0] = clock64() - t0;
+  }
+  __syncwarp();
+  ptx::mbar_wait(&bar_done, 0);
+  ptx::tc_fence_after();
+  for (int c = 0; c < 256; c += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    ptx::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) a.out[(warp * 32 + lane) * 256 + c + j] = __uint_as_float(v[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+namespace mvlm {
+void set_error(const char*, ...) {}
+void count_launch(int) {}
+}  // namespace mvlm
+
+int main() {
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaFree(0);
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return 2;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(sym);
+  // A[m][k] = (m + 1) if k == 0 else 0 ; X[n][k] = 1 if k == 0 -> D[m][n] = m + 1 for every n (one K=16 step, kk = 0)
+  std::vector<__nv_bfloat16> hA(128 * 64), hX(256 * 64);
+  for (int m = 0; m < 128; ++m)
+    for (int kk = 0; kk < 64; ++kk) hA[m * 64 + kk] = __float2bfloat16(kk == 0 ? float(m + 1) : 0.f);
+  for (int n = 0; n < 256; ++n)
+    for (int kk = 0; kk < 64; ++kk) hX[n * 64 + kk] = __float2bfloat16(kk == 0 ? 1.f : 0.f);
+  __nv_bfloat16 *dA, *dX;
+  float* dOut;
+  long long* dCyc;
+  cudaMalloc(&dA, hA.size() * 2);
+  cudaMalloc(&dX, hX.size() * 2);
+  cudaMalloc(&dOut, 128 * 256 * 4);
+  cudaMalloc(&dCyc, 8);
+  cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice);
+  Args a;
+  {
+    cuuint64_t gdim[2] = {64, 128};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
+    if (enc(&a.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE))
+      return 3;
+    cuuint64_t gdim2[2] = {64, 256};
+    cuuint32_t box2[2] = {64, 256};
+    if (enc(&a.tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dX, gdim2, gstr, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE))
+      return 4;
+  }
+  a.out = dOut;
+  a.cycles = dCyc;
+  const int smem = 16384 + 32768 + 2048;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  std::vector<float> h(128 * 256);
+  for (int m : {128, 64}) {
+    a.m = m;
+    a.n_mma = 1;
+    cudaMemset(dOut, 0, 128 * 256 * 4);
+    k<<<1, 128, smem>>>(a);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("M=%d: error %s\n", m, cudaGetErrorString(cudaGetLastError())); return 5; }
+    cudaMemcpy(h.data(), dOut, h.size() * 4, cudaMemcpyDeviceToHost);
+    printf("M=%d: TMEM lane -> value of column 0 (output row index + 1; stale = other):\n ", m);
+    for (int l = 0; l < 128; ++l) printf(" %g", h[l * 256]);
+    printf("\n  column 200 of lanes 0..3, 16..19: %g %g %g %g | %g %g %g %g\n", h[200], h[256 + 200], h[512 + 200], h[768 + 200],
+           h[16 * 256 + 200], h[17 * 256 + 200], h[18 * 256 + 200], h[19 * 256 + 200]);
+    for (int n_mma : {64, 512}) {
+      a.n_mma = n_mma;
+      long long best = 1ll << 60;
+      for (int rep = 0; rep < 3; ++rep) {
+        k<<<1, 128, smem>>>(a);
+        cudaDeviceSynchronize();
+        long long c;
+        cudaMemcpy(&c, dCyc, 8, cudaMemcpyDeviceToHost);
+        if (c < best) best = c;
+      }
+      printf("  M=%d N=256 K=16: %d MMAs in %lld cycles = %.1f cycles per MMA\n", m, n_mma, best, double(best) / n_mma);
+    }
+  }
+  return 0;
+}

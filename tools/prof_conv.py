@@ -38,13 +38,13 @@ print("ok")
 import ctypes as C  # noqa: E402
 from mvlm_b200 import _lib  # noqa: E402
 lib = _lib.load()
-buf = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+buf = torch.zeros((148 + 128, 8), dtype=torch.int64, device="cuda")  # role counters + CTA-0 tile timeline
 lib.mvlm_debug_conv_profile.argtypes = [C.c_void_p]
 lib.mvlm_debug_conv_profile(buf.data_ptr())
 ops.conv2d_bf16(x, wp, n_tile=nt, kh=k, kw=k, **kw)
 torch.cuda.synchronize()
 lib.mvlm_debug_conv_profile(None)
-b = buf.double().mean(0).cpu().numpy()
+b = buf[:148].double().mean(0).cpu().numpy()
 names = ["prod wait A-empty", "prod wait B-empty", "mma wait operands", "mma wait acc-free", "mma total", "epi wait acc-full", "epi total", "prod total"]
 for n, v in zip(names, b):
     print(f"{n:20s} {v / 1e3:10.1f} kcycles")

@@ -20,8 +20,23 @@ peaks = torch.empty((73, V, 3), dtype=torch.float32, device="cuda")
 n = net.num_launches
 ms = (C.c_float * n)()
 roles = (C.c_double * (8 * n))()
-_lib.check(lib.mvlm_debug_hourglass_profile(net._h, img.data_ptr(), None, peaks.data_ptr(), 5, ms, roles,
+trace_op = -1
+for a in sys.argv:
+    if a.startswith("--trace="):
+        trace_op = int(a.split("=")[1])
+trace = (C.c_longlong * (64 * 16))()
+_lib.check(lib.mvlm_debug_hourglass_profile(net._h, img.data_ptr(), None, peaks.data_ptr(), 5, ms, roles, trace_op, trace,
                                             torch.cuda.current_stream().cuda_stream), "profile")
+if trace_op >= 0:
+    lib.mvlm_debug_hourglass_describe(net._h, trace_op, C.create_string_buffer(256), 256)
+    print(f"timeline of CTA 0, op {trace_op} (cycles since kernel start): tile | P halo-issued, P weights-issued | "
+          "M acc-acquired, M halo-landed, M issued | E acc-ready, E released")
+    for t in range(24):
+        r = [trace[t * 16 + k] for k in range(16)]
+        print(f"  tile {t:2d} | {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[4]:8d} | {r[5]:8d} {r[6]:8d}   "
+              f"mma-span {r[4] - r[2]:6d} epi-span {r[6] - r[5]:6d} | unit0: ld {r[8] - r[5]:5d} sts {r[9] - r[8]:5d} "
+              f"out {r[10] - r[9]:5d} end {r[11] - r[10]:5d} | unit1: ld {r[12] - r[11]:5d} sts {r[13] - r[12]:5d} "
+              f"out {r[14] - r[13]:5d} end {r[15] - r[14]:5d}")
 buf = C.create_string_buffer(256)
 agg = defaultdict(lambda: [0, 0.0, [0.0] * 8])
 total = sum(ms)
