@@ -44,8 +44,7 @@ constexpr int kTileW = 8;                               // output tile: 8 px wid
 constexpr int kMaxTileH = 32;                           // ... and up to 32 rows high (N = 256)
 constexpr int kMTile = 128;                             // output channels per CTA tile (UMMA M)
 constexpr int kMaxHSlots = 4;                           // halo (activation) ring, depth chosen per layer
-constexpr int kMaxWSlots = 8;                           // weight ring
-constexpr int kWSlotBytes = kMTile * 128;               // 128 cout rows x 64 cin = 16 KB
+constexpr int kMaxWSlots = 12;                          // weight ring (16 KB slots at M = 128, 8 KB at M = 64)
 constexpr int kPoolBytes = 200 * 1024;                  // both rings
 constexpr int kStageFloats = 16 * 36;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad)
 constexpr int kMaxCout = 256;
@@ -60,7 +59,7 @@ struct __align__(8) Barriers {
   uint64_t t_empty[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(Barriers) <= 256, "barrier block");
+static_assert(sizeof(Barriers) <= 512, "barrier block");
 
 // Per-output-channel epilogue parameters staged once per CTA in shared memory.
 struct EpiParams {
@@ -73,7 +72,7 @@ struct EpiParams {
   float post_t[kMaxCout];
 };
 
-constexpr int kSmemBytes = kPoolBytes + kEpiWarps * kStageFloats * 4 + 256 + static_cast<int>(sizeof(EpiParams)) +
+constexpr int kSmemBytes = kPoolBytes + kEpiWarps * kStageFloats * 4 + 512 + static_cast<int>(sizeof(EpiParams)) +
                            1024 /*align*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -159,7 +158,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 // which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
 enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
               F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */,
-              F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */ };
+              F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */,
+              F_M64 = 1024 /* cout <= 64: UMMA M = 64, 16 channels per TMEM lane group */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 template <int F>
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   uint8_t* w_slots = smem + p.n_hslots * p.h_slot_bytes;
   float* stage_all = reinterpret_cast<float*>(smem + kPoolBytes);
   Barriers* bar = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(stage_all) + kEpiWarps * kStageFloats * 4);
-  EpiParams* ep = reinterpret_cast<EpiParams*>(reinterpret_cast<uint8_t*>(bar) + 256);
+  EpiParams* ep = reinterpret_cast<EpiParams*>(reinterpret_cast<uint8_t*>(bar) + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,10 +184,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const int n_hslots = p.n_hslots, n_wslots = p.n_wslots;
   const int halo_px = kTileW + s.kw - 1;            // pixels per halo row
   const int halo_rows = p.tile_h + s.kh - 1;
-  const int w_rows = s.cout_pad < kMTile ? s.cout_pad : kMTile;  // weight rows actually loaded per tile
-  // cout <= 64: the weight rows are replicated `rep` times along M, so that all four TMEM lane groups (and
+  // cout <= 64 runs with UMMA M = 64 (same cycles per instruction as M = 128, measured in tools/exp_m64.cu, but
+  // half the weight bytes through shared memory, which is the binding resource): output row i sits in TMEM lane
+  // 32 * (i / 16) + i % 16, i.e. every lane group (every epilogue warp) holds 16 channels in its lanes 0..15.
+  constexpr bool M64 = (F & F_M64) != 0;
+  constexpr int kM = M64 ? 64 : kMTile;
+  const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
+  // cout < M: the weight rows are replicated `rep` times along M, so that all four TMEM lane groups (and
   // therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows instead.
-  const int rep = s.cout_pad <= 32 ? 4 : (s.cout_pad <= 64 ? 2 : 1);
+  const int rep = kM / w_rows;
+  const uint32_t w_slot_bytes = static_cast<uint32_t>(kM) * 128u;
+  // stationary weights: all (chunk, tap) tiles of the layer fit in the ring -> loaded once per CTA, never released
+  const bool w_stat = p.w_stationary != 0;
 
   // Tile schedule shared by the three roles.  Default: round-robin (neighbouring CTAs work on neighbouring
   // tiles -> halo / weight reuse in L2).  ARGMAX: contiguous ranges, so that a CTA stays within one image
@@ -293,16 +301,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per weight row
           const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
           for (int tap = 0; tap < s.kw * s.kh; ++tap) {  // tap = kx * KH + ky
-            timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
+            if (!w_stat) timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
             ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
             for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
-              ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * (kMTile / rep) * row_b,
-                               tap * s.cin + c * 64, mt * kMTile);
+              ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * w_slot_bytes + q * w_rows * row_b,
+                               tap * s.cin + c * 64, mt * kM);
             if (++sw == n_wslots) { sw = 0; pw ^= 1; }
           }
         }
         MVLM_TRACE(1);
         ++trace_i;
+        if (w_stat) break;  // one pass over the layer's weights is all there is
       }
       if (prof) p.prof[blockIdx.x * 8 + 1] = w1;
     }
@@ -311,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // elect.sync (not `lane == 0`): the compiler then knows a single lane is active and emits the
     // UTCHMMA / UTCBAR uniform-datapath instructions without a per-lane serialisation loop.
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(kMTile, p.tile_h * kTileW);
+      const uint32_t idesc = ptx::umma_idesc_bf16(kM, p.tile_h * kTileW);
       // descriptor = {lo: start>>4 | LBO, hi: SBO | version | swizzle}; only lo changes per MMA.
       //   A (weights): 8-row groups 8 rows apart.  B (halo tile): 8-row group = the 8 pixels of one image row,
       //   groups one halo row (halo_px pixels) apart.
@@ -339,9 +348,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * p.h_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
           for (int kx = 0; kx < s.kw; ++kx) {
             for (int ky = 0; ky < s.kh; ++ky) {
-              if (p.debug_mode == 0) timed_wait(&bar->w_full[sw], pw, prof, w0);
+              if (p.debug_mode == 0) timed_wait(&bar->w_full[sw], w_stat ? 0u : pw, prof, w0);
               ptx::tc_fence_after();
-              const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * kWSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
+              const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * w_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
               // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
               const uint32_t x_lo = h_lo + ((static_cast<uint32_t>(ky * halo_px + kx) * row_b) >> 4);
               if (nk == 4) {
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
               }
               accumulate = 1;
-              if (p.debug_mode == 0) ptx::umma_commit(&bar->w_empty[sw]);
+              if (p.debug_mode == 0 && !w_stat) ptx::umma_commit(&bar->w_empty[sw]);
               if (++sw == n_wslots) { sw = 0; pw ^= 1; }
             }
           }
@@ -370,9 +379,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   } else {
     // ===================== epilogue =====================
     // Accumulator column n = 8 * (row in tile) + (pixel in row).  One "unit" = 16 columns = 2 image rows x 8 px.
+    constexpr int kChGrp = M64 ? 16 : 32;  // channels per TMEM lane group (M = 64: in lanes 0..15 of the group)
+    constexpr int kPitch = M64 ? 20 : 36;  // floats per pixel row of the transpose buffer
+    constexpr int kPasses = M64 ? 1 : 2;   // pixel-major passes per unit
     const int ew = warp - 2;
     const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
-    const int n_cgrp = 4 / rep;      // distinct 32-channel groups along M
+    const int n_cgrp = 4 / rep;      // distinct channel groups along M
     const int cgrp = lane_grp % n_cgrp;
     const int replica = lane_grp / n_cgrp;
     const int n_units = p.tile_h >> 1;
@@ -385,72 +397,83 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     uint32_t best_hi = 0u, best_lo = 0u;
     int cur_img = -1;
     const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
-    // pixel-major role after the transpose: lane -> (pixel column pj = lane/4, row parity i, channels (lane%4)*8 .. +7)
-    const int pj = lane >> 2;
-    const int cq = (lane & 3) * 8;
+    // channel-major role (TMEM load, bias, transpose store): lane = channel; M = 64 -> lanes 0..15 only.
+    // pixel-major role after the transpose:
+    //   M = 128: lane -> (pixel column pj = lane/4, channels (lane%4)*8 .. +7), rows i = 0, 1 in two passes
+    //   M = 64 : lane -> (pixel column pj = (lane/2)%8, row my_i = lane/16, channels (lane%2)*8 .. +7), one pass
+    const bool cm_lane = !M64 || lane < 16;
+    const int pj = M64 ? ((lane >> 1) & 7) : (lane >> 2);
+    const int my_i = M64 ? (lane >> 4) : 0;
+    const int cq = M64 ? (lane & 1) * 8 : (lane & 3) * 8;
     constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
-    // byte strides of one image row in every tensor the epilogue touches: an access of unit r, row i is then
-    // (per-tile base pointer) + (2r + i) * stride with a compile-time (2r + i)
+    // byte strides of one image row in every tensor the epilogue touches: an access of unit r, pass ip is then
+    // (per-tile base pointer) + (2r + ip) * stride with a compile-time (2r + ip)
     const uint32_t rs_pre = static_cast<uint32_t>(s.w * e.pre_cs) * 2u, rs_res1 = static_cast<uint32_t>(s.w * e.res1_cs) * 2u;
     const uint32_t rs_res2 = static_cast<uint32_t>(s.w * e.res2_cs) * 2u;
     const uint32_t rs_up = static_cast<uint32_t>((s.w >> 1) * e.up_cs) * 2u;
     // F_POOL: raw / post live at half resolution, one pooled row per unit
     const uint32_t rs_raw = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.raw_cs) * 2u;
     const uint32_t rs_post = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.post_cs) * 2u;
+    // Residual inputs do not depend on the accumulator: they are fetched in BATCHES before they are needed -- all
+    // units of a tile while its MMAs still run when they fit in ~64 registers, else units 0..3 then and units 4..7
+    // once the first four are consumed.  (Loads issued one by one while earlier ones are being consumed do not work:
+    // the few hardware scoreboards are shared, so every use then waits for the newest load; measured.)
+    constexpr bool kHasRes = (F & (F_RES1 | F_RES2 | F_UP)) != 0;
+    constexpr int kResRegs = 4 * (kPasses * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + ((F & F_UP) ? 1 : 0));
+    constexpr int kPref = !kHasRes ? 1 : (kResRegs <= 8 ? 8 : 4);  // units per batch
+    uint4 r1[kPref][kPasses], r2[(F & F_RES2) ? kPref : 1][kPasses], ru[(F & F_UP) ? kPref : 1];
     for (int t = t_begin; t < t_end; t += t_step) {
       const TileCoord tc = decode_tile(p, t);
-      const int m0 = tc.mt * kMTile;
-      const int c_lane = m0 + cgrp * 32 + lane;           // channel-major role: my output channel
-      const int c0 = m0 + cgrp * 32 + cq;                 // pixel-major role: first of my 8 channels
-      const bool grp_active = m0 + cgrp * 32 < s.cout_pad;
+      const int m0 = tc.mt * kM;
+      const int c_lane = m0 + cgrp * kChGrp + lane;       // channel-major role: my output channel
+      const int c0 = m0 + cgrp * kChGrp + cq;             // pixel-major role: first of my 8 channels
+      const bool grp_active = m0 + cgrp * kChGrp < s.cout_pad;
       const int y_first = tc.ty * p.tile_h + 2 * u_begin;  // first image row handled by this warp
       const bool rows_active = u_begin < n_units && y_first < s.h;
       const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
       const int xa = tc.tx * kTileW + pj;
       const bool vx = ch_ok && xa < s.w;
-      // element index of pixel (img, y_first, xa); 32-bit: pixel count x channel stride < 2^31 (checked in conv_plan)
-      const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first) * s.w + xa;
-      // F_POOL: element index of the pooled pixel of (img, y_first, xa) in the half-resolution outputs
+      // element index of my pixel in the first unit: (img, y_first + my_i, xa); 32-bit: pixel count x channel
+      // stride < 2^31 (checked in conv_plan)
+      const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first + my_i) * s.w + xa;
+      // element index of the half-resolution pixel (img, y_first/2, xa/2): F_POOL outputs, F_UP input
       const uint32_t ppix0 = (static_cast<uint32_t>(tc.img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
       if ((F & F_ARGMAX) && tc.img != cur_img) {
-        if (cur_img >= 0 && best_hi != 0u && c_lane < e.cout_real)
+        if (cur_img >= 0 && best_hi != 0u && cm_lane && c_lane < e.cout_real)
           atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
                     (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
         best_hi = 0u; best_lo = 0u;
         cur_img = tc.img;
       }
-      // residual rows do not depend on the accumulator: the first kPref units are fetched while the MMAs of this
-      // tile still run, unit r + kPref is fetched as soon as unit r has been consumed (rolling window)
-      constexpr int kPref = (F & (F_RES2 | F_UP)) ? 4 : 8;
-      uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1];
-      // per-tile base pointers of my (pixel column, 8 channels) at the first row of my first unit
+      // per-tile base pointers of my (pixel, 8 channels) in the first unit
       const uint32_t opix0 = (F & F_POOL) ? ppix0 : pix0;
       uint8_t* const b_pre = (F & F_PRE) ? reinterpret_cast<uint8_t*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(pix0) * e.pre_cs) : nullptr;
       uint8_t* const b_raw = (F & F_RAW) ? reinterpret_cast<uint8_t*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(opix0) * e.raw_cs) : nullptr;
       uint8_t* const b_post = (F & F_POST) ? reinterpret_cast<uint8_t*>(e.out_post + e.post_co + c0 + static_cast<size_t>(opix0) * e.post_cs) : nullptr;
+      // rows at / below my first pixel that exist in the image (0 when my pixel column / channels do not):
+      // unit r, pass ip is valid iff 2r + ip < n_rows_ok
+      const int n_rows_ok = vx ? s.h - y_first - my_i : 0;
       const uint8_t* const b_res1 = (F & F_RES1) ? reinterpret_cast<const uint8_t*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix0) * e.res1_cs) : nullptr;
       const uint8_t* const b_res2 = (F & F_RES2) ? reinterpret_cast<const uint8_t*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix0) * e.res2_cs) : nullptr;
       const uint8_t* const b_up = (F & F_UP) ? reinterpret_cast<const uint8_t*>(e.res_up + e.up_co + c0 + static_cast<size_t>(ppix0) * e.up_cs) : nullptr;
-      // rows of this warp's part of the tile that exist in the image (0 when my pixel column / channels do not)
-      const int n_rows_ok = vx ? s.h - y_first : 0;
-      auto prefetch_unit = [&](int u) {  // u: compile-time after unrolling
-        if (u < upw) {
-          const int q = u % kPref;
+      auto prefetch_batch = [&](int u0) {  // units u0 .. u0 + kPref - 1 (u0 compile-time after unrolling)
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (2 * u + i < n_rows_ok) {
-              if (F & F_RES1) r1[q][i] = *reinterpret_cast<const uint4*>(b_res1 + static_cast<size_t>((2 * u + i) * rs_res1));
-              if (F & F_RES2) r2[q][i] = *reinterpret_cast<const uint4*>(b_res2 + static_cast<size_t>((2 * u + i) * rs_res2));
+        for (int q = 0; q < kPref; ++q) {
+          const int u = u0 + q;
+          if (u < upw) {
+#pragma unroll
+            for (int ip = 0; ip < kPasses; ++ip) {
+              if (2 * u + ip < n_rows_ok) {
+                if (F & F_RES1) r1[q][ip] = *reinterpret_cast<const uint4*>(b_res1 + static_cast<size_t>((2 * u + ip) * rs_res1));
+                if (F & F_RES2) r2[q][ip] = *reinterpret_cast<const uint4*>(b_res2 + static_cast<size_t>((2 * u + ip) * rs_res2));
+              }
             }
+            // nearest x2: rows y, y+1 and columns xa, xa^1 all read low-res pixel (y/2, xa/2)
+            if ((F & F_UP) && 2 * u < n_rows_ok) ru[q] = *reinterpret_cast<const uint4*>(b_up + static_cast<size_t>(u * rs_up));
           }
-          // nearest x2: rows y, y+1 and columns xa, xa^1 all read low-res pixel (y/2, xa/2)
-          if ((F & F_UP) && 2 * u < n_rows_ok) ru[q] = *reinterpret_cast<const uint4*>(b_up + static_cast<size_t>(u * rs_up));
         }
       };
-      if ((F & (F_RES1 | F_RES2 | F_UP)) && grp_active && rows_active) {
-#pragma unroll
-        for (int q = 0; q < kPref; ++q) prefetch_unit(q);
-      }
+      if (kHasRes && grp_active && rows_active) prefetch_batch(0);
       // per-channel parameters of my 8 channels (pixel-major role) and my channel (channel-major role)
       float pre_s[8], pre_t[8], post_s[8], post_t[8];
       if (F & F_PRE) { lds8(ep->pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep->pre_t + (ch_ok ? c0 : 0), pre_t); }
@@ -460,14 +483,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       timed_wait(&bar->t_full[acc], pacc, prof, w0);
       ptx::tc_fence_after();
       if (warp == 2 && lane == 0) MVLM_TRACE(5);
-      if (grp_active && rows_active) {
+      {
+        const bool active = grp_active && rows_active;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                                static_cast<uint32_t>(acc * 256 + u_begin * 16);
         uint32_t v[2][16];
-        ptx::tmem_ld16(taddr, v[0]);
+        if (active) ptx::tmem_ld16(taddr, v[0]);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           if (r < upw) {
+           if (active) {
+            if (kHasRes && kPref < 8 && r == kPref) prefetch_batch(kPref);  // second batch: units 4..7
             const int y = y_first + 2 * r;  // image rows y (columns 0..7 of the unit) and y+1 (columns 8..15)
             ptx::tmem_ld_wait();
             if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(8 + 4 * r);
@@ -478,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 // channel-major consumers: lane = channel c_lane, vr[j] = pixel (y + j/8, x0 + j%8)
                 const int x0 = tc.tx * kTileW;
                 const int nvx = s.w - x0;  // >= 8 for interior tiles
-                if (c_lane < e.cout_real) {
+                if (cm_lane && c_lane < e.cout_real) {
 #pragma unroll
                   for (int i = 0; i < 2; ++i) {
                     if (y + i < s.h) {
@@ -508,51 +534,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 }
               }
               if (kBf16Out) {
-                // bias in the channel-major role (one register), then transpose 16 px x 32 ch through shared
-                // memory: row = pixel, 36-float pitch (conflict-free for the STS.32 and the LDS.128)
+                // bias in the channel-major role (one register), then transpose 16 px x 32 (16) ch through shared
+                // memory: row = pixel, 36 (20)-float pitch (conflict-free STS.32; LDS.128 conflict-free at 36)
                 __syncwarp();
+                if (cm_lane) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  float f = __uint_as_float(vr[j]) + bias_c;
-                  if (F & F_MID) f = fmaxf(fmaf(f, mid_s_c, mid_t_c), 0.f);
-                  stage[j * 36 + lane] = f;
+                  for (int j = 0; j < 16; ++j) {
+                    float f = __uint_as_float(vr[j]) + bias_c;
+                    if (F & F_MID) f = fmaxf(fmaf(f, mid_s_c, mid_t_c), 0.f);
+                    stage[j * kPitch + lane] = f;
+                  }
                 }
                 __syncwarp();
                 if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(9 + 4 * r);
-                uint4 pool_cur[2];
+                uint4 pool_cur[kPasses];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const bool valid = 2 * r + i < n_rows_ok;
+                for (int ip = 0; ip < kPasses; ++ip) {
+                  const int i = M64 ? my_i : ip;  // my image row within the unit
+                  const bool valid = 2 * r + ip < n_rows_ok;
                   float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                   if (valid) {
-                    lds8(stage + (pj + 8 * i) * 36 + cq, f);
+                    lds8(stage + (pj + 8 * i) * kPitch + cq, f);
                     if (F & F_PRE)
-                      *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>((2 * r + i) * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
-                    if (F & F_RES1) add8(r1[r % kPref][i], f);
-                    if (F & F_RES2) add8(r2[r % kPref][i], f);
+                      *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>((2 * r + ip) * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
+                    if (F & F_RES1) add8(r1[r % kPref][ip], f);
+                    if (F & F_RES2) add8(r2[r % kPref][ip], f);
                     if (F & F_UP) add8(ru[r % kPref], f);
                   }
                   if (F & F_POOL) {
-                    pool_cur[i] = pack8(f);
+                    pool_cur[ip] = pack8(f);
                   } else if (valid) {
-                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>((2 * r + i) * rs_raw)) = pack8(f);
+                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>((2 * r + ip) * rs_raw)) = pack8(f);
                     if (F & F_POST)
-                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>((2 * r + i) * rs_post)) = affine_relu_pack8(f, post_s, post_t);
+                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>((2 * r + ip) * rs_post)) = affine_relu_pack8(f, post_s, post_t);
                   }
                 }
                 if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(10 + 4 * r);
-                if ((F & (F_RES1 | F_RES2 | F_UP)) && r + kPref < 8) prefetch_unit(r + kPref);
                 if (F & F_POOL) {
-                  // 2x2 max-pool of the bf16-rounded values: vertical partner = the unit's other row (same lane),
-                  // horizontal partner = lane ^ 4 (pixel column pj ^ 1); shuffles run on all lanes
-                  uint4 m = max_bf16x8(pool_cur[0], pool_cur[1]);
+                  // 2x2 max-pool of the bf16-rounded values.  Vertical partner: the unit's other row = my second pass
+                  // (M = 128) or lane ^ 16 (M = 64); horizontal partner (pixel column pj ^ 1): lane ^ 4 (M = 128) or
+                  // lane ^ 2 (M = 64).  Shuffles run on all lanes.
+                  uint4 m = pool_cur[0];
+                  if (M64) {
+                    uint4 o;
+                    o.x = __shfl_xor_sync(0xffffffffu, m.x, 16);
+                    o.y = __shfl_xor_sync(0xffffffffu, m.y, 16);
+                    o.z = __shfl_xor_sync(0xffffffffu, m.z, 16);
+                    o.w = __shfl_xor_sync(0xffffffffu, m.w, 16);
+                    m = max_bf16x8(m, o);
+                  } else {
+                    m = max_bf16x8(m, pool_cur[kPasses - 1]);
+                  }
                   uint4 o;
-                  o.x = __shfl_xor_sync(0xffffffffu, m.x, 4);
-                  o.y = __shfl_xor_sync(0xffffffffu, m.y, 4);
-                  o.z = __shfl_xor_sync(0xffffffffu, m.z, 4);
-                  o.w = __shfl_xor_sync(0xffffffffu, m.w, 4);
+                  o.x = __shfl_xor_sync(0xffffffffu, m.x, M64 ? 2 : 4);
+                  o.y = __shfl_xor_sync(0xffffffffu, m.y, M64 ? 2 : 4);
+                  o.z = __shfl_xor_sync(0xffffffffu, m.z, M64 ? 2 : 4);
+                  o.w = __shfl_xor_sync(0xffffffffu, m.w, M64 ? 2 : 4);
                   m = max_bf16x8(m, o);
-                  if (2 * r < n_rows_ok && (pj & 1) == 0) {  // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
+                  // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
+                  if (2 * r < n_rows_ok && my_i == 0 && (pj & 1) == 0) {
                     if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(r * rs_raw)) = m;
                     if (F & F_POST) {
                       float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -564,6 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(11 + 4 * r);
               }
             }
+           }
           }
         }
       }
@@ -576,8 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
     if ((F & F_ARGMAX) && cur_img >= 0 && best_hi != 0u) {
-      const int c_lane = cgrp * 32 + lane;  // arg-max convs have a single M tile
-      if (c_lane < e.cout_real)
+      const int c_lane = cgrp * kChGrp + lane;  // arg-max convs have a single M tile
+      if (cm_lane && c_lane < e.cout_real)
         atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
                   (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
     }
@@ -670,14 +711,20 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     // ring depths: the halo slot holds the whole (8+KW-1) x (tile_h+KH-1) pixel tile of one 64-channel chunk
     const int hbytes = (kTileW + s.kw - 1) * (tile_h + s.kh - 1) * 128;
     p.h_slot_bytes = (hbytes + 1023) & ~1023;
-    int nh = s.kh * s.kw == 1 ? 3 : 2, nw = s.kh * s.kw == 1 ? 6 : 7;
+    // cout <= 64 -> UMMA M = 64, 8 KB weight slots; all (chunk, tap) tiles resident when they fit the ring
+    const int m_tile = s.cout_pad <= 64 ? 64 : kMTile;
+    const int wslot = m_tile * 128;
+    const int n_wtiles = ((s.cin + 63) / 64) * s.kh * s.kw;
+    int nh = s.kh * s.kw == 1 ? 3 : 2, nw = s.kh * s.kw == 1 ? 6 : (m_tile == 64 ? kMaxWSlots : 7);
+    p.w_stationary = (m_tile == 64 && n_wtiles <= kMaxWSlots && getenv("MVLM_CONV_NO_STATIONARY") == nullptr) ? 1 : 0;
+    if (p.w_stationary) nw = n_wtiles;
     if (const char* env = getenv("MVLM_CONV_RING")) {  // experiment knob: "halo_slots,weight_slots"
       int a = 0, b = 0;
-      if (sscanf(env, "%d,%d", &a, &b) == 2 && a >= 2 && a <= kMaxHSlots && b >= 2 && b <= kMaxWSlots) { nh = a; nw = b; }
+      if (sscanf(env, "%d,%d", &a, &b) == 2 && a >= 2 && a <= kMaxHSlots && b >= 2 && b <= kMaxWSlots && !p.w_stationary) { nh = a; nw = b; }
     }
-    while (nh * p.h_slot_bytes + nw * kWSlotBytes > kPoolBytes && nw > 2) --nw;
-    while (nh * p.h_slot_bytes + nw * kWSlotBytes > kPoolBytes && nh > 2) --nh;
-    MVLM_REQUIRE(nh * p.h_slot_bytes + nw * kWSlotBytes <= kPoolBytes, "conv_plan: operand rings do not fit");
+    while (nh * p.h_slot_bytes + nw * wslot > kPoolBytes && nw > 2 && !p.w_stationary) --nw;
+    while (nh * p.h_slot_bytes + nw * wslot > kPoolBytes && nh > 2) --nh;
+    MVLM_REQUIRE(nh * p.h_slot_bytes + nw * wslot <= kPoolBytes, "conv_plan: operand rings do not fit");
     p.n_hslots = nh;
     p.n_wslots = nw;
   }
@@ -702,7 +749,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     const cuuint64_t ktot = (cuuint64_t)s.kw * s.kh * s.cin;
     cuuint64_t gdim[2] = {ktot, (cuuint64_t)s.cout_pad};
     cuuint64_t gstr[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(s.cout_pad < kMTile ? s.cout_pad : kMTile)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(s.cout_pad < kMTile ? s.cout_pad : kMTile)};  // cout_pad <= 64: M = 64 tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(s.wpacked), gdim,
                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -737,7 +784,7 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   }
   p.tiles_x = ceil_div(s.w, kTileW);
   p.tiles_y = ceil_div(s.h, tile_h);
-  p.n_nt = ceil_div(s.cout_pad, kMTile);
+  p.n_nt = s.cout_pad <= 64 ? 1 : ceil_div(s.cout_pad, kMTile);
   p.total_tiles = s.n * p.tiles_x * p.tiles_y * p.n_nt;
   p.prof = nullptr;
   p.debug_mode = 0;
@@ -756,33 +803,40 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
                 (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0) |
                 (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0) | (e.res_up ? F_UP : 0);
+  // cout <= 64 layers run the M = 64 variant (conv_plan chose the ring geometry accordingly)
+  const bool m64 = p.s.cout_pad <= 64;
+#define MVLM_CASE_BOTH(FLAGS) \
+  case (FLAGS): return m64 ? launch_t<(FLAGS) | F_M64>(p, stream) : launch_t<(FLAGS)>(p, stream)
+#define MVLM_CASE_128(FLAGS) \
+  case (FLAGS):              \
+    if (!m64) return launch_t<(FLAGS)>(p, stream); \
+    break
   switch (f) {
     // the combinations the network plan uses (hourglass.cu)
-    case F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);  // RB conv1/2
-    case F_PRE | F_RES1 | F_RAW: return launch_t<F_PRE | F_RES1 | F_RAW>(p, stream);
-    case F_RES1 | F_RAW | F_POST: return launch_t<F_RES1 | F_RAW | F_POST>(p, stream);                  // RB conv3
-    case F_RES1 | F_RAW: return launch_t<F_RES1 | F_RAW>(p, stream);
-    case F_RAW: return launch_t<F_RAW>(p, stream);                                                      // resample, conv6/10
-    case F_PRE: return launch_t<F_PRE>(p, stream);                                                      // conv5, conv9
-    case F_RES1 | F_RES2 | F_RAW | F_POST: return launch_t<F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);  // conv7
-    case F_ARGMAX: return launch_t<F_ARGMAX>(p, stream);                                                // conv11 phases
-    case F_F32: return launch_t<F_F32>(p, stream);
-    case F_F32 | F_ARGMAX: return launch_t<F_F32 | F_ARGMAX>(p, stream);
-    case F_MID | F_PRE | F_POST: return launch_t<F_MID | F_PRE | F_POST>(p, stream);                    // stem (conv1)
-    case F_POOL | F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_POOL | F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);
-    case F_POOL | F_RES1 | F_RAW | F_POST: return launch_t<F_POOL | F_RES1 | F_RAW | F_POST>(p, stream);
-    case F_POOL | F_RAW: return launch_t<F_POOL | F_RAW>(p, stream);
-    case F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
-      return launch_t<F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
+    MVLM_CASE_BOTH(F_PRE | F_RES1 | F_RAW | F_POST);  // RB conv1/2
+    MVLM_CASE_BOTH(F_PRE | F_RES1 | F_RAW);
+    MVLM_CASE_BOTH(F_RES1 | F_RAW | F_POST);          // RB conv3
+    MVLM_CASE_BOTH(F_RES1 | F_RAW);
+    MVLM_CASE_BOTH(F_RAW);                            // resample, conv6/10
+    MVLM_CASE_128(F_PRE);                             // conv5, conv9
+    MVLM_CASE_128(F_RES1 | F_RES2 | F_RAW | F_POST);  // conv7
+    MVLM_CASE_128(F_ARGMAX);                          // conv11 phases
+    MVLM_CASE_BOTH(F_F32);
+    MVLM_CASE_BOTH(F_F32 | F_ARGMAX);
+    MVLM_CASE_BOTH(F_MID | F_PRE | F_POST);           // stem (conv1)
+    MVLM_CASE_BOTH(F_POOL | F_PRE | F_RES1 | F_RAW | F_POST);  // conv2 block: pooled outputs only
+    MVLM_CASE_BOTH(F_POOL | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_BOTH(F_POOL | F_RAW);
+    MVLM_CASE_128(F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST);
     // skip-branch ResidualBlocks with the up-sampled low path added in the epilogue (hourglass up path)
-    case F_UP | F_PRE | F_RES1 | F_RAW | F_POST: return launch_t<F_UP | F_PRE | F_RES1 | F_RAW | F_POST>(p, stream);
-    case F_UP | F_PRE | F_RES1 | F_RAW: return launch_t<F_UP | F_PRE | F_RES1 | F_RAW>(p, stream);
-    case F_UP | F_RES1 | F_RAW | F_POST: return launch_t<F_UP | F_RES1 | F_RAW | F_POST>(p, stream);
-    case F_UP | F_RES1 | F_RAW: return launch_t<F_UP | F_RES1 | F_RAW>(p, stream);
-    case F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST:
-      return launch_t<F_MID | F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST>(p, stream);
+    MVLM_CASE_BOTH(F_UP | F_PRE | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_BOTH(F_UP | F_PRE | F_RES1 | F_RAW);
+    MVLM_CASE_BOTH(F_UP | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_BOTH(F_UP | F_RES1 | F_RAW);
   }
-  set_error("conv_launch: unsupported epilogue combination 0x%x", f);
+#undef MVLM_CASE_BOTH
+#undef MVLM_CASE_128
+  set_error("conv_launch: unsupported epilogue combination 0x%x (cout_pad %d)", f, p.s.cout_pad);
   return MVLM_E_UNSUPPORTED;
 }
 

@@ -78,6 +78,7 @@ struct alignas(64) ConvParams {
   int tiles_x, tiles_y, n_nt, total_tiles;
   int tile_h;                             // rows of the 8-px-wide output tile: 32 (N = 256), 16, 8 or 4 for low maps
   int h_slot_bytes, n_hslots, n_wslots;   // operand ring geometry (conv_plan)
+  int w_stationary;                       // 1: n_wslots = all weight tiles of the layer, loaded once per CTA
   // optional per-CTA cycle counters (8 x int64 per CTA), see conv_umma.cu "role timing"
   long long* prof;
   int debug_mode;  // 0 normal; 1 = MMA-only experiment (no TMA loads, operand waits skipped; results garbage)
