@@ -45,8 +45,8 @@ constexpr int kMaxTileH = 32;                           // ... and up to 32 rows
 constexpr int kMTile = 128;                             // output channels per CTA tile (UMMA M)
 constexpr int kMaxHSlots = 4;                           // halo (activation) ring, depth chosen per layer
 constexpr int kMaxWSlots = 12;                          // weight ring (16 KB slots at M = 128, 8 KB at M = 64)
-constexpr int kPoolBytes = 200 * 1024;                  // both rings
-constexpr int kStageFloats = 16 * 36;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad)
+constexpr int kPoolBytes = 198 * 1024;                  // both rings
+constexpr int kStageFloats = 32 * 20;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad) | 32 px x (16 + 4)
 constexpr int kMaxCout = 256;
 constexpr int kTraceTiles = 64;                        // debug timeline: tiles traced on CTA 0
 
@@ -378,16 +378,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
   } else {
     // ===================== epilogue =====================
-    // Accumulator column n = 8 * (row in tile) + (pixel in row).  One "unit" = 16 columns = 2 image rows x 8 px.
-    constexpr int kChGrp = M64 ? 16 : 32;  // channels per TMEM lane group (M = 64: in lanes 0..15 of the group)
-    constexpr int kPitch = M64 ? 20 : 36;  // floats per pixel row of the transpose buffer
-    constexpr int kPasses = M64 ? 1 : 2;   // pixel-major passes per unit
+    // Accumulator column n = 8 * (row in tile) + (pixel in row).  One "unit" (one TMEM load, one transpose) =
+    //   M = 128: 16 columns = 2 image rows x 8 px of the warp's 32 channels,
+    //   M = 64 : 32 columns = 4 image rows x 8 px of the warp's 16 channels (lanes 0..15 of the lane group),
+    // i.e. 512 values either way.  The epilogue is latency-bound (two warps per scheduler, dependent
+    // TMEM -> shared -> registers -> global chain per unit), so fewer, fatter units matter.
+    constexpr int kChGrp = M64 ? 16 : 32;      // channels per TMEM lane group
+    constexpr int kPitch = M64 ? 20 : 36;      // floats per pixel row of the transpose buffer
+    constexpr int kCols = M64 ? 32 : 16;       // accumulator columns per unit
+    constexpr int kUnitRows = kCols / 8;       // image rows per unit
+    constexpr int kPassStep = M64 ? 2 : 1;     // image rows between my pixel in pass 0 and in pass 1
+    static_assert(kCols * kPitch <= kStageFloats, "transpose buffer");
     const int ew = warp - 2;
     const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
     const int n_cgrp = 4 / rep;      // distinct channel groups along M
     const int cgrp = lane_grp % n_cgrp;
     const int replica = lane_grp / n_cgrp;
-    const int n_units = p.tile_h >> 1;
+    const int n_units = max(1, p.tile_h / kUnitRows);
     const int upw = max(1, n_units / (2 * rep));              // units per warp
     const int u_begin = ((ew >> 2) * rep + replica) * upw;    // first unit handled by this warp
     float* stage = stage_all + ew * kStageFloats;
@@ -398,43 +405,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     int cur_img = -1;
     const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
     // channel-major role (TMEM load, bias, transpose store): lane = channel; M = 64 -> lanes 0..15 only.
-    // pixel-major role after the transpose:
-    //   M = 128: lane -> (pixel column pj = lane/4, channels (lane%4)*8 .. +7), rows i = 0, 1 in two passes
-    //   M = 64 : lane -> (pixel column pj = (lane/2)%8, row my_i = lane/16, channels (lane%2)*8 .. +7), one pass
+    // pixel-major role after the transpose, two passes per unit:
+    //   M = 128: lane -> (pixel column pj = lane/4, channels (lane%4)*8 .. +7), unit row ip in pass ip
+    //   M = 64 : lane -> (pixel column pj = (lane/2)%8, channels (lane%2)*8 .. +7), unit row lane/16 + 2*ip in pass ip
     const bool cm_lane = !M64 || lane < 16;
     const int pj = M64 ? ((lane >> 1) & 7) : (lane >> 2);
     const int my_i = M64 ? (lane >> 4) : 0;
     const int cq = M64 ? (lane & 1) * 8 : (lane & 3) * 8;
     constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
     // byte strides of one image row in every tensor the epilogue touches: an access of unit r, pass ip is then
-    // (per-tile base pointer) + (2r + ip) * stride with a compile-time (2r + ip)
+    // (per-tile base pointer) + (kUnitRows * r + kPassStep * ip) * stride with a compile-time row offset
     const uint32_t rs_pre = static_cast<uint32_t>(s.w * e.pre_cs) * 2u, rs_res1 = static_cast<uint32_t>(s.w * e.res1_cs) * 2u;
     const uint32_t rs_res2 = static_cast<uint32_t>(s.w * e.res2_cs) * 2u;
     const uint32_t rs_up = static_cast<uint32_t>((s.w >> 1) * e.up_cs) * 2u;
-    // F_POOL: raw / post live at half resolution, one pooled row per unit
+    // F_POOL: raw / post live at half resolution
     const uint32_t rs_raw = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.raw_cs) * 2u;
     const uint32_t rs_post = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.post_cs) * 2u;
     // Residual inputs do not depend on the accumulator: they are fetched in BATCHES before they are needed -- all
-    // units of a tile while its MMAs still run when they fit in ~64 registers, else units 0..3 then and units 4..7
-    // once the first four are consumed.  (Loads issued one by one while earlier ones are being consumed do not work:
+    // units of a tile while its MMAs still run when they fit in ~64 registers, else half of them then and the other
+    // half once the first are consumed.  (Loads issued one by one while earlier ones are being consumed do not work:
     // the few hardware scoreboards are shared, so every use then waits for the newest load; measured.)
     constexpr bool kHasRes = (F & (F_RES1 | F_RES2 | F_UP)) != 0;
-    constexpr int kResRegs = 4 * (kPasses * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + ((F & F_UP) ? 1 : 0));
-    constexpr int kPref = !kHasRes ? 1 : (kResRegs <= 8 ? 8 : 4);  // units per batch
-    uint4 r1[kPref][kPasses], r2[(F & F_RES2) ? kPref : 1][kPasses], ru[(F & F_UP) ? kPref : 1];
+    constexpr int kMaxUpw = M64 ? 4 : 8;  // units per warp at N = 256
+    constexpr int kResRegs = 4 * (2 * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + (M64 ? 2 : 1) * ((F & F_UP) ? 1 : 0));
+    constexpr int kPref = !kHasRes ? 1 : (kResRegs * kMaxUpw <= 64 ? kMaxUpw : kMaxUpw / 2);  // units per batch
+    uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1][M64 ? 2 : 1];
     for (int t = t_begin; t < t_end; t += t_step) {
       const TileCoord tc = decode_tile(p, t);
       const int m0 = tc.mt * kM;
       const int c_lane = m0 + cgrp * kChGrp + lane;       // channel-major role: my output channel
       const int c0 = m0 + cgrp * kChGrp + cq;             // pixel-major role: first of my 8 channels
       const bool grp_active = m0 + cgrp * kChGrp < s.cout_pad;
-      const int y_first = tc.ty * p.tile_h + 2 * u_begin;  // first image row handled by this warp
+      const int y_first = tc.ty * p.tile_h + kUnitRows * u_begin;  // first image row handled by this warp
       const bool rows_active = u_begin < n_units && y_first < s.h;
       const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
       const int xa = tc.tx * kTileW + pj;
       const bool vx = ch_ok && xa < s.w;
-      // element index of my pixel in the first unit: (img, y_first + my_i, xa); 32-bit: pixel count x channel
-      // stride < 2^31 (checked in conv_plan)
+      // element index of my pixel in pass 0 of the first unit: (img, y_first + my_i, xa); 32-bit: pixel count x
+      // channel stride < 2^31 (checked in conv_plan)
       const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first + my_i) * s.w + xa;
       // element index of the half-resolution pixel (img, y_first/2, xa/2): F_POOL outputs, F_UP input
       const uint32_t ppix0 = (static_cast<uint32_t>(tc.img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       uint8_t* const b_raw = (F & F_RAW) ? reinterpret_cast<uint8_t*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(opix0) * e.raw_cs) : nullptr;
       uint8_t* const b_post = (F & F_POST) ? reinterpret_cast<uint8_t*>(e.out_post + e.post_co + c0 + static_cast<size_t>(opix0) * e.post_cs) : nullptr;
       // rows at / below my first pixel that exist in the image (0 when my pixel column / channels do not):
-      // unit r, pass ip is valid iff 2r + ip < n_rows_ok
+      // unit r, pass ip is valid iff kUnitRows * r + kPassStep * ip < n_rows_ok
       const int n_rows_ok = vx ? s.h - y_first - my_i : 0;
       const uint8_t* const b_res1 = (F & F_RES1) ? reinterpret_cast<const uint8_t*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix0) * e.res1_cs) : nullptr;
       const uint8_t* const b_res2 = (F & F_RES2) ? reinterpret_cast<const uint8_t*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix0) * e.res2_cs) : nullptr;
@@ -462,14 +470,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const int u = u0 + q;
           if (u < upw) {
 #pragma unroll
-            for (int ip = 0; ip < kPasses; ++ip) {
-              if (2 * u + ip < n_rows_ok) {
-                if (F & F_RES1) r1[q][ip] = *reinterpret_cast<const uint4*>(b_res1 + static_cast<size_t>((2 * u + ip) * rs_res1));
-                if (F & F_RES2) r2[q][ip] = *reinterpret_cast<const uint4*>(b_res2 + static_cast<size_t>((2 * u + ip) * rs_res2));
+            for (int ip = 0; ip < 2; ++ip) {
+              const int row = kUnitRows * u + kPassStep * ip;
+              if (row < n_rows_ok) {
+                if (F & F_RES1) r1[q][ip] = *reinterpret_cast<const uint4*>(b_res1 + static_cast<size_t>(row * rs_res1));
+                if (F & F_RES2) r2[q][ip] = *reinterpret_cast<const uint4*>(b_res2 + static_cast<size_t>(row * rs_res2));
+                // nearest x2: rows 2k, 2k+1 and columns xa, xa^1 all read low-res pixel (k, xa/2);
+                // M = 128: both passes share one low-res row per unit, M = 64: pass ip reads low-res row 2u + ip
+                if ((F & F_UP) && (M64 || ip == 0))
+                  ru[q][M64 ? ip : 0] = *reinterpret_cast<const uint4*>(b_up + static_cast<size_t>((row >> 1) * rs_up));
               }
             }
-            // nearest x2: rows y, y+1 and columns xa, xa^1 all read low-res pixel (y/2, xa/2)
-            if ((F & F_UP) && 2 * u < n_rows_ok) ru[q] = *reinterpret_cast<const uint4*>(b_up + static_cast<size_t>(u * rs_up));
           }
         }
       };
@@ -483,22 +494,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       timed_wait(&bar->t_full[acc], pacc, prof, w0);
       ptx::tc_fence_after();
       if (warp == 2 && lane == 0) MVLM_TRACE(5);
-      {
-        const bool active = grp_active && rows_active;
+      if (grp_active && rows_active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                               static_cast<uint32_t>(acc * 256 + u_begin * 16);
-        uint32_t v[2][16];
-        if (active) ptx::tmem_ld16(taddr, v[0]);
+                               static_cast<uint32_t>(acc * 256 + u_begin * kCols);
+        // one register buffer: the load of unit r+1 is issued as soon as unit r has left the registers
+        uint32_t vr[kCols];
+        auto tmem_load = [&](int u) {
+          if constexpr (M64) ptx::tmem_ld32(taddr + u * kCols, vr);
+          else ptx::tmem_ld16(taddr + u * kCols, vr);
+        };
+        tmem_load(0);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kMaxUpw; ++r) {
           if (r < upw) {
-           if (active) {
-            if (kHasRes && kPref < 8 && r == kPref) prefetch_batch(kPref);  // second batch: units 4..7
-            const int y = y_first + 2 * r;  // image rows y (columns 0..7 of the unit) and y+1 (columns 8..15)
+            if (kHasRes && kPref < kMaxUpw && r == kPref) prefetch_batch(kPref);  // second batch
+            const int y = y_first + kUnitRows * r;  // first image row of the unit
             ptx::tmem_ld_wait();
             if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(8 + 4 * r);
-            if (r + 1 < upw) ptx::tmem_ld16(taddr + (r + 1) * 16, v[(r + 1) & 1]);  // next unit in flight
-            const uint32_t(&vr)[16] = v[r & 1];
             if (y < s.h) {
               if (F & F_HEAD) {
                 // channel-major consumers: lane = channel c_lane, vr[j] = pixel (y + j/8, x0 + j%8)
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 const int nvx = s.w - x0;  // >= 8 for interior tiles
                 if (cm_lane && c_lane < e.cout_real) {
 #pragma unroll
-                  for (int i = 0; i < 2; ++i) {
+                  for (int i = 0; i < kUnitRows; ++i) {
                     if (y + i < s.h) {
                       const int oy = (y + i) * e.up_sy + e.up_py;
                       const uint32_t idx0 = static_cast<uint32_t>(oy * ow + x0 * e.up_sx + e.up_px);
@@ -534,77 +546,87 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 }
               }
               if (kBf16Out) {
-                // bias in the channel-major role (one register), then transpose 16 px x 32 (16) ch through shared
-                // memory: row = pixel, 36 (20)-float pitch (conflict-free STS.32; LDS.128 conflict-free at 36)
+                // bias in the channel-major role (one register), then transpose the unit through shared memory:
+                // row = pixel, 36 (20)-float pitch (conflict-free STS.32; LDS.128 conflict-free at 36)
                 __syncwarp();
                 if (cm_lane) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
+                  for (int j = 0; j < kCols; ++j) {
                     float f = __uint_as_float(vr[j]) + bias_c;
                     if (F & F_MID) f = fmaxf(fmaf(f, mid_s_c, mid_t_c), 0.f);
                     stage[j * kPitch + lane] = f;
                   }
                 }
+              }
+            }
+            if (r + 1 < upw) tmem_load(r + 1);  // next unit in flight while this one is post-processed
+            if (y < s.h) {
+              if (kBf16Out) {
                 __syncwarp();
                 if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(9 + 4 * r);
-                uint4 pool_cur[kPasses];
+                uint4 pool_cur[2];
 #pragma unroll
-                for (int ip = 0; ip < kPasses; ++ip) {
-                  const int i = M64 ? my_i : ip;  // my image row within the unit
-                  const bool valid = 2 * r + ip < n_rows_ok;
+                for (int ip = 0; ip < 2; ++ip) {
+                  const int row = kUnitRows * r + kPassStep * ip;  // my image row in this pass, relative to my first
+                  const bool valid = row < n_rows_ok;
                   float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                   if (valid) {
-                    lds8(stage + (pj + 8 * i) * kPitch + cq, f);
+                    lds8(stage + (pj + 8 * (my_i + kPassStep * ip)) * kPitch + cq, f);
                     if (F & F_PRE)
-                      *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>((2 * r + ip) * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
+                      *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>(row * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
                     if (F & F_RES1) add8(r1[r % kPref][ip], f);
                     if (F & F_RES2) add8(r2[r % kPref][ip], f);
-                    if (F & F_UP) add8(ru[r % kPref], f);
+                    if (F & F_UP) add8(ru[r % kPref][M64 ? ip : 0], f);
                   }
                   if (F & F_POOL) {
                     pool_cur[ip] = pack8(f);
                   } else if (valid) {
-                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>((2 * r + ip) * rs_raw)) = pack8(f);
+                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(row * rs_raw)) = pack8(f);
                     if (F & F_POST)
-                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>((2 * r + ip) * rs_post)) = affine_relu_pack8(f, post_s, post_t);
+                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(row * rs_post)) = affine_relu_pack8(f, post_s, post_t);
                   }
                 }
                 if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(10 + 4 * r);
                 if (F & F_POOL) {
-                  // 2x2 max-pool of the bf16-rounded values.  Vertical partner: the unit's other row = my second pass
-                  // (M = 128) or lane ^ 16 (M = 64); horizontal partner (pixel column pj ^ 1): lane ^ 4 (M = 128) or
-                  // lane ^ 2 (M = 64).  Shuffles run on all lanes.
-                  uint4 m = pool_cur[0];
-                  if (M64) {
+                  // 2x2 max-pool of the bf16-rounded values; shuffles run on all lanes.
+                  //   M = 128: vertical partner = my other pass, horizontal (pixel column pj ^ 1) = lane ^ 4,
+                  //            one pooled row per unit;
+                  //   M = 64 : vertical partner = lane ^ 16 (same pass), horizontal = lane ^ 2, pass ip is pooled row
+                  //            2r + ip of my part of the tile.
+#pragma unroll
+                  for (int pp = 0; pp < (M64 ? 2 : 1); ++pp) {
+                    uint4 m = pool_cur[pp];
+                    if (M64) {
+                      uint4 o;
+                      o.x = __shfl_xor_sync(0xffffffffu, m.x, 16);
+                      o.y = __shfl_xor_sync(0xffffffffu, m.y, 16);
+                      o.z = __shfl_xor_sync(0xffffffffu, m.z, 16);
+                      o.w = __shfl_xor_sync(0xffffffffu, m.w, 16);
+                      m = max_bf16x8(m, o);
+                    } else {
+                      m = max_bf16x8(m, pool_cur[1]);
+                    }
                     uint4 o;
-                    o.x = __shfl_xor_sync(0xffffffffu, m.x, 16);
-                    o.y = __shfl_xor_sync(0xffffffffu, m.y, 16);
-                    o.z = __shfl_xor_sync(0xffffffffu, m.z, 16);
-                    o.w = __shfl_xor_sync(0xffffffffu, m.w, 16);
+                    o.x = __shfl_xor_sync(0xffffffffu, m.x, M64 ? 2 : 4);
+                    o.y = __shfl_xor_sync(0xffffffffu, m.y, M64 ? 2 : 4);
+                    o.z = __shfl_xor_sync(0xffffffffu, m.z, M64 ? 2 : 4);
+                    o.w = __shfl_xor_sync(0xffffffffu, m.w, M64 ? 2 : 4);
                     m = max_bf16x8(m, o);
-                  } else {
-                    m = max_bf16x8(m, pool_cur[kPasses - 1]);
-                  }
-                  uint4 o;
-                  o.x = __shfl_xor_sync(0xffffffffu, m.x, M64 ? 2 : 4);
-                  o.y = __shfl_xor_sync(0xffffffffu, m.y, M64 ? 2 : 4);
-                  o.z = __shfl_xor_sync(0xffffffffu, m.z, M64 ? 2 : 4);
-                  o.w = __shfl_xor_sync(0xffffffffu, m.w, M64 ? 2 : 4);
-                  m = max_bf16x8(m, o);
-                  // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
-                  if (2 * r < n_rows_ok && my_i == 0 && (pj & 1) == 0) {
-                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(r * rs_raw)) = m;
-                    if (F & F_POST) {
-                      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                      add8(m, g);
-                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(r * rs_post)) = affine_relu_pack8(g, post_s, post_t);
+                    // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
+                    const int prow = (kUnitRows / 2) * r + pp;  // pooled row relative to y_first / 2
+                    if (2 * prow < n_rows_ok && my_i == 0 && (pj & 1) == 0) {
+                      if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(prow * rs_raw)) = m;
+                      if (F & F_POST) {
+                        float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        add8(m, g);
+                        *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(prow * rs_post)) = affine_relu_pack8(g, post_s, post_t);
+                      }
                     }
                   }
                 }
                 if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(11 + 4 * r);
               }
             }
-           }
           }
         }
       }
