@@ -86,6 +86,20 @@ int mvlm_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw
                           int cin_pad, void* out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Scan loader (host, multi-threaded): Wavefront OBJ -> flat arrays.            */
+/* Replaces vtkOBJReader in obj_to_actor, src/mvlm/utils/utils3d.py:16-21       */
+/* (error "does not contain any points" :20-21).  Output vertices are the       */
+/* unique (position, vt) pairs in ascending order, faces fan-triangulated.      */
+/* n_threads <= 0: one thread per host core (at most 16).                       */
+/* ------------------------------------------------------------------------- */
+typedef struct mvlm_obj mvlm_obj;
+int mvlm_obj_load(const char* path, int n_threads, mvlm_obj** out);
+int mvlm_obj_counts(const mvlm_obj* obj, int* n_verts, int* n_tris, int* has_uv);
+/* verts f32[n_verts*3], uvs f32[n_verts*2] (may be NULL), tris i32[n_tris*3]: host memory */
+int mvlm_obj_copy(const mvlm_obj* obj, float* verts, float* uvs, int32_t* tris);
+void mvlm_obj_free(mvlm_obj* obj);
+
+/* ------------------------------------------------------------------------- */
 /* Stage 1: batched multi-view orthographic rasteriser.                       */
 /* Replaces ObjVTKRenderer3D.render_3d_multi_rgb_geometry_depth               */
 /*   src/mvlm/utils/render3d.py:114-177 (+ camera :53-59,:136,:150-152, depth  */

@@ -81,6 +81,10 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_debug_hourglass_describe": ([vp, i32, C.c_char_p, i32], i32),
         "mvlm_hourglass_probe": ([vp, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
         "mvlm_hourglass_destroy": ([vp], None),
+        "mvlm_obj_load": ([C.c_char_p, i32, C.POINTER(vp)], i32),
+        "mvlm_obj_counts": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
+        "mvlm_obj_copy": ([vp, vp, vp, vp], i32),
+        "mvlm_obj_free": ([vp], None),
         "mvlm_heatmap_peaks": ([vp, i32, i32, i32, i32, i32, vp, vp], i32),
         "mvlm_rays_from_peaks": ([vp, vp, i32, i32, i32, vp, vp, vp], i32),
         "mvlm_consensus_workspace_bytes": ([i32, i32, i32], C.c_size_t),

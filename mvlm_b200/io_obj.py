@@ -27,34 +27,78 @@ class Mesh:
         return float(np.linalg.norm(self.verts.max(0) - self.verts.min(0)))
 
 
-def load_obj(path: Path | str, load_texture: bool = True) -> Mesh:
+def _load_texture(path: Path):
+    jpg = path.with_suffix(".jpg")
+    if not jpg.exists():
+        return None
+    try:
+        from PIL import Image
+
+        return np.asarray(Image.open(jpg).convert("RGB"), dtype=np.uint8)
+    except Exception:  # noqa: BLE001 - same policy as the reference: ignore an unreadable texture
+        return None
+
+
+def load_obj(path: Path | str, load_texture: bool = True, n_threads: int = 0) -> Mesh:
+    """Native loader (csrc/obj_loader.cu through the C-ABI, multi-threaded parse): what the pipeline uses."""
+    import ctypes as C
+
+    from . import _lib
+
+    path = Path(path)
+    if not path.is_file():
+        raise ValueError(f"File {path} does not exist.")
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.mvlm_obj_load(str(path).encode(), n_threads, C.byref(h))
+    if rc != 0:
+        raise ValueError(lib.mvlm_last_error().decode("utf-8", "replace"))
+    try:
+        nv, nt, has_uv = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.mvlm_obj_counts(h, C.byref(nv), C.byref(nt), C.byref(has_uv)), "mvlm_obj_counts")
+        verts = np.empty((nv.value, 3), dtype=np.float32)
+        tris = np.empty((nt.value, 3), dtype=np.int32)
+        uvs = np.empty((nv.value, 2), dtype=np.float32) if has_uv.value else None
+        _lib.check(lib.mvlm_obj_copy(h, verts.ctypes.data, None if uvs is None else uvs.ctypes.data, tris.ctypes.data),
+                   "mvlm_obj_copy")
+    finally:
+        lib.mvlm_obj_free(h)
+    texture = _load_texture(path) if (load_texture and uvs is not None) else None
+    return Mesh(verts=verts, tris=tris, uvs=uvs, texture=texture, path=path)
+
+
+def load_obj_python(path: Path | str, load_texture: bool = True) -> Mesh:
+    """Pure numpy restatement of the same loader: test infrastructure (the checker of the native parser)."""
     path = Path(path)
     if not path.is_file():
         raise ValueError(f"File {path} does not exist.")
     v_rows, vt_rows, f_rows = [], [], []
+    n_v = n_vt = 0
     with open(path, "r", errors="replace") as fh:
         for line in fh:
             if line.startswith("v "):
                 v_rows.append(line[2:])
+                n_v += 1
             elif line.startswith("vt "):
                 vt_rows.append(line[3:])
+                n_vt += 1
             elif line.startswith("f "):
-                f_rows.append(line[2:])
+                f_rows.append((line[2:], n_v, n_vt))  # counts so far: negative indices are relative to them
     if len(v_rows) == 0:
         raise ValueError(f"File {path} does not contain any points.")
     pos = np.loadtxt(v_rows, dtype=np.float64, ndmin=2, usecols=(0, 1, 2)).astype(np.float32)
     tex = np.loadtxt(vt_rows, dtype=np.float64, ndmin=2, usecols=(0, 1)).astype(np.float32) if vt_rows else None
     corners_v, corners_t = [], []
-    for row in f_rows:
+    for row, v_seen, vt_seen in f_rows:
         toks = row.split()
         vi, ti = [], []
         for tok in toks:
             parts = tok.split("/")
             a = int(parts[0])
-            vi.append(a - 1 if a > 0 else len(pos) + a)
+            vi.append(a - 1 if a > 0 else v_seen + a)
             if len(parts) > 1 and parts[1] != "":
                 b = int(parts[1])
-                ti.append(b - 1 if b > 0 else (len(tex) + b if tex is not None else -1))
+                ti.append(b - 1 if b > 0 else vt_seen + b)
             else:
                 ti.append(-1)
         for k in range(1, len(vi) - 1):
@@ -71,14 +115,6 @@ def load_obj(path: Path | str, load_texture: bool = True) -> Mesh:
         verts = pos[uniq[:, 0]]
         uvs = np.where(uniq[:, 1:2] >= 0, tex[np.clip(uniq[:, 1], 0, None)], 0.0).astype(np.float32)
         tris = inv.reshape(-1, 3).astype(np.int32)
-    texture = None
-    jpg = path.with_suffix(".jpg")
-    if load_texture and uvs is not None and jpg.exists():
-        try:
-            from PIL import Image
-
-            texture = np.asarray(Image.open(jpg).convert("RGB"), dtype=np.uint8)
-        except Exception:  # noqa: BLE001 - same policy as the reference: ignore an unreadable texture
-            texture = None
+    texture = _load_texture(path) if (load_texture and uvs is not None) else None
     return Mesh(verts=np.ascontiguousarray(verts), tris=np.ascontiguousarray(tris),
                 uvs=None if uvs is None else np.ascontiguousarray(uvs), texture=texture, path=path)

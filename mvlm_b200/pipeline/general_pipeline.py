@@ -100,6 +100,39 @@ class Pipeline(abc.ABC, TimeMixin):
             return landmarks
         return self._predict_seams(file_name, full_s)
 
+    def predict_files(self, file_names, prefetch: int = 2) -> list:
+        """Batch driver (the reference's main.py:50-62 loop is strictly serial): the native loader parses / decodes the
+        next `prefetch` scans on background threads (the C parser and the JPEG decoder release the GIL) while the GPU
+        works on the current one.  Returns one (L,3) array (or None for a missing file) per input, in order."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        if self.predictor_2d is None:
+            raise ValueError("Predictor2D is not initialized.")
+        files = [Path(f) for f in file_names]
+
+        def load(f: Path):
+            if not f.exists():
+                return None
+            if not f.is_file():
+                raise FileNotFoundError(f"File {f} is not a file")
+            if not f.suffix == ".obj":
+                raise ValueError(f"File {f} is not an .obj file. Only .obj files are supported.")
+            return load_obj(f)
+
+        results = []
+        with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
+            pending = [pool.submit(load, f) for f in files[:prefetch]]
+            for i, f in enumerate(files):
+                mesh = pending.pop(0).result()
+                if i + prefetch < len(files):
+                    pending.append(pool.submit(load, files[i + prefetch]))
+                if mesh is None:
+                    print(f"File {f} does not exist")
+                    results.append(None)
+                else:
+                    results.append(self.predict_mesh(mesh))
+        return results
+
     def predict_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None) -> np.ndarray:
         """Fused device path for an already loaded scan (host arrays in, (L,3) float64 out)."""
         r, p, e = self.renderer_3d, self.predictor_2d, self.estimator_3d

@@ -81,7 +81,8 @@ def predict_files(pipeline, paths, group=None):
     ranks; rank 0 receives all results.  Returns {index: (L,3) array} on rank 0, own share elsewhere."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    mine = {i: pipeline.predict_one_file(paths[i]) for i in shard_scans(len(paths), rank, world)}
+    idx = shard_scans(len(paths), rank, world)
+    mine = dict(zip(idx, pipeline.predict_files([paths[i] for i in idx])))  # prefetching loader, see Pipeline.predict_files
     if world == 1:
         return mine
     gathered = [None] * world

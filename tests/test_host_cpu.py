@@ -93,6 +93,45 @@ def test_obj_roundtrip_and_vertex_duplication(tmp_path):
         load_obj(tmp_path / "d.obj")
 
 
+def test_native_obj_loader_matches_python_restatement(tmp_path):
+    """csrc/obj_loader.cu (multi-threaded C++ parse behind the C-ABI) == the numpy restatement, bit for bit:
+    index forms a, a/b, a/b/c, a//c, negative (relative) indices between interleaved v / f blocks, polygons,
+    CRLF line ends, '+' signs and exponents, vertices shared by several vt, unreferenced positions."""
+    from mvlm_b200.io_obj import load_obj_python
+
+    rng = np.random.RandomState(7)
+    cases = {
+        "forms.obj": "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 2 2 2\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                     "f 1/1/1 2/2/1 3/3/1 4/4/1\nf 1//1 2//1 3//1\nf 1/3 2/2 4/1\nf 4 3 2 1\n",
+        "relative.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nf -3/-3 -2/-2 -1/-1\n"
+                        "v 5 5 5\nv 6 5 5\nv 5 6 5\nvt 0.5 0.5\nf -3/-1 -2/2 -1/-4\nf 1/1 5/4 6/2\n",
+        "crlf.obj": "# comment\r\nv +1.5e0 -2.25E-1 3\r\nv 1e-3 2 3\r\nv 0.1 0.2 0.3\r\n\r\nf 1 2 3\r\n",
+        "nouv.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 9 9 9\nvt 0 0\nf 1 2 3\n",
+    }
+    v, uv, t = synth.face_mesh(grid=40, seed=3)
+    synth.write_obj(tmp_path / "grid.obj", v, uv, t, None)
+    # a big random soup: many positions with several vt each, spans several parser threads
+    n_v, n_t, n_f = 3000, 2500, 9000
+    lines = [f"v {a:.6f} {b:.6f} {c:.6f}" for a, b, c in rng.randn(n_v, 3)] + [f"vt {a:.5f} {b:.5f}" for a, b in rng.rand(n_t, 2)]
+    for _ in range(n_f):
+        k = rng.randint(3, 6)
+        lines.append("f " + " ".join(f"{rng.randint(1, n_v + 1)}/{rng.randint(1, n_t + 1)}" for _ in range(k)))
+    (tmp_path / "soup.obj").write_text("\n".join(lines) + "\n")
+    for name, text in cases.items():
+        (tmp_path / name).write_text(text)
+    for name in list(cases) + ["grid.obj", "soup.obj"]:
+        ref = load_obj_python(tmp_path / name)
+        for threads in (1, 3, 0):
+            got = load_obj(tmp_path / name, n_threads=threads)
+            assert np.array_equal(got.verts, ref.verts) and np.array_equal(got.tris, ref.tris), name
+            assert (got.uvs is None) == (ref.uvs is None) and (ref.uvs is None or np.array_equal(got.uvs, ref.uvs)), name
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 7\n")
+    with pytest.raises(ValueError, match="references vertex"):
+        load_obj(tmp_path / "bad.obj")
+    with pytest.raises(ValueError, match="does not exist"):
+        load_obj(tmp_path / "missing.obj")
+
+
 def test_create_pipeline_name_handling():
     import mvlm
 

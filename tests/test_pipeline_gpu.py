@@ -104,3 +104,25 @@ def test_reference_rng_replay(lib, scan):
     for _ in range(73):
         np.random.choice(range(4), 8, replace=True)
     assert np.array_equal(np.random.get_state()[1][:4], state_after)
+
+
+def test_predict_files_prefetching_driver(lib, scan, tmp_path):
+    """Pipeline.predict_files (background native loader, scans in order) == a loop of predict_one_file
+    (the reference's main.py:50-62), incl. a missing file -> None."""
+    import shutil
+
+    import mvlm
+
+    sd = seeded_state_dict(73, "RGB+depth", seed=3)
+    dm = mvlm.pipeline.create_pipeline("dtu3d", n_views=8, weights=sd, seed=5, verbose=False, image_size=(64, 64))
+    v, uv, t = synth.face_mesh(grid=60, seed=12)
+    synth.write_obj(tmp_path / "other.obj", v, uv, t, synth.face_texture(128, seed=12))
+    shutil.copy(scan, tmp_path / "face.obj")
+    shutil.copy(scan.with_suffix(".jpg"), tmp_path / "face.jpg")
+    files = [tmp_path / "face.obj", tmp_path / "other.obj", tmp_path / "missing.obj", tmp_path / "face.obj", tmp_path / "other.obj"]
+    serial = [dm.predict_one_file(f) for f in files]
+    batch = dm.predict_files(files, prefetch=2)
+    assert len(batch) == len(files) and batch[2] is None and serial[2] is None
+    for a, b in zip(serial, batch):
+        assert (a is None and b is None) or np.array_equal(a, b)
+    assert not np.array_equal(batch[0], batch[1])
