@@ -32,7 +32,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_LANDMARKS = 73
-CNN_DRAM_BYTES_PER_STEP = 54.9e9  # measured with ncu, see profiles/r1_dram_per_launch.csv
+CNN_DRAM_BYTES_PER_STEP = 50.6e9  # measured with ncu, see profiles/r1_dram_per_launch.csv (30.3 GB read + 20.3 GB written)
 IMAGE_MODE = "RGB+depth"
 
 
@@ -355,8 +355,8 @@ def run_ours(args):
             "stages_ms": stage_ms,
             "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (CNN stage incl. its stem/pool/upsample glue launches)",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum summed over the 164 CNN launches of one step
-                         # (ncu capture of this command, profiles/r1_dram_per_launch.csv: 32.5 GB read + 22.4 GB written)
+                         # dram__bytes_read.sum + dram__bytes_write.sum summed over the 154 CNN launches of one step
+                         # (ncu capture of this command, profiles/r1_dram_per_launch.csv: 30.3 GB read + 20.3 GB written)
                          "traffic": CNN_DRAM_BYTES_PER_STEP if (args.views, args.size) == (100, 256) else None,
                          "traffic_note": "bytes per step over all CNN launches; = %.0f%% of measured HBM peak at this step time" % (
                              100 * CNN_DRAM_BYTES_PER_STEP / (stage_ms["cnn"] / 1e3) / 1e9 / pk["hbm_gbs"]),

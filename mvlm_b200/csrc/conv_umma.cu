@@ -244,6 +244,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, per-channel parameters,
+  // none of which another launch of the plan writes) may overlap the tail of the previous kernel in the stream;
+  // every read or write of an activation tensor comes after this wait.  The next kernel may start its own
+  // prologue as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = bar->tmem_base;
   const bool prof = p.prof != nullptr;
   const long long t_kernel0 = clock64();
@@ -673,6 +679,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// programmatic dependent launch of consecutive conv kernels (MVLM_CONV_NO_PDL=1 switches it off)
+const bool g_pdl = getenv("MVLM_CONV_NO_PDL") == nullptr;
+
 template <int F>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
   static bool configured = false;
@@ -681,7 +690,17 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv_umma_kernel<F><<<grid, kThreads, kSmemBytes, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MVLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<F>, p));
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
