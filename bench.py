@@ -345,7 +345,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, one scan per step per GPU",
                        "n_landmarks": N_LANDMARKS, "ransac_hypotheses": args.hyp, "weights": "seeded random init",
-                       "l2": "per-step activations (22.7 GB workspace at 100 views) exceed the 126 MB L2; no explicit flush",
+                       "l2": "per-step activations (%.1f GB workspace at %d views) exceed the 126 MB L2; no explicit flush" % (
+                           lib.mvlm_hourglass_workspace_bytes(N_LANDMARKS, 4, args.views, args.size, args.size) / 1e9, args.views),
                        "parallelism": f"scans sharded over {world} GPU(s), no collective"},
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "e2e_files": {"value": files_value, "unit": "scans/s",
