@@ -63,10 +63,23 @@ class PaulsenModel(Predictor2D):
     def network(self, n_views: int, h: int, w: int) -> ops.Hourglass:
         key = (n_views, h, w)
         if key not in self._nets:
-            self._nets.clear()  # one workspace at a time (22.7 GB at 100 views of 256^2)
+            self._nets.clear()  # one workspace at a time (20.6 GB at 100 views of 256^2)
             self._nets[key] = ops.Hourglass(self._state_dict, self.get_lm_count(), IMAGE_CHANNELS[self.image_mode],
                                             n_views, h, w, device=self.device)
         return self._nets[key]
+
+    def max_views_per_launch(self, v: int, h: int, w: int) -> int:
+        """Largest slice of the view axis one plan may take: 32-bit element offsets and, on a GPU, half of the free
+        memory for the workspace.  Prefers a divisor of v so that every slice reuses the same plan."""
+        limit = (2 ** 31 - 1) // (h * w * 256)
+        if self.device.type == "cuda":
+            free, _ = torch.cuda.mem_get_info(self.device)
+            cached = sum(n.workspace.numel() for n in self._nets.values())
+            limit = min(limit, max(1, int((free + cached) * 0.5) // (h * w * 3200)))
+        if v <= limit:
+            return v
+        best = max(d for d in range(1, limit + 1) if v % d == 0)
+        return best if best * 2 > limit else limit
 
     # ------------------------------------------------------------------ paulsenpredictor.py:167-217
     def predict_landmarks_from_images(self, image_stack: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
@@ -83,6 +96,11 @@ class PaulsenModel(Predictor2D):
         if img.dtype == torch.float32 and img.shape[3] > cin:
             img = img[..., :cin].contiguous()   # e.g. an RGB model fed the 4-channel stack
         v, h, w = img.shape[0], img.shape[1], img.shape[2]
+        # View batches: the conv kernel indexes its NHWC tensors with 32-bit element offsets (V*H*W*256 < 2^31) and the
+        # plan's workspace grows with V (3.2 KB per pixel); larger stacks run as equal slices of the view axis.
+        chunk = self.max_views_per_launch(v, h, w)
+        if chunk < v:
+            return torch.cat([self.predict_landmarks_device(img[i:i + chunk]).clone() for i in range(0, v, chunk)], dim=1)
         net = self.network(v, h, w)
         if self.selection_method == "simple":
             # the rasteriser's persistent u8 image has a stable address: replay the captured CUDA graph

@@ -94,3 +94,21 @@ def test_c5_consensus_microbench_parity(lib):
     # size-independent properties at full size: more hypotheses never increase the error; robust to 30 % outliers
     assert (err <= err64.cpu().numpy() + 1e-12).all()
     assert np.abs(lm - truth).max() < 1.0                     # mm, rays carry 0.5 mm jitter
+
+
+def test_view_axis_slicing_equals_one_launch(lib, monkeypatch):
+    """Stacks beyond one plan's limits (32-bit element offsets / workspace) run as slices of the view axis: same peaks."""
+    import mvlm
+    from mvlm_b200.prediction.paulsenpredictor import PaulsenModel
+
+    mesh = _mesh(grid=60)
+    tr = synth.random_view_transforms(12, seed=4)
+    dm = mvlm.pipeline.create_pipeline("dtu3d", n_views=12, weights=seeded_state_dict(73, "RGB+depth", 5), seed=3,
+                                       verbose=False, image_size=(64, 64), transforms=tr)
+    dmesh = dm.renderer_3d.upload(mesh)
+    u8 = dm.renderer_3d.render_device(dmesh, tr)["u8"]
+    whole = dm.predictor_2d.predict_landmarks_device(u8).clone()
+    assert dm.predictor_2d.max_views_per_launch(100, 512, 512) == 25      # 2^31 / (512*512*256) = 31 -> divisor 25
+    monkeypatch.setattr(PaulsenModel, "max_views_per_launch", lambda self, v, h, w: min(v, 4))
+    sliced = dm.predictor_2d.predict_landmarks_device(u8)
+    assert torch.equal(whole, sliced)
