@@ -63,7 +63,14 @@ class PaulsenModel(Predictor2D):
     def network(self, n_views: int, h: int, w: int) -> ops.Hourglass:
         key = (n_views, h, w)
         if key not in self._nets:
-            self._nets.clear()  # one workspace at a time (20.6 GB at 100 views of 256^2)
+            # at most two plans alive (20.6 GB of workspace at 100 views of 256^2): the current stack shape and, when a
+            # stack is sliced along the view axis, the shorter last slice
+            while len(self._nets) >= 2:
+                self._nets.pop(next(iter(self._nets)))
+            if self._nets and self.device.type == "cuda":
+                free, _ = torch.cuda.mem_get_info(self.device)
+                if free < 3200 * n_views * h * w * 1.2:
+                    self._nets.clear()
             self._nets[key] = ops.Hourglass(self._state_dict, self.get_lm_count(), IMAGE_CHANNELS[self.image_mode],
                                             n_views, h, w, device=self.device)
         return self._nets[key]

@@ -39,14 +39,14 @@ for _ in range(3):
     split = predict_mesh_view_split(dm, mesh, tr)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 3
-ok = True
+ok, checked = True, False
 if views * size * size <= 64 * 256 * 256:  # single-rank reference only when it fits comfortably
     single = dm.predict_mesh(mesh)
-    ok = bool(np.array_equal(single, split))
+    ok, checked = bool(np.array_equal(single, split)), True
 flag = torch.tensor([int(ok)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"view-split over {world} ranks: {views} views {size}^2, {len(t)} tris: {dt * 1e3:.2f} ms/scan, "
-          f"identical to single rank: {bool(flag.item())}")
+          + (f"identical to single rank: {bool(flag.item())}" if checked else "single-rank comparison skipped at this size"))
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
