@@ -102,8 +102,9 @@ class Pipeline(abc.ABC, TimeMixin):
 
     def predict_files(self, file_names, prefetch: int = 2) -> list:
         """Batch driver (the reference's main.py:50-62 loop is strictly serial): the native loader parses / decodes the
-        next `prefetch` scans on background threads (the C parser and the JPEG decoder release the GIL) while the GPU
-        works on the current one.  Returns one (L,3) array (or None for a missing file) per input, in order."""
+        next `prefetch` scans on background threads (the C parser and the JPEG decoder release the GIL) and the copies
+        and launches of scan i+1 are enqueued while the GPU still works on scan i (see predict_meshes).
+        Returns one (L,3) array (or None for a missing file) per input, in order."""
         from concurrent.futures import ThreadPoolExecutor
 
         if self.predictor_2d is None:
@@ -117,24 +118,27 @@ class Pipeline(abc.ABC, TimeMixin):
                 raise FileNotFoundError(f"File {f} is not a file")
             if not f.suffix == ".obj":
                 raise ValueError(f"File {f} is not an .obj file. Only .obj files are supported.")
-            return load_obj(f)
+            # four parser threads per scan: with more, the loaders of `prefetch` scans oversubscribe the host and the
+            # thread that feeds the GPU gets descheduled (measured on the 16-core box: 36 scans/s with 16, 51 with 4)
+            return load_obj(f, n_threads=4)
 
-        results = []
-        with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
-            pending = [pool.submit(load, f) for f in files[:prefetch]]
-            for i, f in enumerate(files):
-                mesh = pending.pop(0).result()
-                if i + prefetch < len(files):
-                    pending.append(pool.submit(load, files[i + prefetch]))
-                if mesh is None:
-                    print(f"File {f} does not exist")
-                    results.append(None)
-                else:
-                    results.append(self.predict_mesh(mesh))
-        return results
+        def meshes():
+            with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
+                pending = [pool.submit(load, f) for f in files[:prefetch]]
+                for i, f in enumerate(files):
+                    mesh = pending.pop(0).result()
+                    if i + prefetch < len(files):
+                        pending.append(pool.submit(load, files[i + prefetch]))
+                    if mesh is None:
+                        print(f"File {f} does not exist")
+                    yield mesh
 
-    def predict_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None) -> np.ndarray:
-        """Fused device path for an already loaded scan (host arrays in, (L,3) float64 out)."""
+        return self.predict_meshes(meshes())
+
+    def _enqueue_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None):
+        """Enqueues the whole hot path of one scan on the current stream WITHOUT waiting for it: host -> device copies
+        of the scan, raster, CNN, rays, consensus, snap, device -> pinned-host copy of the (L*3 + 1) result.
+        Returns (pinned host tensor, CUDA event recorded after the copy, objects to keep alive until then)."""
         r, p, e = self.renderer_3d, self.predictor_2d, self.estimator_3d
         if transforms is None:
             transforms = r.generate_3d_transformations()
@@ -146,17 +150,48 @@ class Pipeline(abc.ABC, TimeMixin):
         if e.seed is not None:
             draws_d = e.seeded_draws_device(peaks.shape[0])
         else:
-            # reference RNG replay needs the per-landmark line counts -> one small D2H of the peak values
+            # reference RNG replay needs the per-landmark line counts -> one small D2H of the peak values (synchronises)
             draws = e.reference_draws(peaks.cpu().numpy())
             draws_d = torch.from_numpy(draws.view(np.int32)).to(self.device)
         lm, err, _ = e.estimate_landmarks_from_lines_device(peaks, starts, ends, draws_d)
         from .. import ops
 
         snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm)
-        result = torch.cat([snapped.reshape(-1), err.sum().reshape(1) / err.numel()]).cpu().numpy()
+        result = torch.cat([snapped.reshape(-1), err.sum().reshape(1) / err.numel()])
+        host = torch.empty(result.shape, dtype=result.dtype, pin_memory=True)
+        host.copy_(result, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return host, done, (dmesh, result, peaks, starts, ends, lm)
+
+    def _finish(self, host: torch.Tensor, done) -> np.ndarray:
+        done.synchronize()
+        result = host.numpy().copy()
         self.last_error = float(result[-1])
         self._print("Landmarks [Error]: ", f"{self.last_error:08.6f}", " mm")
         return result[:-1].reshape(-1, 3)
+
+    def predict_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None) -> np.ndarray:
+        """Fused device path for an already loaded scan (host arrays in, (L,3) float64 out)."""
+        host, done, _keep = self._enqueue_mesh(mesh, transforms)
+        return self._finish(host, done)
+
+    def predict_meshes(self, meshes, depth: int = 2) -> list:
+        """Batch form of predict_mesh: same results, but up to `depth` scans are in flight -- the copies and launches of
+        the next scan are enqueued (one stream, so buffers are reused in order) before the host waits for the landmarks
+        of the previous one, which keeps host-side latency off the GPU's critical path.  A None entry yields None."""
+        results, inflight = [], []
+        for mesh in meshes:
+            if mesh is None:
+                inflight.append(None)
+            else:
+                inflight.append(self._enqueue_mesh(mesh))
+            while len([x for x in inflight if x is not None]) > depth or (inflight and inflight[0] is None):
+                head = inflight.pop(0)
+                results.append(None if head is None else self._finish(head[0], head[1]))
+        for head in inflight:
+            results.append(None if head is None else self._finish(head[0], head[1]))
+        return results
 
     def _predict_seams(self, file_name: Path, full_s: float):
         self.tic()

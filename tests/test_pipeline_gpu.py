@@ -126,3 +126,24 @@ def test_predict_files_prefetching_driver(lib, scan, tmp_path):
     for a, b in zip(serial, batch):
         assert (a is None and b is None) or np.array_equal(a, b)
     assert not np.array_equal(batch[0], batch[1])
+
+
+def test_predict_meshes_pipelined_equals_blocking_calls(lib, scan):
+    """Pipeline.predict_meshes (scans in flight back to back on one stream, buffers reused in order) == one blocking
+    predict_mesh per scan, for different scans in one batch and with a None entry."""
+    import mvlm
+
+    sd = seeded_state_dict(73, "RGB+depth", seed=3)
+    dm = mvlm.pipeline.create_pipeline("dtu3d", n_views=8, weights=sd, seed=5, verbose=False, image_size=(64, 64))
+    a = load_obj(scan)
+    v, uv, t = synth.face_mesh(grid=50, seed=13)
+    from mvlm_b200.io_obj import Mesh
+
+    b = Mesh(verts=v, tris=t, uvs=uv, texture=synth.face_texture(64, seed=13))
+    batch = [a, b, None, b, a, a, b]
+    blocking = [None if m is None else dm.predict_mesh(m) for m in batch]
+    for depth in (1, 2, 4):
+        got = dm.predict_meshes(batch, depth=depth)
+        assert len(got) == len(batch) and got[2] is None
+        for x, y in zip(blocking, got):
+            assert (x is None and y is None) or np.array_equal(x, y)
