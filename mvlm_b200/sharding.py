@@ -66,10 +66,16 @@ def predict_mesh_view_split(pipeline, mesh, transforms: np.ndarray, group=None) 
     local = r.render_device(dmesh, transforms[start:start + count])
     peaks_local = p.predict_landmarks_device(local["u8"])
     peaks = allgather_peaks(peaks_local, n_views, group)
-    starts, ends = e.estimate_landmark_lines_device(peaks, transforms, r.image_size[0])
     if e.seed is None:
         raise ValueError("view-split prediction needs a seeded hypothesis table (Estimator3D.seed)")
-    draws = torch.from_numpy(e.seeded_draws(peaks.shape[0]).view(np.int32)).to(peaks.device)
+    # rotation matrices of ALL views and the hypothesis table are cached on the device across scans
+    if getattr(pipeline, "_vs_rot_key", None) != transforms.tobytes():
+        from .utils.render3d import rotation_matrices
+
+        pipeline._vs_rot = torch.from_numpy(rotation_matrices(transforms).reshape(-1, 9)).to(peaks.device)
+        pipeline._vs_rot_key = transforms.tobytes()
+    starts, ends = e.estimate_landmark_lines_device(peaks, transforms, r.image_size[0], rot=pipeline._vs_rot)
+    draws = e.seeded_draws_device(peaks.shape[0])
     lm, err, _ = e.estimate_landmarks_from_lines_device(peaks, starts, ends, draws)
     snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm)
     pipeline.last_error = float((err.sum() / err.numel()).item())

@@ -31,14 +31,15 @@ tr = synth.random_view_transforms(views, seed=77)
 sd = seeded_state_dict(73, "RGB+depth", 1234)
 dm = create_pipeline("dtu3d", n_views=views, weights=sd, seed=5, n_hypotheses=8, verbose=False, image_size=(size, size),
                      transforms=tr, device=f"cuda:{local}")
-split = predict_mesh_view_split(dm, mesh, tr)
+for _ in range(5):  # plan creation, graph capture and the renderer's pinned staging slots are first-use costs
+    split = predict_mesh_view_split(dm, mesh, tr)
 torch.cuda.synchronize()
 dist.barrier()
 t0 = time.perf_counter()
-for _ in range(3):
+for _ in range(5):
     split = predict_mesh_view_split(dm, mesh, tr)
 torch.cuda.synchronize()
-dt = (time.perf_counter() - t0) / 3
+dt = (time.perf_counter() - t0) / 5
 ok, checked = True, False
 if views * size * size <= 64 * 256 * 256:  # single-rank reference only when it fits comfortably
     single = dm.predict_mesh(mesh)
