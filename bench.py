@@ -327,7 +327,7 @@ def run_ours(args):
 
     # ---- from files: Pipeline.predict_files(paths) = native multi-threaded OBJ parse + JPEG decode of the next scans
     #      on background threads while the GPU works (what predict_one_file(path) users get); informational
-    files_value = None
+    files_value = files_nvjpeg_value = None
     if not args.profile:
         import tempfile
 
@@ -346,6 +346,18 @@ def run_ours(args):
                 dist.all_reduce(tf, op=dist.ReduceOp.MAX)
             files_value = world * n_files / float(tf.item())
             assert len(out) == n_files and all(o is not None and o.shape == (N_LANDMARKS, 3) for o in out)
+            # same with the texture decoded on the GPU (nvJPEG, opt-in: pixel values differ slightly from libjpeg-turbo)
+            dm.texture_decoder = "nvjpeg"
+            dm.predict_files(paths[:2])
+            barrier()
+            t0 = time.perf_counter()
+            out = dm.predict_files([paths[i % 4] for i in range(n_files)])
+            torch.cuda.synchronize()
+            tf = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            files_nvjpeg_value = world * n_files / float(tf.item())
+            dm.texture_decoder = "pil"
 
     if rank == 0:
         pk, pk_kind = peaks_file()
@@ -365,7 +377,7 @@ def run_ours(args):
                     "api": "Pipeline.predict_meshes(host meshes): up to two scans in flight on one stream",
                     "sync_value": e2e_sync_value,
                     "sync_api": "Pipeline.predict_mesh(host mesh), one blocking call per scan"},
-            "e2e_files": {"value": files_value, "unit": "scans/s",
+            "e2e_files": {"value": files_value, "nvjpeg_value": files_nvjpeg_value, "unit": "scans/s",
                           "note": "Pipeline.predict_files(paths): .obj (6.3 MB text) + .jpg read from disk per scan, native "
                                   "multi-threaded parser, 2-deep prefetch; informational, not the contract's e2e"},
             "gpu_launches": int(launches),

@@ -99,6 +99,12 @@ int mvlm_obj_counts(const mvlm_obj* obj, int* n_verts, int* n_tris, int* has_uv)
 int mvlm_obj_copy(const mvlm_obj* obj, float* verts, float* uvs, int32_t* tris);
 void mvlm_obj_free(mvlm_obj* obj);
 
+/* Texture decode on the GPU (nvJPEG); replaces vtkJPEGReader in obj_to_actor, src/mvlm/utils/utils3d.py:26-36.  */
+/* data/len: the compressed file in host memory; out_rgb_dev: device buffer u8[height][width][3], row 0 = top.    */
+/* Thread-safe (one decoder state per calling thread); asynchronous on `stream` after the host-side parse.        */
+int mvlm_jpeg_info(const uint8_t* data, size_t len, int* width, int* height);
+int mvlm_jpeg_decode_rgb(const uint8_t* data, size_t len, uint8_t* out_rgb_dev, int width, int height, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Stage 1: batched multi-view orthographic rasteriser.                       */
 /* Replaces ObjVTKRenderer3D.render_3d_multi_rgb_geometry_depth               */

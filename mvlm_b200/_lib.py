@@ -85,6 +85,8 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_obj_counts": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
         "mvlm_obj_copy": ([vp, vp, vp, vp], i32),
         "mvlm_obj_free": ([vp], None),
+        "mvlm_jpeg_info": ([C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32)], i32),
+        "mvlm_jpeg_decode_rgb": ([C.c_char_p, C.c_size_t, vp, i32, i32, vp], i32),
         "mvlm_heatmap_peaks": ([vp, i32, i32, i32, i32, i32, vp, vp], i32),
         "mvlm_rays_from_peaks": ([vp, vp, i32, i32, i32, vp, vp, vp], i32),
         "mvlm_consensus_workspace_bytes": ([i32, i32, i32], C.c_size_t),

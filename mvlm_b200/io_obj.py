@@ -19,8 +19,9 @@ class Mesh:
     verts: np.ndarray          # (Nv,3) float32
     tris: np.ndarray           # (Nt,3) int32
     uvs: np.ndarray | None     # (Nv,2) float32
-    texture: np.ndarray | None  # (Th,Tw,3) uint8, row 0 = top of the image
+    texture: object | None     # (Th,Tw,3) uint8, row 0 = top of the image: numpy array, or a CUDA tensor (nvJPEG decode)
     path: Path | None = None
+    texture_ready: object | None = None  # CUDA event recorded after a device-side decode (texture is a CUDA tensor)
 
     @property
     def bbox_diagonal(self) -> float:
@@ -39,8 +40,48 @@ def _load_texture(path: Path):
         return None
 
 
-def load_obj(path: Path | str, load_texture: bool = True, n_threads: int = 0) -> Mesh:
-    """Native loader (csrc/obj_loader.cu through the C-ABI, multi-threaded parse): what the pipeline uses."""
+_tls = None
+
+
+def _decode_texture_nvjpeg(path: Path, device):
+    """`<stem>.jpg` -> (Th,Tw,3) uint8 CUDA tensor + the event recorded behind the decode (mvlm_jpeg_decode_rgb on a
+    per-thread side stream: the loader threads of Pipeline.predict_files decode while the main stream computes)."""
+    import threading
+
+    import torch
+
+    from . import _lib
+
+    global _tls
+    if _tls is None:
+        _tls = threading.local()
+    jpg = path.with_suffix(".jpg")
+    if not jpg.exists():
+        return None, None
+    data = jpg.read_bytes()
+    lib = _lib.load()
+    import ctypes as C
+
+    w, h = C.c_int(), C.c_int()
+    if lib.mvlm_jpeg_info(data, len(data), C.byref(w), C.byref(h)) != 0:
+        return None, None  # same policy as the reference: ignore an unreadable texture
+    device = torch.device(device)
+    if getattr(_tls, "stream", None) is None or _tls.device != device:
+        _tls.stream, _tls.device = torch.cuda.Stream(device), device
+    with torch.cuda.device(device), torch.cuda.stream(_tls.stream):
+        tex = torch.empty((h.value, w.value, 3), dtype=torch.uint8, device=device)
+        if lib.mvlm_jpeg_decode_rgb(data, len(data), tex.data_ptr(), w.value, h.value, _tls.stream.cuda_stream) != 0:
+            return None, None
+        ready = torch.cuda.Event()
+        ready.record(_tls.stream)
+    return tex, ready
+
+
+def load_obj(path: Path | str, load_texture: bool = True, n_threads: int = 0, texture_decoder: str = "pil",
+             device="cuda") -> Mesh:
+    """Native loader (csrc/obj_loader.cu through the C-ABI, multi-threaded parse): what the pipeline uses.
+    texture_decoder: "pil" (host decode, libjpeg-turbo: the decoder the parity tests share with the oracle) or
+    "nvjpeg" (csrc/jpeg_decode.cu: decoded on the GPU into device memory; values may differ by a few LSB)."""
     import ctypes as C
 
     from . import _lib
@@ -63,8 +104,15 @@ def load_obj(path: Path | str, load_texture: bool = True, n_threads: int = 0) ->
                    "mvlm_obj_copy")
     finally:
         lib.mvlm_obj_free(h)
-    texture = _load_texture(path) if (load_texture and uvs is not None) else None
-    return Mesh(verts=verts, tris=tris, uvs=uvs, texture=texture, path=path)
+    texture, ready = None, None
+    if load_texture and uvs is not None:
+        if texture_decoder == "nvjpeg":
+            texture, ready = _decode_texture_nvjpeg(path, device)
+        elif texture_decoder == "pil":
+            texture = _load_texture(path)
+        else:
+            raise ValueError(f"Unknown texture decoder: {texture_decoder}")
+    return Mesh(verts=verts, tris=tris, uvs=uvs, texture=texture, path=path, texture_ready=ready)
 
 
 def load_obj_python(path: Path | str, load_texture: bool = True) -> Mesh:

@@ -45,7 +45,8 @@ class Pipeline(abc.ABC, TimeMixin):
                  render_image_folder: Path | None = None, visualize_rays: bool = False,
                  screenshot_folder: Path | None = None, *, image_size: tuple = (256, 256),
                  channel_mode: str = "RGB+depth", n_hypotheses: int = 1, seed: int | None = None,
-                 transforms: np.ndarray | None = None, device: str = "cuda", verbose: bool = True):
+                 transforms: np.ndarray | None = None, device: str = "cuda", verbose: bool = True,
+                 texture_decoder: str = "pil"):
         TimeMixin.__init__(self)
         self.render_image_stack = render_image_stack
         self.render_image_folder = render_image_folder
@@ -54,6 +55,8 @@ class Pipeline(abc.ABC, TimeMixin):
         self.screenshot_folder = screenshot_folder
         self.verbose = verbose
         self.device = torch.device(device)
+        # "pil": host decode (shared with the parity oracle); "nvjpeg": decode on the GPU into device memory
+        self.texture_decoder = texture_decoder
 
         self.renderer_3d = ObjRenderer3D(image_size=image_size, offscreen=offscreen, n_views=n_views,
                                          channel_mode=channel_mode, device=device)
@@ -93,7 +96,7 @@ class Pipeline(abc.ABC, TimeMixin):
             if not file_name.suffix == ".obj":
                 raise ValueError(f"File {file_name} is not an .obj file. Only .obj files are supported.")
             self.tic()
-            mesh = load_obj(file_name)
+            mesh = load_obj(file_name, texture_decoder=self.texture_decoder, device=self.device)
             self._print("Render [1] - Setup time: ", self.toc_p())
             landmarks = self.predict_mesh(mesh)
             self._print("Landmarks 3D Total: ", self.p_time(time.time() - full_s))
@@ -120,7 +123,7 @@ class Pipeline(abc.ABC, TimeMixin):
                 raise ValueError(f"File {f} is not an .obj file. Only .obj files are supported.")
             # four parser threads per scan: with more, the loaders of `prefetch` scans oversubscribe the host and the
             # thread that feeds the GPU gets descheduled (measured on the 16-core box: 36 scans/s with 16, 51 with 4)
-            return load_obj(f, n_threads=4)
+            return load_obj(f, n_threads=4, texture_decoder=self.texture_decoder, device=self.device)
 
         def meshes():
             with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:

@@ -82,6 +82,11 @@ class DeviceMesh:
         def up(name, a):
             if a is None:
                 return None
+            if isinstance(a, torch.Tensor):  # texture decoded on the device (nvJPEG) on the loader's side stream
+                if mesh.texture_ready is not None:
+                    torch.cuda.current_stream().wait_event(mesh.texture_ready)
+                a.record_stream(torch.cuda.current_stream())
+                return a
             a = np.ascontiguousarray(a)
             if device.type != "cuda":
                 return torch.from_numpy(a.copy()).to(device)

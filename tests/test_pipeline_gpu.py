@@ -147,3 +147,34 @@ def test_predict_meshes_pipelined_equals_blocking_calls(lib, scan):
         assert len(got) == len(batch) and got[2] is None
         for x, y in zip(blocking, got):
             assert (x is None and y is None) or np.array_equal(x, y)
+
+
+def test_nvjpeg_texture_decoder(lib, scan, tmp_path):
+    """Opt-in GPU texture decode (csrc/jpeg_decode.cu): same image as the host decoder up to decoder arithmetic
+    (mean |diff| of a few LSB on this small, busy texture, < 1 LSB at 1024^2 and above; single pixels on sharp chroma
+    edges differ more: libjpeg-turbo interpolates the
+    sub-sampled chroma planes, nvJPEG replicates them), the pipeline runs from files with it, and the default stays
+    the host decoder."""
+    import mvlm
+
+    a = load_obj(scan)                                   # PIL / libjpeg-turbo
+    b = load_obj(scan, texture_decoder="nvjpeg")
+    assert isinstance(b.texture, torch.Tensor) and b.texture.is_cuda and b.texture_ready is not None
+    b.texture_ready.synchronize()
+    got = b.texture.cpu().numpy().astype(np.int32)
+    ref = a.texture.astype(np.int32)
+    assert got.shape == ref.shape
+    diff = np.abs(got - ref)
+    # a channel swap, a vertical flip or a wrong pitch would give mean differences of tens of LSB
+    assert diff.mean() <= 5.0 and (diff > 32).mean() <= 0.02, (diff.max(), diff.mean(), (diff > 32).mean())
+    assert np.array_equal(a.verts, b.verts) and np.array_equal(a.tris, b.tris)
+    with pytest.raises(ValueError, match="Unknown texture decoder"):
+        load_obj(scan, texture_decoder="nope")
+    sd = seeded_state_dict(73, "RGB+depth", seed=3)
+    dm = mvlm.pipeline.create_pipeline("dtu3d", n_views=8, weights=sd, seed=5, verbose=False, image_size=(64, 64),
+                                       texture_decoder="nvjpeg")
+    one = dm.predict_one_file(scan)
+    many = dm.predict_files([scan, scan, scan])
+    assert one.shape == (73, 3) and np.isfinite(one).all()
+    assert all(np.array_equal(one, m) for m in many)     # deterministic decode, same result through the batch driver
+    assert mvlm.pipeline.create_pipeline("dtu3d", weights=sd, verbose=False, image_size=(64, 64)).texture_decoder == "pil"
