@@ -105,7 +105,7 @@ class PaulsenModel(Predictor2D):
         v, h, w = img.shape[0], img.shape[1], img.shape[2]
         # View batches: the conv kernel indexes its NHWC tensors with 32-bit element offsets (V*H*W*256 < 2^31) and the
         # plan's workspace grows with V (3.2 KB per pixel); larger stacks run as equal slices of the view axis.
-        chunk = self.max_views_per_launch(v, h, w)
+        chunk = v if (v, h, w) in self._nets else self.max_views_per_launch(v, h, w)  # a cached plan fits by construction
         if chunk < v:
             return torch.cat([self.predict_landmarks_device(img[i:i + chunk]).clone() for i in range(0, v, chunk)], dim=1)
         net = self.network(v, h, w)
