@@ -110,5 +110,7 @@ def test_view_axis_slicing_equals_one_launch(lib, monkeypatch):
     whole = dm.predictor_2d.predict_landmarks_device(u8).clone()
     assert dm.predictor_2d.max_views_per_launch(100, 512, 512) == 25      # 2^31 / (512*512*256) = 31 -> divisor 25
     monkeypatch.setattr(PaulsenModel, "max_views_per_launch", lambda self, v, h, w: min(v, 4))
+    dm.predictor_2d._nets.clear()                                          # forget the 12-view plan: slices of 4 now
     sliced = dm.predictor_2d.predict_landmarks_device(u8)
     assert torch.equal(whole, sliced)
+    assert list(dm.predictor_2d._nets) == [(4, 64, 64)]
