@@ -209,3 +209,56 @@ def test_conv_upsampled_residual(lib):
         if with_post:
             post_ref = torch.relu(v2 * s2 + t2)
             assert (out_post[..., 32:32 + cout].float() - post_ref).abs().max().item() <= tol * s2.abs().max().item() + post_ref.abs().max().item() * 2.0 ** -8
+
+
+def test_conv_random_shape_sweep(lib):
+    """Seeded sweep over ragged map sizes / channel counts / kernel sizes and the epilogue combinations the plan uses
+    (both the M = 128 and the M = 64 kernels, stationary and streamed weights): bias + pre + res1 [+ up] + raw + post."""
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    rng = torch.Generator().manual_seed(2024)
+
+    def pick(seq):
+        return seq[int(torch.randint(0, len(seq), (1,), generator=rng))]
+
+    for case in range(28):
+        k = pick([1, 3, 3, 3])
+        cin = pick([16, 32, 64, 80, 96, 128, 256])
+        cout = pick([32, 64, 64, 128, 128, 256])
+        n = pick([1, 2, 3])
+        even = case % 2 == 0                      # res_up needs even H, W
+        h = int(torch.randint(1, 36, (1,), generator=rng)) * (2 if even else 1)
+        w = int(torch.randint(1, 20, (1,), generator=rng)) * (2 if even else 1)
+        with_pre, with_post, with_up = pick([True, False]), pick([True, False]), even and pick([True, False])
+        g = torch.Generator(device="cuda").manual_seed(100 + case)
+        cs_in = max(cin, 64) if cin % 64 else cin
+        x = torch.randn((n, h, w, cs_in), generator=g, device="cuda").to(torch.bfloat16)
+        wt = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+        bias = torch.randn((cout,), generator=g, device="cuda")
+        s1, t1, s2, t2 = (torch.randn((cout,), generator=g, device="cuda") for _ in range(4))
+        res = torch.randn((n, h, w, cout + 32), generator=g, device="cuda").to(torch.bfloat16)
+        low = torch.randn((n, max(h // 2, 1), max(w // 2, 1), cout + 16), generator=g, device="cuda").to(torch.bfloat16)
+        wp = ops.pack_conv_weight(wt, cout, cin)
+        out_pre = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        out_raw = torch.full((n, h, w, cout + 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+        out_post = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.conv2d_bf16(x, wp, cin=cin, n_tile=min(cout, 128), kh=k, kw=k, bias=bias,
+                        pre=(s1, t1, out_pre, 0) if with_pre else None, res1=(res, 32),
+                        res_up=(low, 16) if with_up else None, out_raw=(out_raw, 8),
+                        post=(s2, t2, out_post, 0) if with_post else None)
+        torch.cuda.synchronize()
+        tag = (case, n, h, w, cin, cout, k, with_pre, with_post, with_up)
+        v = _ref_conv(x[..., :cin], wt, bias, k, k, -(k // 2), -(k // 2))
+        tol = 2e-3 * v.abs().max().item()
+        if with_pre:
+            pre_ref = torch.relu(v * s1 + t1)
+            assert (out_pre.float() - pre_ref).abs().max().item() <= tol * s1.abs().max().item() + pre_ref.abs().max().item() * 2.0 ** -8, tag
+        v2 = v + res[..., 32:].float()
+        if with_up:
+            v2 = v2 + F.interpolate(low[..., 16:].float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+        assert (out_raw[..., 8:].float() - v2).abs().max().item() <= tol + v2.abs().max().item() * 2.0 ** -8, tag
+        assert torch.isnan(out_raw[..., :8].float()).all(), tag           # neighbouring channels untouched
+        if with_post:
+            post_ref = torch.relu(v2 * s2 + t2)
+            assert (out_post.float() - post_ref).abs().max().item() <= tol * s2.abs().max().item() + post_ref.abs().max().item() * 2.0 ** -8, tag
