@@ -161,16 +161,13 @@ class Pipeline(abc.ABC, TimeMixin):
 
         snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm)
         result = torch.cat([snapped.reshape(-1), err.sum().reshape(1) / err.numel()])
-        # ring of page-locked result buffers (one pinned allocation per slot for the life of the pipeline)
+        # ring of page-locked result buffers, allocated together on first use (cudaHostAlloc synchronises the device)
         ring = self.__dict__.setdefault("_result_ring", [])
-        if len(ring) < 16 or ring[0].numel() != result.numel():
-            if ring and ring[0].numel() != result.numel():
-                ring.clear()
-            ring.append(torch.empty(result.shape, dtype=result.dtype, pin_memory=True))
-            host = ring[-1]
-        else:
-            self._result_i = (getattr(self, "_result_i", -1) + 1) % len(ring)
-            host = ring[self._result_i]
+        if not ring or ring[0].numel() != result.numel():
+            ring.clear()
+            ring.extend(torch.empty(result.shape, dtype=result.dtype, pin_memory=True) for _ in range(8))
+        self._result_i = (getattr(self, "_result_i", -1) + 1) % len(ring)
+        host = ring[self._result_i]
         host.copy_(result, non_blocking=True)
         done = torch.cuda.Event()
         done.record()
@@ -192,7 +189,7 @@ class Pipeline(abc.ABC, TimeMixin):
         """Batch form of predict_mesh: same results, but up to `depth` scans are in flight -- the copies and launches of
         the next scan are enqueued (one stream, so buffers are reused in order) before the host waits for the landmarks
         of the previous one, which keeps host-side latency off the GPU's critical path.  A None entry yields None."""
-        assert depth < 16, "depth is bounded by the ring of result buffers"
+        assert depth < 8, "depth is bounded by the ring of result buffers"
         results, inflight = [], []
         for mesh in meshes:
             if mesh is None:
