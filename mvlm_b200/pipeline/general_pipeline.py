@@ -64,6 +64,12 @@ class Pipeline(abc.ABC, TimeMixin):
         self.renderer_3d.verbose = verbose
         self.estimator_3d = Estimator3D(n_hypotheses=n_hypotheses, seed=seed, device=device)
         self.estimator_3d.verbose = verbose
+        # One pipeline object = one set of device buffers (renderer images, CNN workspace, CUDA graphs): calls from
+        # several threads (the reference's FastAPI server shares one pipeline across its thread pool without a lock,
+        # 3DMD_server.py:24-31) are serialised here.
+        import threading
+
+        self._lock = threading.RLock()
         self.predictor_2d = None  # assigned by the subclasses
         self.last_error = None    # "Landmarks [Error]" of the last scan (general_pipeline.py:109)
 
@@ -79,64 +85,66 @@ class Pipeline(abc.ABC, TimeMixin):
     # ------------------------------------------------------------------ general_pipeline.py:67-131
     def predict_one_file(self, file_name: Path, landmark_indices: list[int] | None = None,
                          view_indices: list[int] | None = None, clip_rays_to_mesh: bool = True):
-        if self.predictor_2d is None:
-            raise ValueError("Predictor2D is not initialized.")
-        file_name = Path(file_name)
-        full_s = time.time()
-        if not file_name.exists():
-            print(f"File {file_name} does not exist")
-            return None
-        fused = (isinstance(self.predictor_2d, PaulsenModel) and type(self.renderer_3d) is ObjRenderer3D
-                 and type(self.estimator_3d) is Estimator3D and not self.render_image_stack
-                 and self.predictor_2d.selection_method == "simple")
-        if fused:
-            r = self.renderer_3d
-            if not file_name.is_file():
-                raise FileNotFoundError(f"File {file_name} is not a file")
-            if not file_name.suffix == ".obj":
-                raise ValueError(f"File {file_name} is not an .obj file. Only .obj files are supported.")
-            self.tic()
-            mesh = load_obj(file_name, texture_decoder=self.texture_decoder, device=self.device)
-            self._print("Render [1] - Setup time: ", self.toc_p())
-            landmarks = self.predict_mesh(mesh)
-            self._print("Landmarks 3D Total: ", self.p_time(time.time() - full_s))
-            return landmarks
-        return self._predict_seams(file_name, full_s)
+        with self._lock:
+            if self.predictor_2d is None:
+                raise ValueError("Predictor2D is not initialized.")
+            file_name = Path(file_name)
+            full_s = time.time()
+            if not file_name.exists():
+                print(f"File {file_name} does not exist")
+                return None
+            fused = (isinstance(self.predictor_2d, PaulsenModel) and type(self.renderer_3d) is ObjRenderer3D
+                     and type(self.estimator_3d) is Estimator3D and not self.render_image_stack
+                     and self.predictor_2d.selection_method == "simple")
+            if fused:
+                r = self.renderer_3d
+                if not file_name.is_file():
+                    raise FileNotFoundError(f"File {file_name} is not a file")
+                if not file_name.suffix == ".obj":
+                    raise ValueError(f"File {file_name} is not an .obj file. Only .obj files are supported.")
+                self.tic()
+                mesh = load_obj(file_name, texture_decoder=self.texture_decoder, device=self.device)
+                self._print("Render [1] - Setup time: ", self.toc_p())
+                landmarks = self.predict_mesh(mesh)
+                self._print("Landmarks 3D Total: ", self.p_time(time.time() - full_s))
+                return landmarks
+            return self._predict_seams(file_name, full_s)
 
     def predict_files(self, file_names, prefetch: int = 2) -> list:
         """Batch driver (the reference's main.py:50-62 loop is strictly serial): the native loader parses / decodes the
         next `prefetch` scans on background threads (the C parser and the JPEG decoder release the GIL) and the copies
         and launches of scan i+1 are enqueued while the GPU still works on scan i (see predict_meshes).
         Returns one (L,3) array (or None for a missing file) per input, in order."""
-        from concurrent.futures import ThreadPoolExecutor
+        with self._lock:
+            from concurrent.futures import ThreadPoolExecutor
 
-        if self.predictor_2d is None:
-            raise ValueError("Predictor2D is not initialized.")
-        files = [Path(f) for f in file_names]
+            if self.predictor_2d is None:
+                raise ValueError("Predictor2D is not initialized.")
+            files = [Path(f) for f in file_names]
 
-        def load(f: Path):
-            if not f.exists():
-                return None
-            if not f.is_file():
-                raise FileNotFoundError(f"File {f} is not a file")
-            if not f.suffix == ".obj":
-                raise ValueError(f"File {f} is not an .obj file. Only .obj files are supported.")
-            # four parser threads per scan: with more, the loaders of `prefetch` scans oversubscribe the host and the
-            # thread that feeds the GPU gets descheduled (measured on the 16-core box: 36 scans/s with 16, 51 with 4)
-            return load_obj(f, n_threads=4, texture_decoder=self.texture_decoder, device=self.device)
+            def load(f: Path):
+                if not f.exists():
+                    return None
+                if not f.is_file():
+                    raise FileNotFoundError(f"File {f} is not a file")
+                if not f.suffix == ".obj":
+                    raise ValueError(f"File {f} is not an .obj file. Only .obj files are supported.")
+                # four parser threads per scan: with more, the loaders of `prefetch` scans oversubscribe the host and the
+                # thread that feeds the GPU gets descheduled (measured on the 16-core box: 36 scans/s with 16, 51 with 4)
+                return load_obj(f, n_threads=4, texture_decoder=self.texture_decoder, device=self.device)
 
-        def meshes():
-            with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
-                pending = [pool.submit(load, f) for f in files[:prefetch]]
-                for i, f in enumerate(files):
-                    mesh = pending.pop(0).result()
-                    if i + prefetch < len(files):
-                        pending.append(pool.submit(load, files[i + prefetch]))
-                    if mesh is None:
-                        print(f"File {f} does not exist")
-                    yield mesh
+            def meshes():
+                with ThreadPoolExecutor(max_workers=max(1, prefetch)) as pool:
+                    pending = [pool.submit(load, f) for f in files[:prefetch]]
+                    for i, f in enumerate(files):
+                        mesh = pending.pop(0).result()
+                        if i + prefetch < len(files):
+                            pending.append(pool.submit(load, files[i + prefetch]))
+                        if mesh is None:
+                            print(f"File {f} does not exist")
+                        yield mesh
 
-        return self.predict_meshes(meshes())
+            return self.predict_meshes(meshes())
 
     def _enqueue_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None):
         """Enqueues the whole hot path of one scan on the current stream WITHOUT waiting for it: host -> device copies
@@ -182,26 +190,28 @@ class Pipeline(abc.ABC, TimeMixin):
 
     def predict_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None) -> np.ndarray:
         """Fused device path for an already loaded scan (host arrays in, (L,3) float64 out)."""
-        host, done, _keep = self._enqueue_mesh(mesh, transforms)
-        return self._finish(host, done)
+        with self._lock:
+            host, done, _keep = self._enqueue_mesh(mesh, transforms)
+            return self._finish(host, done)
 
     def predict_meshes(self, meshes, depth: int = 2) -> list:
         """Batch form of predict_mesh: same results, but up to `depth` scans are in flight -- the copies and launches of
         the next scan are enqueued (one stream, so buffers are reused in order) before the host waits for the landmarks
         of the previous one, which keeps host-side latency off the GPU's critical path.  A None entry yields None."""
-        assert depth < 8, "depth is bounded by the ring of result buffers"
-        results, inflight = [], []
-        for mesh in meshes:
-            if mesh is None:
-                inflight.append(None)
-            else:
-                inflight.append(self._enqueue_mesh(mesh))
-            while len([x for x in inflight if x is not None]) > depth or (inflight and inflight[0] is None):
-                head = inflight.pop(0)
+        with self._lock:
+            assert depth < 8, "depth is bounded by the ring of result buffers"
+            results, inflight = [], []
+            for mesh in meshes:
+                if mesh is None:
+                    inflight.append(None)
+                else:
+                    inflight.append(self._enqueue_mesh(mesh))
+                while len([x for x in inflight if x is not None]) > depth or (inflight and inflight[0] is None):
+                    head = inflight.pop(0)
+                    results.append(None if head is None else self._finish(head[0], head[1]))
+            for head in inflight:
                 results.append(None if head is None else self._finish(head[0], head[1]))
-        for head in inflight:
-            results.append(None if head is None else self._finish(head[0], head[1]))
-        return results
+            return results
 
     def _predict_seams(self, file_name: Path, full_s: float):
         self.tic()

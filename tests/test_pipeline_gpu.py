@@ -178,3 +178,25 @@ def test_nvjpeg_texture_decoder(lib, scan, tmp_path):
     assert one.shape == (73, 3) and np.isfinite(one).all()
     assert all(np.array_equal(one, m) for m in many)     # deterministic decode, same result through the batch driver
     assert mvlm.pipeline.create_pipeline("dtu3d", weights=sd, verbose=False, image_size=(64, 64)).texture_decoder == "pil"
+
+
+def test_pipeline_is_safe_to_share_between_threads(lib, scan):
+    """One pipeline shared by a thread pool (the reference's FastAPI server does that without a lock,
+    3DMD_server.py:24-31): calls are serialised, every thread gets the landmarks of ITS scan."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import mvlm
+    from mvlm_b200.io_obj import Mesh
+
+    sd = seeded_state_dict(73, "RGB+depth", seed=3)
+    dm = mvlm.pipeline.create_pipeline("dtu3d", n_views=8, weights=sd, seed=5, verbose=False, image_size=(64, 64))
+    meshes = [load_obj(scan)]
+    for seed in (21, 22, 23):
+        v, uv, t = synth.face_mesh(grid=40 + seed, seed=seed)
+        meshes.append(Mesh(verts=v, tris=t, uvs=uv, texture=synth.face_texture(64, seed=seed)))
+    serial = [dm.predict_mesh(m) for m in meshes]
+    jobs = [i % len(meshes) for i in range(24)]
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        got = list(pool.map(lambda i: dm.predict_mesh(meshes[i]), jobs))
+    for i, g in zip(jobs, got):
+        assert np.array_equal(g, serial[i])
