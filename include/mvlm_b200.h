@@ -140,7 +140,7 @@ int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, int
                           size_t workspace_bytes, mvlm_hourglass** out);
 int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                            float* out_heatmaps, float* out_peaks, void* stream);
-/* Same result as mvlm_hourglass_forward; the ~175 launches are captured into a CUDA graph per distinct
+/* Same result as mvlm_hourglass_forward; the ~155 launches are captured into a CUDA graph per distinct
  * (img, out) pointer tuple on first use and replayed afterwards (buffers must stay valid and unchanged). */
 int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                                  float* out_heatmaps, float* out_peaks, void* stream);

@@ -1,6 +1,5 @@
 // Memory-bound glue between convolutions (NHWC bf16, 16-byte vector accesses, 8 channels/thread):
 //   pool2_act  : F.max_pool2d(x, 2)            (+ consumer BN+ReLU copy)   paulsenpredictor.py:309,314,319,324,329,411
-//   upadd_act  : F.interpolate(nearest,x2)+skip (+ consumer BN+ReLU copy)  paulsenpredictor.py:335-359
 //   bn_relu    : F.relu(bn(x)) for a second consumer of a stored tensor     paulsenpredictor.py:263-265
 #include "common.cuh"
 #include "stages.cuh"
@@ -74,34 +73,6 @@ __global__ void __launch_bounds__(256) pool2_act_kernel(const uint4* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) upadd_act_kernel(const uint4* __restrict__ low, const uint4* __restrict__ skip,
-                                                        int n, int h, int w, int c8, uint4* __restrict__ out_raw,
-                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                        uint4* __restrict__ out_act) {
-  const int hl = h >> 1, wl = w >> 1;
-  const size_t total = static_cast<size_t>(n) * h * w * c8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % c8);
-    size_t r = i / c8;
-    const int x = static_cast<int>(r % w);
-    r /= w;
-    const int y = static_cast<int>(r % h);
-    const int img = static_cast<int>(r / h);
-    float a[8], b[8];
-    unpack8(__ldg(low + ((static_cast<size_t>(img) * hl + (y >> 1)) * wl + (x >> 1)) * c8 + cv), a);
-    unpack8(__ldg(skip + i), b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += b[j];
-    if (out_raw) out_raw[i] = pack8(a);
-    if (out_act) {
-      float o[8];
-      act8(a, scale, shift, cv * 8, o);
-      out_act[i] = pack8(o);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) bn_relu_kernel(const uint4* __restrict__ in, size_t total, int c8,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                       uint4* __restrict__ out) {
@@ -128,21 +99,6 @@ int pool2_act(const __nv_bfloat16* in, int n, int h, int w, int c, __nv_bfloat16
   MVLM_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "pool2_act: bad shape %dx%dx%d", h, w, c);
   const size_t total = static_cast<size_t>(n) * (h / 2) * (w / 2) * (c / 8);
   pool2_act_kernel<<<grid_for(total), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), n, h, w, c / 8,
-                                                   reinterpret_cast<uint4*>(out_raw), scale, shift,
-                                                   reinterpret_cast<uint4*>(out_act));
-  count_launch();
-  MVLM_CHECK_CUDA(cudaGetLastError());
-  return MVLM_OK;
-}
-
-int upadd_act(const __nv_bfloat16* low, const __nv_bfloat16* skip, int n, int h, int w, int c,
-              __nv_bfloat16* out_raw, const float* scale, const float* shift, __nv_bfloat16* out_act,
-              cudaStream_t s) {
-  MVLM_REQUIRE(low && skip && (out_raw || out_act), "upadd_act: null pointer");
-  MVLM_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "upadd_act: bad shape %dx%dx%d", h, w, c);
-  const size_t total = static_cast<size_t>(n) * h * w * (c / 8);
-  upadd_act_kernel<<<grid_for(total), 256, 0, s>>>(reinterpret_cast<const uint4*>(low),
-                                                   reinterpret_cast<const uint4*>(skip), n, h, w, c / 8,
                                                    reinterpret_cast<uint4*>(out_raw), scale, shift,
                                                    reinterpret_cast<uint4*>(out_act));
   count_launch();

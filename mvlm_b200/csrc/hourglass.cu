@@ -280,19 +280,6 @@ int HourglassNet::emit_pool(T in, T out_raw, const char* bn_name, T out_act) {
   return MVLM_OK;
 }
 
-int HourglassNet::emit_upadd(T low, T skip, T out_raw, const char* bn_name, T out_act) {
-  NetOp op;
-  op.kind = NetOp::UPADD;
-  op.in0 = low.p; op.in1 = skip.p; op.out_raw = out_raw.p; op.out_act = out_act.p;
-  op.h = skip.h; op.w = skip.w; op.c = skip.c;
-  if (bn_name) {
-    int rc = bn(bn_name, skip.c, &op.scale, &op.shift);
-    if (rc) return rc;
-  }
-  ops_.push_back(op);
-  return MVLM_OK;
-}
-
 int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
   // HourGlassModule.forward (:301-361).  The skip-branch blocks (rb1, rb3, rb5, rb7, rb9) are scheduled on the way
   // UP, after the low path of their level has returned, so that `F.interpolate(low, 2) + skip` (:334-359) is one
@@ -524,8 +511,6 @@ int HourglassNet::run_op(NetOp& op, const unsigned char* img_u8, const float* im
       return conv_launch(op.conv, stream);
     case NetOp::POOL:
       return pool2_act(op.in0, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
-    case NetOp::UPADD:
-      return upadd_act(op.in0, op.in1, V_, op.h, op.w, op.c, op.out_raw, op.scale, op.shift, op.out_act, stream);
     case NetOp::BNRELU:
       return bn_relu(op.in0, static_cast<size_t>(V_) * op.h * op.w, op.c, op.scale, op.shift, op.out_act, stream);
     case NetOp::MEMSET:
@@ -618,7 +603,6 @@ std::string HourglassNet::describe_op(int i) const {
       break;
     }
     case NetOp::POOL: snprintf(buf, sizeof(buf), "pool %dx%dx%d", op.h, op.w, op.c); break;
-    case NetOp::UPADD: snprintf(buf, sizeof(buf), "upadd %dx%dx%d%s", op.h, op.w, op.c, op.out_act ? " act" : ""); break;
     case NetOp::BNRELU: snprintf(buf, sizeof(buf), "bnrelu %dx%dx%d", op.h, op.w, op.c); break;
     case NetOp::STEM: snprintf(buf, sizeof(buf), "stem-stage %dx%dx%d", op.h, op.w, op.c); break;
     case NetOp::MEMSET: snprintf(buf, sizeof(buf), "memset %zu", op.bytes); break;

@@ -10,7 +10,7 @@
 namespace mvlm {
 
 struct NetOp {
-  enum Kind { CONV, POOL, UPADD, BNRELU, STEM, MEMSET, PEAKS } kind;  // STEM = image -> hi/lo bf16 staging
+  enum Kind { CONV, POOL, BNRELU, STEM, MEMSET, PEAKS } kind;  // STEM = image -> hi/lo bf16 staging
   ConvParams conv;  // CONV
   // eltwise / memset
   const __nv_bfloat16* in0 = nullptr;
@@ -38,7 +38,7 @@ class HourglassNet {
   int run_op(NetOp& op, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
              cudaStream_t stream);
   // Captures the launch sequence of forward() into a CUDA graph per distinct argument tuple and replays it
-  // (the plan is static: ~175 launches per call).  Falls back to plain launches if capture is unavailable.
+  // (the plan is static: ~155 launches per call).  Falls back to plain launches if capture is unavailable.
   int forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
                     cudaStream_t stream);
 
@@ -47,7 +47,7 @@ class HourglassNet {
   // trace_out (optional, kConvTraceTiles x 8 int64): per-tile timeline of CTA 0 of conv op `trace_op`.
   int profile_ops(const unsigned char* img_u8, const float* img_f32, float* out_peaks, int reps, float* ms_out,
                   double* roles_out, int trace_op, long long* trace_out, cudaStream_t stream);
-  // one-line description of op i ("conv rb.conv 128x128 256->128 k3 F=0x1b", "upadd 64x64x256", ...)
+  // one-line description of op i ("conv rb.conv 128x128 256->128 k3 pre res1 raw", "pool 64x64x256", ...)
   std::string describe_op(int i) const;
 
   size_t workspace_needed() const { return ws_off_; }
@@ -80,7 +80,6 @@ class HourglassNet {
          T* pool_raw = nullptr, const T* up_low = nullptr);
   int hourglass(const std::string& p, T x, T a_x, T* out);
   int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
-  int emit_upadd(T low, T skip, T out_raw, const char* bn_name, T out_act);
 
   const std::map<std::string, const float*>* sd_ = nullptr;
   bool dry_ = true;

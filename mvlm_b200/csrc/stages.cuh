@@ -64,9 +64,6 @@ int snap_launch(const float* verts, const int* tris, int nt, const double* lm, i
 // out_raw/out_act may be null; scale/shift are fp32[c] (folded BN) used only when out_act != null
 int pool2_act(const __nv_bfloat16* in, int n, int h, int w, int c, __nv_bfloat16* out_raw,
               const float* scale, const float* shift, __nv_bfloat16* out_act, cudaStream_t s);
-int upadd_act(const __nv_bfloat16* low, const __nv_bfloat16* skip, int n, int h, int w, int c,
-              __nv_bfloat16* out_raw, const float* scale, const float* shift, __nv_bfloat16* out_act,
-              cudaStream_t s);
 int bn_relu(const __nv_bfloat16* in, size_t npix, int c, const float* scale, const float* shift,
             __nv_bfloat16* out_act, cudaStream_t s);
 
