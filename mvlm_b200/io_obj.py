@@ -28,9 +28,23 @@ class Mesh:
         return float(np.linalg.norm(self.verts.max(0) - self.verts.min(0)))
 
 
-def _load_texture(path: Path):
+def _texture_file(path: Path):
+    """`<stem>.jpg` next to the scan (utils3d.py:26); FLAME models (`flame*.obj`) use `mean_texture.jpg` of their folder
+    instead (utils3d.py:39-51).  Returns None when there is no texture file."""
+    if path.name.startswith("flame"):
+        print("Loading flame texture")
+        jpg = path.parent / "mean_texture.jpg"
+        if not jpg.exists():
+            print("Could not load flame texture", jpg)
+            return None
+        return jpg
     jpg = path.with_suffix(".jpg")
-    if not jpg.exists():
+    return jpg if jpg.exists() else None
+
+
+def _load_texture(path: Path):
+    jpg = _texture_file(path)
+    if jpg is None:
         return None
     try:
         from PIL import Image
@@ -55,8 +69,8 @@ def _decode_texture_nvjpeg(path: Path, device):
     global _tls
     if _tls is None:
         _tls = threading.local()
-    jpg = path.with_suffix(".jpg")
-    if not jpg.exists():
+    jpg = _texture_file(path)
+    if jpg is None:
         return None, None
     data = jpg.read_bytes()
     lib = _lib.load()

@@ -91,6 +91,14 @@ def test_obj_roundtrip_and_vertex_duplication(tmp_path):
     (tmp_path / "d.obj").write_text("# empty\n")
     with pytest.raises(ValueError, match="does not contain any points"):
         load_obj(tmp_path / "d.obj")
+    # FLAME models take `mean_texture.jpg` of their folder instead of `<stem>.jpg` (utils3d.py:39-51)
+    from PIL import Image
+
+    synth.write_obj(tmp_path / "flame_head.obj", v, uv, t, synth.face_texture(32, 0))
+    Image.fromarray(synth.face_texture(16, 5)).save(tmp_path / "mean_texture.jpg")
+    assert load_obj(tmp_path / "flame_head.obj").texture.shape == (16, 16, 3)
+    (tmp_path / "mean_texture.jpg").unlink()
+    assert load_obj(tmp_path / "flame_head.obj").texture is None
 
 
 def test_native_obj_loader_matches_python_restatement(tmp_path):
