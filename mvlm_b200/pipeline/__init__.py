@@ -10,9 +10,13 @@ from .paulsen_pipeline import BU3DFEPipeline, DTU3DPipeline
 def create_pipeline(name: str, **kwargs):
     name = name.lower()
     if name == "bu3dfe":
-        return BU3DFEPipeline(**kwargs)
+        p = BU3DFEPipeline(**kwargs)
+        p.name = name
+        return p
     elif name == "dtu3d":
-        return DTU3DPipeline(**kwargs)
+        p = DTU3DPipeline(**kwargs)
+        p.name = name
+        return p
     elif name in ("mediapipe", "dlib", "face_alignment"):
         raise ValueError(f"Unknown pipeline: {name} (third-party predictor pipelines are not part of mvlm_b200)")
     else:

@@ -146,6 +146,31 @@ class Pipeline(abc.ABC, TimeMixin):
 
             return self.predict_meshes(meshes())
 
+    def predict_folder(self, path, out=None) -> dict:
+        """The reference's batch loop (main.py:23-62) for this pipeline: every `*.obj` of a folder (sorted), or one
+        file; landmarks are written as `<out>/<stem>_<pipeline name>.txt` with `np.savetxt(..., delimiter=",")`, files
+        whose landmarks could not be predicted are skipped.  Returns {file: landmarks | None}."""
+        path = Path(path)
+        if not path.exists():
+            raise FileNotFoundError(f"{path.as_posix()} does not exist.")
+        if path.is_file():
+            if path.suffix.lower() != ".obj":
+                raise ValueError(f"{path.as_posix()} is not an .obj file.")
+            files, out_dir = [path], Path(out) if out is not None else path.parent
+        else:
+            files, out_dir = sorted(path.glob("*.obj")), Path(out) if out is not None else path
+            if len(files) == 0:
+                raise ValueError("Given folder does not contain any .obj files.")
+        out_dir.mkdir(parents=True, exist_ok=True)
+        pname = getattr(self, "name", type(self).__name__.lower())
+        results = dict(zip(files, self.predict_files(files)))
+        for f, lm in results.items():
+            if lm is None:
+                print(f"Landmarks for {f} could not be predicted -> skipping file [{f.stem}] for pipeline {pname}")
+                continue
+            np.savetxt((out_dir / f"{f.stem}_{pname}.txt").as_posix(), lm, delimiter=",")
+        return results
+
     def _enqueue_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None):
         """Enqueues the whole hot path of one scan on the current stream WITHOUT waiting for it: host -> device copies
         of the scan, raster, CNN, rays, consensus, snap, device -> pinned-host copy of the (L*3 + 1) result.

@@ -200,3 +200,27 @@ def test_pipeline_is_safe_to_share_between_threads(lib, scan):
         got = list(pool.map(lambda i: dm.predict_mesh(meshes[i]), jobs))
     for i, g in zip(jobs, got):
         assert np.array_equal(g, serial[i])
+
+
+def test_predict_folder_writes_reference_txt_files(lib, scan, tmp_path):
+    """Batch loop of the reference's main.py:50-62: `<stem>_<pipeline>.txt` written with np.savetxt(delimiter=",")."""
+    import shutil
+
+    import mvlm
+
+    src = tmp_path / "in"
+    src.mkdir()
+    for name in ("b_face", "a_face"):
+        shutil.copy(scan, src / f"{name}.obj")
+        shutil.copy(scan.with_suffix(".jpg"), src / f"{name}.jpg")
+    sd = seeded_state_dict(84, "RGB+depth", seed=3)
+    dm = mvlm.pipeline.create_pipeline("BU3DFE", n_views=8, weights=sd, seed=5, verbose=False, image_size=(64, 64))
+    res = dm.predict_folder(src, tmp_path / "out")
+    assert [f.name for f in res] == ["a_face.obj", "b_face.obj"]
+    for f, lm in res.items():
+        txt = tmp_path / "out" / f"{f.stem}_bu3dfe.txt"
+        assert txt.exists()
+        back = np.loadtxt(txt, delimiter=",")
+        assert back.shape == (84, 3) and np.array_equal(back, lm)      # %.18e round-trips float64 exactly
+    with pytest.raises(ValueError, match="does not contain any .obj"):
+        dm.predict_folder(tmp_path / "out")
