@@ -103,3 +103,38 @@ def make_model(n_landmarks: int, image_channels: str, state_dict: dict):
     m.load_state_dict(state_dict, strict=True)
     m.eval()
     return m
+
+
+def load_renderer_class():
+    """The reference's ObjVTKRenderer3D (utils/render3d.py) with `vtk` replaced by a permissive mock: its constructor
+    only configures VTK objects, and the view-list generators `random_transform` / `generate_3d_transformations`
+    (:79-112) are plain numpy -- those are what tools/make_golden.py runs verbatim.  The VTK render path itself
+    cannot be executed here."""
+    from unittest import mock
+
+    if not available():
+        raise RuntimeError("reference tree not present")
+    names = ("vtk", "vtk.util", "vtk.util.numpy_support", "mvlm", "mvlm.utils", "mvlm.utils.utils3d")
+    saved = {k: sys.modules.get(k) for k in names}
+    vtk = mock.MagicMock(name="vtk")
+    sys.modules.update({"vtk": vtk, "vtk.util": vtk.util, "vtk.util.numpy_support": vtk.util.numpy_support})
+    pk = types.ModuleType("mvlm")
+    pk.__path__ = [str(REF_SRC / "mvlm")]
+    pu = types.ModuleType("mvlm.utils")
+    pu.__path__ = [str(REF_SRC / "mvlm" / "utils")]
+    sys.modules.update({"mvlm": pk, "mvlm.utils": pu})
+    try:
+        for modname, rel in (("mvlm.utils.utils3d", "utils/utils3d.py"), ("mvlm.utils.render3d", "utils/render3d.py")):
+            spec = importlib.util.spec_from_file_location(modname, REF_SRC / "mvlm" / rel)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[modname] = mod
+            spec.loader.exec_module(mod)
+        cls = sys.modules["mvlm.utils.render3d"].ObjVTKRenderer3D
+    finally:
+        for k in list(sys.modules):
+            if k == "mvlm" or k.startswith("mvlm.") or k in ("vtk", "vtk.util", "vtk.util.numpy_support"):
+                del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    return cls

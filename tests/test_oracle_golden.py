@@ -143,3 +143,22 @@ def test_snap_oracle_properties():
     assert (d <= dv + 1e-9).all()             # at least as close as the closest vertex
     out2, _ = native.snap_to_mesh(verts, tris, out)
     assert np.abs(out2 - out).max() <= 1e-9   # idempotent
+
+
+def test_view_lists_match_reference_renderer():
+    """R1 (render3d.py:79-112): the fixed 8-view preset and the random view lists drawn from the GLOBAL numpy RNG, pinned
+    against the reference's ObjVTKRenderer3D executed verbatim (tests/golden/views.npz, tools/make_golden.py)."""
+    from mvlm_b200.utils.render3d import ObjRenderer3D
+
+    g = np.load(GOLD / "views.npz")
+    r8 = ObjRenderer3D(n_views=8, device="cpu")
+    got = r8.generate_3d_transformations()
+    assert got.dtype == g["views_8"].dtype and np.array_equal(got, g["views_8"])
+    for key in ("views_5_seed4", "views_100_seed1234", "views_200_seed77"):
+        n, seed = int(key.split("_")[1]), int(key.split("seed")[1])
+        np.random.seed(seed)
+        got = ObjRenderer3D(n_views=n, device="cpu").generate_3d_transformations()
+        assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+        assert np.array_equal(synth.random_view_transforms(n, seed=seed), g[key]), key   # what bench.py / the tests inject
+    np.random.seed(11)
+    assert np.array_equal(ObjRenderer3D(n_views=3, device="cpu").random_transform(3), g["random_transform_3_seed11"])

@@ -126,6 +126,22 @@ def stages_golden():
     print("stages:", sorted(res))
 
 
+def views_golden():
+    """View lists of the reference renderer (render3d.py:79-112), global numpy RNG seeded: the 8-view preset and the
+    random lists the pipelines draw for any other n_views."""
+    cls = ref_loader.load_renderer_class()
+    res = {}
+    r8 = cls(n_views=8)
+    res["views_8"] = np.asarray(r8.generate_3d_transformations())
+    for n, seed in ((5, 4), (100, 1234), (200, 77)):
+        np.random.seed(seed)
+        res[f"views_{n}_seed{seed}"] = np.asarray(cls(n_views=n).generate_3d_transformations())
+    np.random.seed(11)
+    res["random_transform_3_seed11"] = np.asarray(cls(n_views=3).random_transform(3))
+    np.savez_compressed(OUT / "views.npz", **res)
+    print("views:", {k: (v.shape, str(v.dtype)) for k, v in res.items()})
+
+
 def main():
     if not ref_loader.available():
         raise SystemExit("reference tree not present: goldens can only be regenerated in the build container")
@@ -133,6 +149,7 @@ def main():
     cnn_golden("dtu3d_rgbd_64", 73, "RGB+depth", 64, 1234)
     cnn_golden("bu3dfe_geod_64", 84, "geometry+depth", 64, 99)
     stages_golden()
+    views_golden()
 
 
 if __name__ == "__main__":
