@@ -234,8 +234,9 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
   }
   if (pool_raw) *pool_raw = alloc(h / 2, w / 2, cout);
   const int c1 = cout / 2, c2 = cout / 4;
-  T a1 = scratch(h, w, c1 < 64 ? 64 : c1, 1);
-  T a2 = scratch(h, w, c2 < 64 ? 64 : c2, 2);
+  // tightly packed intermediates (a 32-channel a2 in a 64-channel-stride buffer doubles its DRAM traffic)
+  T a1 = scratch(h, w, c1, 1);
+  T a2 = scratch(h, w, c2, 2);
   const int widths[3] = {c1, c2, c2};
   const int offs[3] = {0, c1, c1 + c2};
   const int cins[3] = {cin, c1, c2};
