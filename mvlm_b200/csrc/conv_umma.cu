@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     constexpr int kCols = M64 ? 32 : 16;       // accumulator columns per unit
     constexpr int kUnitRows = kCols / 8;       // image rows per unit
     constexpr int kPassStep = M64 ? 2 : 1;     // image rows between my pixel in pass 0 and in pass 1
+    constexpr bool kFrag = M64 && (F & F_HEAD) == 0;  // M = 64 accumulators read with the 16x256b shape
     static_assert(kCols * kPitch <= kStageFloats, "transpose buffer");
     const int ew = warp - 2;
     const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
@@ -504,9 +505,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                                static_cast<uint32_t>(acc * 256 + u_begin * kCols);
         // one register buffer: the load of unit r+1 is issued as soon as unit r has left the registers
-        uint32_t vr[kCols];
+        // M = 64 without channel-major consumers: the 16 data lanes of the lane group are read with the 16x256b shape,
+        // which spreads them over all 32 threads (2 channels x 16 pixels each): half the registers and, above all,
+        // full 32-lane transpose stores -- the shared-memory pipe is what bounds these layers
+        uint32_t vr[kFrag ? 16 : kCols];
         auto tmem_load = [&](int u) {
-          if constexpr (M64) ptx::tmem_ld32(taddr + u * kCols, vr);
+          if constexpr (kFrag) ptx::tmem_ld_16x256b_x4(taddr + u * kCols, vr);
+          else if constexpr (M64) ptx::tmem_ld32(taddr + u * kCols, vr);
           else ptx::tmem_ld16(taddr + u * kCols, vr);
         };
         tmem_load(0);
@@ -555,7 +560,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 // bias in the channel-major role (one register), then transpose the unit through shared memory:
                 // row = pixel, 36 (20)-float pitch (conflict-free STS.32; LDS.128 conflict-free at 36)
                 __syncwarp();
-                if (cm_lane) {
+                if constexpr (kFrag) {
+                  // register 4k + 2h + e = (channel lane/4 + 8h, pixel 8k + 2(lane%4) + e); conflict-free at pitch 20
+                  const int cb = m0 + cgrp * kChGrp + (lane >> 2);
+                  const int p0 = 2 * (lane & 3);
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const int ch = (cb + 8 * h) < kMaxCout ? cb + 8 * h : 0;
+                    const float bias_h = ep->bias[ch];
+                    const float ms = (F & F_MID) ? ep->mid_s[ch] : 1.f, mt_ = (F & F_MID) ? ep->mid_t[ch] : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                      for (int e2 = 0; e2 < 2; ++e2) {
+                        float f = __uint_as_float(vr[4 * k + 2 * h + e2]) + bias_h;
+                        if (F & F_MID) f = fmaxf(fmaf(f, ms, mt_), 0.f);
+                        stage[(8 * k + p0 + e2) * kPitch + (lane >> 2) + 8 * h] = f;
+                      }
+                    }
+                  }
+                } else if (cm_lane) {
 #pragma unroll
                   for (int j = 0; j < kCols; ++j) {
                     float f = __uint_as_float(vr[j]) + bias_c;

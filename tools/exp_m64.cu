@@ -11,6 +11,7 @@ using namespace mvlm;
 struct Args {
   CUtensorMap tm_a, tm_x;
   float* out;  // [128][256]
+  float* frag; // [32 threads][16 regs]: tcgen05.ld.16x256b.x4 of lanes 0..15, columns 64..95, by warp 0
   long long* cycles;
   int m, n_mma;
 };
@@ -63,6 +64,18 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ Args a) {
     ptx::tmem_ld_wait();
     for (int j = 0; j < 16; ++j) a.out[(warp * 32 + lane) * 256 + c + j] = __uint_as_float(v[j]);
   }
+  if (warp == 0) {
+    uint32_t f[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(f[0]), "=r"(f[1]), "=r"(f[2]), "=r"(f[3]), "=r"(f[4]), "=r"(f[5]), "=r"(f[6]), "=r"(f[7]), "=r"(f[8]),
+          "=r"(f[9]), "=r"(f[10]), "=r"(f[11]), "=r"(f[12]), "=r"(f[13]), "=r"(f[14]), "=r"(f[15])
+        : "r"(tmem + 64)
+        : "memory");
+    ptx::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) a.frag[lane * 16 + j] = __uint_as_float(f[j]);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -88,9 +101,9 @@ int main() {
   // A[m][k] = (m + 1) if k == 0 else 0 ; X[n][k] = 1 if k == 0 -> D[m][n] = m + 1 for every n (one K=16 step, kk = 0)
   std::vector<__nv_bfloat16> hA(128 * 64), hX(256 * 64);
   for (int m = 0; m < 128; ++m)
-    for (int kk = 0; kk < 64; ++kk) hA[m * 64 + kk] = __float2bfloat16(kk == 0 ? float(m + 1) : 0.f);
+    for (int kk = 0; kk < 64; ++kk) hA[m * 64 + kk] = __float2bfloat16(kk == 0 ? float(m + 1) : (kk == 1 ? 1.f / 256.f : 0.f));
   for (int n = 0; n < 256; ++n)
-    for (int kk = 0; kk < 64; ++kk) hX[n * 64 + kk] = __float2bfloat16(kk == 0 ? 1.f : 0.f);
+    for (int kk = 0; kk < 64; ++kk) hX[n * 64 + kk] = __float2bfloat16(kk == 0 ? 1.f : (kk == 1 ? float(n) : 0.f));
   __nv_bfloat16 *dA, *dX;
   float* dOut;
   long long* dCyc;
@@ -98,6 +111,8 @@ int main() {
   cudaMalloc(&dX, hX.size() * 2);
   cudaMalloc(&dOut, 128 * 256 * 4);
   cudaMalloc(&dCyc, 8);
+  float* dFrag;
+  cudaMalloc(&dFrag, 32 * 16 * 4);
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice);
   Args a;
@@ -115,6 +130,7 @@ int main() {
       return 4;
   }
   a.out = dOut;
+  a.frag = dFrag;
   a.cycles = dCyc;
   const int smem = 16384 + 32768 + 2048;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -130,6 +146,20 @@ int main() {
     for (int l = 0; l < 128; ++l) printf(" %g", h[l * 256]);
     printf("\n  column 200 of lanes 0..3, 16..19: %g %g %g %g | %g %g %g %g\n", h[200], h[256 + 200], h[512 + 200], h[768 + 200],
            h[16 * 256 + 200], h[17 * 256 + 200], h[18 * 256 + 200], h[19 * 256 + 200]);
+    {
+      std::vector<float> fr(32 * 16);
+      cudaMemcpy(fr.data(), dFrag, fr.size() * 4, cudaMemcpyDeviceToHost);
+      printf("  16x256b.x4 fragment of warp 0 at column 64 (value = row+1 + col/256 -> (row, col)):\n");
+      for (int t : {0, 1, 2, 3, 4, 5, 31}) {
+        printf("    thread %2d:", t);
+        for (int j = 0; j < 16; ++j) {
+          const float v = fr[t * 16 + j];
+          const int row = static_cast<int>(v) - 1, col = static_cast<int>((v - static_cast<int>(v)) * 256.f + 0.5f);
+          printf(" r%d=(%d,%d)", j, row, col);
+        }
+        printf("\n");
+      }
+    }
     for (int n_mma : {64, 512}) {
       a.n_mma = n_mma;
       long long best = 1ll << 60;
