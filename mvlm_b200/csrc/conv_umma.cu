@@ -77,8 +77,9 @@ constexpr int kSmemBytes = kPoolBytes + kEpiWarps * kStageFloats * 4 + 512 + sta
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t order_f32(float f) {
-  uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  const uint32_t b = __float_as_uint(f);
+  // negative: ~b, else b | 0x80000000  ==  b ^ (sign-extended sign | 0x80000000)
+  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
@@ -534,17 +535,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                       const int oy = (y + i) * e.up_sy + e.up_py;
                       const uint32_t idx0 = static_cast<uint32_t>(oy * ow + x0 * e.up_sx + e.up_px);
                       if (F & F_ARGMAX) {
-                        unsigned long long best = (static_cast<unsigned long long>(best_hi) << 32) | best_lo;
-                        uint32_t lo = 0xFFFFFFFFu - idx0;
+                        // first maximum of the row's 8 pixels by a tournament over ordered keys (pixel index grows
+                        // with j, so "the later one only if strictly greater" keeps the first), then ONE merge with
+                        // the running best: a serial compare-select chain per pixel made this epilogue latency-bound
+                        uint32_t k8[8];
+                        uint32_t j8[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                          const unsigned long long key =
-                              (static_cast<unsigned long long>(order_f32(__uint_as_float(vr[8 * i + j]) + bias_c)) << 32) | lo;
-                          if (j < nvx && key > best) best = key;
-                          lo -= static_cast<uint32_t>(e.up_sx);
+                          k8[j] = j < nvx ? order_f32(__uint_as_float(vr[8 * i + j]) + bias_c) : 0u;
+                          j8[j] = static_cast<uint32_t>(j);
                         }
-                        best_hi = static_cast<uint32_t>(best >> 32);
-                        best_lo = static_cast<uint32_t>(best);
+#pragma unroll
+                        for (int st = 1; st < 8; st *= 2) {
+#pragma unroll
+                          for (int j = 0; j < 8; j += 2 * st) {
+                            const bool take = k8[j + st] > k8[j];
+                            k8[j] = take ? k8[j + st] : k8[j];
+                            j8[j] = take ? j8[j + st] : j8[j];
+                          }
+                        }
+                        const uint32_t lo = 0xFFFFFFFFu - (idx0 + j8[0] * static_cast<uint32_t>(e.up_sx));
+                        if (k8[0] > best_hi || (k8[0] == best_hi && lo > best_lo)) {
+                          best_hi = k8[0];
+                          best_lo = lo;
+                        }
                       }
                       if (F & F_F32) {
                         float* dst = e.out_f32 + (static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh * ow + idx0;

@@ -20,6 +20,8 @@ constexpr int kRows = 34, kPx = 10;
 struct Args {
   CUtensorMap tm_a, tm_x;
   float* out;  // [128][256]
+  long long* cyc;
+  int reps;
   int kx, ky, base_mode, n, ch;  // ch = 64 | 32 | 16 channels per pixel row (SWIZZLE_128B | 64B | 32B)
 };
 
@@ -58,17 +60,41 @@ __global__ void __launch_bounds__(128, 1) exp_kernel(const __grid_constant__ Arg
         : "memory");
     ptx::mbar_wait(&bar_full, 0);
     ptx::tc_fence_after();
+    if (a.reps < 0) {  // TMA timing: the halo box again and again (L2 hits), one at a time / four in flight
+      uint32_t par = 1;
+      const long long t0 = clock64();
+      for (int r = 0; r < -a.reps; ++r) {
+        ptx::mbar_expect_tx(&bar_full, kRows * kPx * rb);
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            :
+            : "r"(ptx::smem_u32(sX)), "l"(reinterpret_cast<uint64_t>(&a.tm_x)), "r"(ptx::smem_u32(&bar_full)), "r"(0),
+              "r"(0), "r"(0)
+            : "memory");
+        ptx::mbar_wait(&bar_full, par);
+        par ^= 1;
+      }
+      a.cyc[0] = clock64() - t0;
+      ptx::umma_commit(&bar_done);
+    } else {
     const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n);
     const uint32_t xa = ptx::smem_u32(sX) + static_cast<uint32_t>(a.ky * kPx + a.kx) * rb;
     const uint64_t base_off = a.base_mode == 1 ? ((xa >> 7) & 7u) : 0u;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < a.reps; ++rep)
     for (int k = 0; k < a.ch / 16; ++k) {
       const uint64_t da = static_cast<uint64_t>(((ptx::smem_u32(sA) + k * 32) >> 4) & 0x3FFF) | (1ull << 16) |
                           (static_cast<uint64_t>((8 * rb) >> 4) << 32) | (1ull << 46) | (layout << 61);
       const uint64_t db = static_cast<uint64_t>(((xa + k * 32) >> 4) & 0x3FFF) | (1ull << 16) |
                           (static_cast<uint64_t>((kPx * rb) >> 4) << 32) | (1ull << 46) | (base_off << 49) | (layout << 61);
-      ptx::umma_bf16(tmem, da, db, idesc, k > 0 ? 1u : 0u);
+      ptx::umma_bf16(tmem, da, db, idesc, (k > 0 || rep > 0) ? 1u : 0u);
     }
     ptx::umma_commit(&bar_done);
+    if (a.reps > 1) {
+      ptx::mbar_wait(&bar_done, 0);
+      a.cyc[0] = clock64() - t0;
+    }
+    }
   }
   __syncwarp();
   ptx::mbar_wait(&bar_done, 0);
@@ -139,6 +165,10 @@ int main() {
     }
     a.out = dOut;
     a.ch = ch;
+    a.reps = 1;
+    long long* dCyc;
+    cudaMalloc(&dCyc, 8);
+    a.cyc = dCyc;
     const int smem = 16384 + kRows * kPx * 128 + 2048;
     cudaFuncSetAttribute(exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<float> h(128 * 256);
@@ -175,6 +205,25 @@ int main() {
           }
           printf(")\n");
         }
+    // timing: 64 / (ch/16) repetitions = 64 MMAs back to back per variant, tap (1,1) and tap (0,0)
+    for (int tap = 0; tap < 2; ++tap) {
+      a.kx = tap; a.ky = tap; a.base_mode = 0; a.n = 256; a.reps = 256 / (ch / 16);
+      exp_kernel<<<1, 128, smem>>>(a);
+      cudaDeviceSynchronize();
+      long long c = 0;
+      cudaMemcpy(&c, dCyc, 8, cudaMemcpyDeviceToHost);
+      printf("ch=%d (row %d B) N=256 tap(%d,%d): %.1f cycles per MMA (256 MMAs)\n", ch, ch * 2, tap, tap, double(c) / 256.0);
+    }
+    a.reps = -64;
+    exp_kernel<<<1, 128, smem>>>(a);
+    cudaDeviceSynchronize();
+    {
+      long long c = 0;
+      cudaMemcpy(&c, dCyc, 8, cudaMemcpyDeviceToHost);
+      printf("ch=%d: TMA box (%d ch x 10 px x 34 rows = %d B, %d-byte rows), one at a time, L2-hot: %.0f cycles per load\n", ch, ch,
+             340 * ch * 2, ch * 2, double(c) / 64.0);
+    }
+    a.reps = 1;
     cudaFree(dA); cudaFree(dX); cudaFree(dOut);
   }
   printf("%d of %d variants exact\n", all_ok, total);
