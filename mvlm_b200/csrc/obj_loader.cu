@@ -5,7 +5,7 @@
 // polygons fan-triangulated).  Like vtkOBJReader, a position referenced with different `vt` indices is
 // duplicated so that every output vertex has exactly one (position, uv) pair; output vertices are the
 // unique (position index, uv index) pairs in ascending order, i.e. the same arrays, bit for bit, as the
-// Python loader mvlm_b200/io_obj.py::load_obj (the checker in tests/test_host_cpu.py).
+// numpy restatement oracle/obj_ref.py::load_obj_python (the checker in tests/test_host_cpu.py).
 //
 // At ~50 scans/s on the GPU the text parse is the bottleneck of predict_one_file(path) (6 MB of text per
 // scan; 1.05 s in numpy): the file is split at line boundaries into one chunk per thread, every chunk is

@@ -105,7 +105,7 @@ def test_native_obj_loader_matches_python_restatement(tmp_path):
     """csrc/obj_loader.cu (multi-threaded C++ parse behind the C-ABI) == the numpy restatement, bit for bit:
     index forms a, a/b, a/b/c, a//c, negative (relative) indices between interleaved v / f blocks, polygons,
     CRLF line ends, '+' signs and exponents, vertices shared by several vt, unreferenced positions."""
-    from mvlm_b200.io_obj import load_obj_python
+    from oracle.obj_ref import load_obj_python
 
     rng = np.random.RandomState(7)
     cases = {
