@@ -18,7 +18,7 @@ for cin, cout, nt in ((256, 128, 128),):
     w = torch.randn((cout, cin, 3, 3), device="cuda") / 48
     wp = ops.pack_conv_weight(w, cout, cin)
     out = torch.zeros((v, h, h, cout), device="cuda", dtype=torch.bfloat16)
-    for mode in (0, 1):
+    for mode in (0, 1, 0, 1):
         buf = torch.zeros((148 + 128, 8), dtype=torch.int64, device="cuda")  # role counters + CTA-0 tile timeline
         lib.mvlm_debug_conv_mode(mode)
         lib.mvlm_debug_conv_profile(buf.data_ptr())
@@ -28,5 +28,5 @@ for cin, cout, nt in ((256, 128, 128),):
         lib.mvlm_debug_conv_mode(0)
         b = buf[:148].double().mean(0).cpu().numpy()
         n_mma = v * (h // 16) ** 2 / 148 * (cin // 64) * 9 * 4
-        print(f"N={nt:3d} mode={mode}: mma total {b[4] / 1e3:8.1f} kcyc, wait operands {b[2] / 1e3:8.1f}, wait acc {b[3] / 1e3:7.1f} "
-              f"-> {(b[4] - b[2] - b[3]) / n_mma:6.1f} cyc per MMA issued (floor {nt / 2:.0f})")
+        print(f"{cin}->{cout}@{h}^2 mode={mode}: mma total {b[4] / 1e3:8.1f} kcyc, wait operands {b[2] / 1e3:8.1f}, wait acc {b[3] / 1e3:7.1f} "
+              f"-> {b[4] / n_mma:6.1f} cycles per MMA over the whole run, {(b[4] - b[2] - b[3]) / n_mma:6.1f} without the timed waits (floor 128)")
