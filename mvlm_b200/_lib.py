@@ -93,6 +93,10 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_consensus": ([vp, vp, vp, i32, i32, i32, f64, f32, vp, i32, f64, vp, C.c_size_t, vp, vp, vp, vp], i32),
         "mvlm_snap_workspace_bytes": ([i32, i32], C.c_size_t),
         "mvlm_snap_to_mesh": ([vp, vp, i32, vp, i32, vp, C.c_size_t, vp, vp, vp], i32),
+        "mvlm_snap_grid_bytes": ([i32], C.c_size_t),
+        "mvlm_snap_grid_build": ([vp, vp, i32, vp, C.c_size_t, vp], i32),
+        "mvlm_snap_grid_query": ([vp, vp, i32, vp, C.c_size_t, vp, i32, vp, vp, vp, vp], i32),
+        "mvlm_debug_snap_grid_describe": ([vp, vp, vp, vp], i32),
     }
     sigs.update(_EXTRA_SIGS)
     for name, (argtypes, restype) in sigs.items():

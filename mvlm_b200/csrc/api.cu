@@ -223,4 +223,21 @@ int mvlm_snap_to_mesh(const float* verts, const int32_t* tris, int n_tris, const
                      static_cast<cudaStream_t>(stream));
 }
 
+size_t mvlm_snap_grid_bytes(int n_tris) { return snap_grid_bytes(n_tris); }
+
+int mvlm_snap_grid_build(const float* verts, const int32_t* tris, int n_tris, void* grid, size_t grid_bytes, void* stream) {
+  return snap_grid_build(verts, tris, n_tris, grid, grid_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_snap_grid_query(const float* verts, const int32_t* tris, int n_tris, const void* grid, size_t grid_bytes,
+                         const double* landmarks, int n_landmarks, double* out, int32_t* out_tri, int32_t* out_stats,
+                         void* stream) {
+  return snap_grid_query(verts, tris, n_tris, grid, grid_bytes, landmarks, n_landmarks, out, out_tri, out_stats,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_debug_snap_grid_describe(const void* grid, int32_t* dims_nover, double* edge_tau, void* stream) {
+  return snap_grid_describe(grid, dims_nover, edge_tau, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

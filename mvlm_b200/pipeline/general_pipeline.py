@@ -192,7 +192,7 @@ class Pipeline(abc.ABC, TimeMixin):
         lm, err, _ = e.estimate_landmarks_from_lines_device(peaks, starts, ends, draws_d)
         from .. import ops
 
-        snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm)
+        snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm, grid=dmesh.snap_grid())
         result = torch.cat([snapped.reshape(-1), err.sum().reshape(1) / err.numel()])
         # ring of page-locked result buffers, allocated together on first use (cudaHostAlloc synchronises the device)
         ring = self.__dict__.setdefault("_result_ring", [])

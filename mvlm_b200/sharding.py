@@ -77,7 +77,7 @@ def predict_mesh_view_split(pipeline, mesh, transforms: np.ndarray, group=None) 
     starts, ends = e.estimate_landmark_lines_device(peaks, transforms, r.image_size[0], rot=pipeline._vs_rot)
     draws = e.seeded_draws_device(peaks.shape[0])
     lm, err, _ = e.estimate_landmarks_from_lines_device(peaks, starts, ends, draws)
-    snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm)
+    snapped, _ = ops.snap_to_mesh(dmesh.verts, dmesh.tris, lm, grid=dmesh.snap_grid())
     pipeline.last_error = float((err.sum() / err.numel()).item())
     return snapped.cpu().numpy()
 

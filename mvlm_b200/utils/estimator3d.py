@@ -105,5 +105,5 @@ class Estimator3D:
         verts = pd.verts if hasattr(pd, "mesh") else torch.from_numpy(mesh.verts).to(self.device)
         tris = pd.tris if hasattr(pd, "mesh") else torch.from_numpy(mesh.tris).to(self.device)
         lm = torch.from_numpy(np.ascontiguousarray(landmarks, dtype=np.float64)).to(self.device)
-        out, _ = ops.snap_to_mesh(verts, tris, lm)
+        out, _ = ops.snap_to_mesh(verts, tris, lm, grid=pd.snap_grid() if hasattr(pd, "snap_grid") else "auto")
         return out.cpu().numpy()

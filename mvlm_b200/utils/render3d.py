@@ -105,6 +105,13 @@ class DeviceMesh:
             stage.done = torch.cuda.Event()
             stage.done.record()
 
+    def snap_grid(self):
+        """Spatial index for the surface snap, built at most once per device mesh (None below ops.SNAP_GRID_MIN_TRIS,
+        where the brute-force scan is faster than building the grid)."""
+        if "_snap_grid" not in self.__dict__:
+            self._snap_grid = ops.SnapGrid(self.verts, self.tris) if self.tris.shape[0] >= ops.SNAP_GRID_MIN_TRIS else None
+        return self._snap_grid
+
     @property
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.verts, self.tris, self.uvs, self.tex) if t is not None)

@@ -196,3 +196,81 @@ def test_snap_matches_oracle(lib):
     d_ref = np.linalg.norm(ref - lm, axis=1)
     d_got = np.linalg.norm(out - lm, axis=1)
     assert np.allclose(d_ref, d_got, atol=1e-9)
+
+
+def _snap_cases(rng, verts, n):
+    """Landmarks near the surface (the pipeline's case), on vertices, inside the bounding box, far outside, non-finite."""
+    ext = verts.max(0) - verts.min(0)
+    near = verts[rng.randint(0, len(verts), n)] + rng.normal(0, 0.01, (n, 3)) * ext
+    inside = rng.uniform(verts.min(0), verts.max(0), (n // 2, 3))
+    far = rng.uniform(-30, 30, (8, 3)) * ext + verts.mean(0)
+    on = verts[rng.randint(0, len(verts), 6)].astype(np.float64)
+    odd = np.array([[np.nan, 0, 0], [np.inf, 0, 0], [1e30, -1e30, 0]])
+    return np.concatenate([near, inside, far, on, odd]).astype(np.float64)
+
+
+@pytest.mark.parametrize("case", ["face", "face_big_tris", "slivers", "two_tris", "degenerate", "duplicates"])
+def test_snap_grid_equals_brute_force(lib, case):
+    """the grid is only an accelerator (like vtkCellLocator, estimator3d.py:258-262) -- same
+    triangle id and bit-identical point as the full scan, for every kind of landmark and mesh."""
+    from mvlm_b200 import ops
+
+    rng = np.random.RandomState(11)
+    if case in ("face", "face_big_tris", "duplicates"):
+        verts, _, tris = synth.face_mesh(grid=140, seed=4)
+        if case == "face_big_tris":  # a few huge triangles -> oversize list
+            extra = np.array([[-500, -500, -80], [500, -500, -80], [0, 600, -90], [300, 300, 300]], np.float32)
+            tris = np.concatenate([tris, len(verts) + np.array([[0, 1, 2], [1, 2, 3]], np.int32)])
+            verts = np.concatenate([verts, extra])
+        if case == "duplicates":  # exact ties between coincident triangles -> lowest id must win
+            tris = np.concatenate([tris, tris[::7]])
+    elif case == "slivers":
+        n = 4000
+        a = rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+        verts = np.concatenate([a, a + rng.normal(0, 30, (n, 3)).astype(np.float32), a + rng.normal(0, 0.01, (n, 3)).astype(np.float32)])
+        tris = np.stack([np.arange(n), np.arange(n) + n, np.arange(n) + 2 * n], 1).astype(np.int32)
+    elif case == "two_tris":
+        verts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5]], np.float32)
+        tris = np.array([[0, 1, 2], [1, 3, 2]], np.int32)
+    else:  # all vertices identical / collinear: zero-area triangles, zero-extent bounding box
+        verts = np.concatenate([np.zeros((3, 3), np.float32), np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2]], np.float32)])
+        tris = np.array([[0, 1, 2], [3, 4, 5], [0, 0, 0]], np.int32)
+    lm = _snap_cases(rng, verts, 60)
+    dv, dt, dl = cuda(verts), cuda(tris), cuda(lm)
+    ref, ref_tri = ops.snap_to_mesh(dv, dt, dl)
+    grid = ops.SnapGrid(dv, dt)
+    out, tid, stats = grid.query(dl, want_stats=True)
+    info = grid.describe()
+    finite = np.isfinite(lm).all(1)
+    assert torch.equal(tid, ref_tri), (info, (tid != ref_tri).nonzero().flatten().tolist())
+    assert np.array_equal(out.cpu().numpy()[finite].view(np.int64), ref.cpu().numpy()[finite].view(np.int64))
+    st = stats.cpu().numpy()
+    print(case, info, "tests/landmark: median", int(np.median(st[:, 0])), "max", int(st[:, 0].max()), "of", len(tris),
+          "; full-scan fallbacks", int((st[:, 1] < 0).sum()))
+    if case == "face":
+        near = st[:60]
+        assert (near[:, 1] >= 0).all() and np.median(near[:, 0]) < 0.05 * len(tris)  # the index actually prunes
+    if case == "face_big_tris":
+        assert info["n_oversize"] >= 2
+    # CPU oracle agrees too
+    o_ref, _ = native.snap_to_mesh(verts, tris, lm[finite])
+    assert np.abs(out.cpu().numpy()[finite] - o_ref).max() <= 1e-9 * max(1.0, np.abs(lm[finite]).max())
+
+
+def test_snap_grid_auto_selection(lib, monkeypatch):
+    """ops.snap_to_mesh(grid="auto") and DeviceMesh.snap_grid() switch on the triangle count; same answer either way."""
+    from mvlm_b200 import ops
+    from mvlm_b200.io_obj import Mesh
+    from mvlm_b200.utils.render3d import DeviceMesh
+
+    verts, uvs, tris = synth.face_mesh(grid=60, seed=2)
+    lm = cuda(verts[::97].astype(np.float64) + 0.3)
+    dm = DeviceMesh(Mesh(verts=verts, uvs=uvs, tris=tris, texture=None), torch.device("cuda"))
+    assert dm.snap_grid() is None  # small mesh: brute force
+    a, ta = ops.snap_to_mesh(dm.verts, dm.tris, lm, grid="auto")
+    monkeypatch.setattr(ops, "SNAP_GRID_MIN_TRIS", 1000)
+    dm2 = DeviceMesh(dm.mesh, torch.device("cuda"))
+    assert isinstance(dm2.snap_grid(), ops.SnapGrid) and dm2.snap_grid() is dm2.snap_grid()
+    b, tb = ops.snap_to_mesh(dm2.verts, dm2.tris, lm, grid=dm2.snap_grid())
+    c, tc = ops.snap_to_mesh(dm2.verts, dm2.tris, lm, grid="auto")
+    assert torch.equal(a, b) and torch.equal(ta, tb) and torch.equal(a, c) and torch.equal(ta, tc)
