@@ -198,14 +198,17 @@ int mvlm_snap_to_mesh(const float* verts, const int32_t* tris, int n_tris, const
 /* builds a vtkCellLocator inside every call, estimator3d.py:258-262).  mvlm_snap_grid_build fills `grid` */
 /* (mvlm_snap_grid_bytes(n_tris) bytes of device memory, 16-byte aligned) with a uniform grid over the    */
 /* triangle centroids, entirely on the device; mvlm_snap_grid_query returns exactly what                  */
-/* mvlm_snap_to_mesh returns (same triangle, same point).  out_stats (2L ints or NULL): point-triangle    */
-/* tests and shells walked per landmark (-1 = fell back to the full scan).                                */
+/* mvlm_snap_to_mesh returns (same triangle, same point); landmarks many cells away from the surface are  */
+/* handed to the full scan inside the same call.  out_stats (2L ints or NULL): point-triangle tests and   */
+/* shells walked per landmark (-1 = full scan).                                                           */
 size_t mvlm_snap_grid_bytes(int n_tris);
+size_t mvlm_snap_grid_query_workspace_bytes(int n_landmarks, int n_tris);
 int mvlm_snap_grid_build(const float* verts, const int32_t* tris, int n_tris, void* grid, size_t grid_bytes,
                          void* stream);
 int mvlm_snap_grid_query(const float* verts, const int32_t* tris, int n_tris, const void* grid,
-                         size_t grid_bytes, const double* landmarks, int n_landmarks, double* out /* (L,3) */,
-                         int32_t* out_tri /* (L) or NULL */, int32_t* out_stats /* (L,2) or NULL */, void* stream);
+                         size_t grid_bytes, const double* landmarks, int n_landmarks, void* workspace,
+                         size_t workspace_bytes, double* out /* (L,3) */, int32_t* out_tri /* (L) or NULL */,
+                         int32_t* out_stats /* (L,2) or NULL */, void* stream);
 /* debug: grid dims[3] + oversize-list length, cell edge + largest binned triangle radius (synchronises) */
 int mvlm_debug_snap_grid_describe(const void* grid, int32_t* dims_nover /* [4] */, double* edge_tau /* [2] */,
                                   void* stream);

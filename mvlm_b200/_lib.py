@@ -95,7 +95,8 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_snap_to_mesh": ([vp, vp, i32, vp, i32, vp, C.c_size_t, vp, vp, vp], i32),
         "mvlm_snap_grid_bytes": ([i32], C.c_size_t),
         "mvlm_snap_grid_build": ([vp, vp, i32, vp, C.c_size_t, vp], i32),
-        "mvlm_snap_grid_query": ([vp, vp, i32, vp, C.c_size_t, vp, i32, vp, vp, vp, vp], i32),
+        "mvlm_snap_grid_query_workspace_bytes": ([i32, i32], C.c_size_t),
+        "mvlm_snap_grid_query": ([vp, vp, i32, vp, C.c_size_t, vp, i32, vp, C.c_size_t, vp, vp, vp, vp], i32),
         "mvlm_debug_snap_grid_describe": ([vp, vp, vp, vp], i32),
     }
     sigs.update(_EXTRA_SIGS)

@@ -229,11 +229,15 @@ int mvlm_snap_grid_build(const float* verts, const int32_t* tris, int n_tris, vo
   return snap_grid_build(verts, tris, n_tris, grid, grid_bytes, static_cast<cudaStream_t>(stream));
 }
 
+size_t mvlm_snap_grid_query_workspace_bytes(int n_landmarks, int n_tris) {
+  return snap_grid_query_workspace_bytes(n_landmarks, n_tris);
+}
+
 int mvlm_snap_grid_query(const float* verts, const int32_t* tris, int n_tris, const void* grid, size_t grid_bytes,
-                         const double* landmarks, int n_landmarks, double* out, int32_t* out_tri, int32_t* out_stats,
-                         void* stream) {
-  return snap_grid_query(verts, tris, n_tris, grid, grid_bytes, landmarks, n_landmarks, out, out_tri, out_stats,
-                         static_cast<cudaStream_t>(stream));
+                         const double* landmarks, int n_landmarks, void* workspace, size_t workspace_bytes, double* out,
+                         int32_t* out_tri, int32_t* out_stats, void* stream) {
+  return snap_grid_query(verts, tris, n_tris, grid, grid_bytes, landmarks, n_landmarks, workspace, workspace_bytes, out,
+                         out_tri, out_stats, static_cast<cudaStream_t>(stream));
 }
 
 int mvlm_debug_snap_grid_describe(const void* grid, int32_t* dims_nover, double* edge_tau, void* stream) {

@@ -94,8 +94,9 @@ __device__ __forceinline__ void tri_closest(const float* __restrict__ verts, con
 
 __global__ void __launch_bounds__(256) snap_scan_kernel(const float* __restrict__ verts, const int* __restrict__ tris,
                                                         int nt, const double* __restrict__ lm, int splits,
-                                                        double* __restrict__ part) {
+                                                        double* __restrict__ part, const int* __restrict__ only) {
   const int l = blockIdx.x, split = blockIdx.y;
+  if (only && !only[l]) return;  // grid path: only the landmarks its query handed back
   const double p[3] = {lm[3 * l], lm[3 * l + 1], lm[3 * l + 2]};
   const int chunk = (nt + splits - 1) / splits;
   const int t0 = split * chunk, t1 = min(nt, t0 + chunk);
@@ -131,9 +132,9 @@ __global__ void __launch_bounds__(256) snap_scan_kernel(const float* __restrict_
 }
 
 __global__ void snap_finalize_kernel(const double* __restrict__ part, int L, int splits, double* __restrict__ out,
-                                     int* __restrict__ out_tri) {
+                                     int* __restrict__ out_tri, const int* __restrict__ only) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
+  if (l >= L || (only && !only[l])) return;
   const double* q = part + static_cast<size_t>(l) * splits * kSnapPart;
   int bs = 0;
   for (int s = 1; s < splits; ++s)
@@ -165,8 +166,8 @@ int snap_launch(const float* verts, const int* tris, int nt, const double* lm, i
   MVLM_REQUIRE(nt > 0 && l > 0, "snap: bad sizes");
   MVLM_REQUIRE(workspace_bytes >= snap_workspace_bytes(l, nt), "snap: workspace too small");
   const int splits = snap_splits(l, nt);
-  snap_scan_kernel<<<dim3(l, splits), 256, 0, s>>>(verts, tris, nt, lm, splits, static_cast<double*>(workspace));
-  snap_finalize_kernel<<<ceil_div(l, 128), 128, 0, s>>>(static_cast<double*>(workspace), l, splits, out, out_tri);
+  snap_scan_kernel<<<dim3(l, splits), 256, 0, s>>>(verts, tris, nt, lm, splits, static_cast<double*>(workspace), nullptr);
+  snap_finalize_kernel<<<ceil_div(l, 128), 128, 0, s>>>(static_cast<double*>(workspace), l, splits, out, out_tri, nullptr);
   count_launch(2);
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
@@ -178,7 +179,8 @@ int snap_launch(const float* verts, const int* tris, int nt, const double* lm, i
 namespace {
 
 constexpr int kScanItems = 4096;  // cells per scan block (256 threads x 16)
-constexpr int kMaxShells = 8;     // shells walked before a query gives up and scans every triangle
+constexpr int kMaxShells = 8;     // shells walked before a query hands its landmark to the full scan (see 7c: a long walk
+                                  // costs more than the scan, which then bounds the worst case at scan + ~50 us)
 constexpr int kGridHdrBytes = 256;
 
 struct GridHdr {
@@ -424,7 +426,8 @@ constexpr int kQueryList = 4096;  // triangle ids gathered per shell before they
 __global__ void __launch_bounds__(kQueryThreads) grid_query_kernel(
     const float* __restrict__ verts, const int* __restrict__ tris, const GridHdr* __restrict__ hdr,
     const int* __restrict__ cell_start, const int* __restrict__ sorted, const int* __restrict__ over,
-    const double* __restrict__ lm, double* __restrict__ out, int* __restrict__ out_tri, int* __restrict__ out_stats) {
+    const double* __restrict__ lm, double* __restrict__ out, int* __restrict__ out_tri, int* __restrict__ out_stats,
+    int* __restrict__ handed_back) {
   __shared__ int s_list[kQueryList];
   __shared__ int s_total;
   __shared__ double s_best[kQueryThreads / 32];
@@ -460,20 +463,34 @@ __global__ void __launch_bounds__(kQueryThreads) grid_query_kernel(
   bool exhaustive = !finite;  // every decision below is uniform over the block
   for (int r = r_min; r <= r_max && !exhaustive; ++r, ++shells) {
     if (shells >= kMaxShells) { exhaustive = true; break; }
-    int lo[3], n[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      lo[i] = max(ci[i] - r, 0);
-      n[i] = min(ci[i] + r, h.dim[i] - 1) - lo[i] + 1;
-    }
-    const long long total_ll = static_cast<long long>(n[0]) * n[1] * n[2];
-    if (total_ll > 65536) { exhaustive = true; break; }  // landmark far outside: a slab of the grid per shell
+    // the shell = surface of the (2r+1)^3 box of cells: two full z faces, then the square's perimeter on the levels between
+    const int side = 2 * r + 1, face = side * side, ring = 8 * r;
+    const long long total_ll = r == 0 ? 1 : 2ll * face + static_cast<long long>(side - 2) * ring;
+    if (total_ll > 8192) { exhaustive = true; break; }  // landmark cell > 18 cells outside the grid: far from any triangle
     const int total = static_cast<int>(total_ll);
     if (tid == 0) s_total = 0;
     __syncthreads();
     for (int j = tid; j < total; j += kQueryThreads) {
-      const int x = lo[0] + j % n[0], y = lo[1] + (j / n[0]) % n[1], z = lo[2] + j / (n[0] * n[1]);
-      if (max(abs(x - ci[0]), max(abs(y - ci[1]), abs(z - ci[2]))) != r) continue;  // inner cells: earlier shells
+      int dx, dy, dz;
+      if (j < 2 * face) {
+        const int jj = j < face ? j : j - face;
+        dz = j < face ? -r : r;
+        dx = jj % side - r;
+        dy = jj / side - r;
+      } else {
+        const int k = j - 2 * face, m = k % ring;
+        dz = k / ring - r + 1;
+        if (m < 2 * side) {
+          dx = (m < side ? m : m - side) - r;
+          dy = m < side ? -r : r;
+        } else {
+          const int mm = m - 2 * side;
+          dx = mm / (side - 2) ? r : -r;
+          dy = mm % (side - 2) - r + 1;
+        }
+      }
+      const int x = ci[0] + dx, y = ci[1] + dy, z = ci[2] + dz;
+      if (x < 0 || y < 0 || z < 0 || x >= h.dim[0] || y >= h.dim[1] || z >= h.dim[2]) continue;
       const int cell = (z * h.dim[1] + y) * h.dim[0] + x;
       const int b = cell_start[cell], cnt = cell_start[cell + 1] - b;
       if (cnt <= 0) continue;
@@ -502,8 +519,13 @@ __global__ void __launch_bounds__(kQueryThreads) grid_query_kernel(
     const double lb = h.c * (r + margin) * (1.0 - 1e-9) - 1e-9 * h.c - tau;
     if (lb > 0.0 && wbest < lb * lb) break;
   }
-  if (exhaustive)  // far-away or non-finite landmark: same full scan as the brute-force kernel
-    for (int t = tid; t < h.nt; t += kQueryThreads) test(t);
+  if (exhaustive) {  // far from the surface (in cells) or non-finite: the (L, splits) scan kernels that follow do this one
+    if (tid == 0) {
+      handed_back[l] = 1;
+      if (out_stats) { out_stats[2 * l] = h.nt; out_stats[2 * l + 1] = -1; }
+    }
+    return;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double od = __shfl_xor_sync(0xffffffffu, best, o);
@@ -522,7 +544,8 @@ __global__ void __launch_bounds__(kQueryThreads) grid_query_kernel(
     if (bt != 0x7fffffff) tri_closest(verts, tris, bt, p, q);
     out[3 * l] = q[0]; out[3 * l + 1] = q[1]; out[3 * l + 2] = q[2];
     if (out_tri) out_tri[l] = bt;
-    if (out_stats) { out_stats[2 * l] = n_tests; out_stats[2 * l + 1] = exhaustive ? -1 : shells; }
+    if (out_stats) { out_stats[2 * l] = n_tests; out_stats[2 * l + 1] = shells; }
+    handed_back[l] = 0;
   }
 }
 
@@ -558,18 +581,33 @@ int snap_grid_build(const float* verts, const int* tris, int nt, void* grid, siz
   return MVLM_OK;
 }
 
+size_t snap_grid_query_workspace_bytes(int l, int nt) {
+  return snap_workspace_bytes(l, nt) + (static_cast<size_t>(l) * sizeof(int) + 63) / 64 * 64;
+}
+
 int snap_grid_query(const float* verts, const int* tris, int nt, const void* grid, size_t grid_bytes, const double* lm,
-                    int l, double* out, int* out_tri, int* out_stats, cudaStream_t s) {
-  MVLM_REQUIRE(verts && tris && grid && lm && out, "snap grid: null pointer");
+                    int l, void* workspace, size_t workspace_bytes, double* out, int* out_tri, int* out_stats,
+                    cudaStream_t s) {
+  MVLM_REQUIRE(verts && tris && grid && lm && out && workspace, "snap grid: null pointer");
   MVLM_REQUIRE(nt > 0 && l > 0, "snap grid: bad sizes");
   const GridLayout g = grid_layout(nt);
   MVLM_REQUIRE(grid_bytes >= g.total, "snap grid: buffer too small");
+  MVLM_REQUIRE(workspace_bytes >= snap_grid_query_workspace_bytes(l, nt), "snap grid: workspace too small");
+  MVLM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "snap grid: workspace must be 8-byte aligned");
   const uint8_t* base = static_cast<const uint8_t*>(grid);
+  int* handed_back = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + snap_workspace_bytes(l, nt));
+  double* part = static_cast<double*>(workspace);
   grid_query_kernel<<<l, kQueryThreads, 0, s>>>(verts, tris, reinterpret_cast<const GridHdr*>(base),
                                       reinterpret_cast<const int*>(base + g.cell_start),
                                       reinterpret_cast<const int*>(base + g.sorted),
-                                      reinterpret_cast<const int*>(base + g.over), lm, out, out_tri, out_stats);
-  count_launch(1);
+                                      reinterpret_cast<const int*>(base + g.over), lm, out, out_tri, out_stats,
+                                      handed_back);
+  // landmarks the walk gave up on (more than kMaxShells cells from the surface, non-finite): the full scan, spread over
+  // (L, splits) blocks; blocks of the other landmarks return at once
+  const int splits = snap_splits(l, nt);
+  snap_scan_kernel<<<dim3(l, splits), 256, 0, s>>>(verts, tris, nt, lm, splits, part, handed_back);
+  snap_finalize_kernel<<<ceil_div(l, 128), 128, 0, s>>>(part, l, splits, out, out_tri, handed_back);
+  count_launch(3);
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
 }

@@ -62,8 +62,10 @@ int snap_launch(const float* verts, const int* tris, int nt, const double* lm, i
 // uniform grid over triangle centroids: built once per mesh on the device, exact queries (same result as snap_launch)
 size_t snap_grid_bytes(int nt);
 int snap_grid_build(const float* verts, const int* tris, int nt, void* grid, size_t grid_bytes, cudaStream_t s);
+size_t snap_grid_query_workspace_bytes(int l, int nt);
 int snap_grid_query(const float* verts, const int* tris, int nt, const void* grid, size_t grid_bytes, const double* lm,
-                    int l, double* out, int* out_tri, int* out_stats, cudaStream_t s);
+                    int l, void* workspace, size_t workspace_bytes, double* out, int* out_tri, int* out_stats,
+                    cudaStream_t s);
 int snap_grid_describe(const void* grid, int* dims_nover, double* edge_tau, cudaStream_t s);
 
 // ---- eltwise.cu / stem.cu ---------------------------------------------------

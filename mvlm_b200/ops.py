@@ -232,8 +232,10 @@ class SnapGrid:
         out = torch.empty((l, 3), dtype=torch.float64, device=self.verts.device)
         tid = torch.empty((l,), dtype=torch.int32, device=self.verts.device)
         stats = torch.empty((l, 2), dtype=torch.int32, device=self.verts.device) if want_stats else None
+        ws = torch.empty((lib.mvlm_snap_grid_query_workspace_bytes(l, self.n_tris),), dtype=torch.uint8, device=self.verts.device)
         check(lib.mvlm_snap_grid_query(ptr(self.verts), ptr(self.tris), self.n_tris, ptr(self.buf), self.buf.numel(),
-                                       ptr(landmarks), l, ptr(out), ptr(tid), ptr(stats), cur_stream()), "mvlm_snap_grid_query")
+                                       ptr(landmarks), l, ptr(ws), ws.numel(), ptr(out), ptr(tid), ptr(stats), cur_stream()),
+              "mvlm_snap_grid_query")
         return (out, tid, stats) if want_stats else (out, tid)
 
     def describe(self):
