@@ -49,10 +49,69 @@ def allgather_peaks(local_peaks: torch.Tensor, n_views: int, group=None) -> torc
     return out
 
 
+# Scans at least this large take the sharded upload in predict_mesh_view_split.  Measured (profiles/r1_view_split_c4.txt):
+# 5 MB scan 1.05 -> 0.37 ms on 8 GPUs, 0.55 -> 0.53 ms on 2; 47 MB scan 8.98 -> 1.20 ms on 8, 3.40 -> 2.95 ms on 2.
+SHARDED_UPLOAD_MIN_BYTES = 4 << 20
+
+
+def allgather_bytes(array: np.ndarray, device, stage=None, name: str = "a", group=None) -> torch.Tensor:
+    """`array` is the same on every rank: rank r moves only the r-th 1/world of its bytes from host to device and the
+    slices are all-gathered (NCCL over NVLink on GPUs, gloo on CPU), so a scan crosses each rank's PCIe link and host
+    memory once per `world` ranks instead of once per rank.  Returns the whole array on `device`."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    a = np.ascontiguousarray(array)
+    raw = a.reshape(-1).view(np.uint8)
+    chunk = (-(-raw.size // world) + 15) // 16 * 16
+    lo, hi = min(rank * chunk, raw.size), min((rank + 1) * chunk, raw.size)
+    send = torch.zeros((chunk,), dtype=torch.uint8, device=device) if hi - lo < chunk else \
+        torch.empty((chunk,), dtype=torch.uint8, device=device)
+    if hi > lo:
+        part = raw[lo:hi]
+        if stage is not None and torch.device(device).type == "cuda":
+            send[:hi - lo].copy_(stage.stage(name + "@shard", part), non_blocking=True)
+        else:
+            send[:hi - lo].copy_(torch.from_numpy(part.copy()))
+    recv = torch.empty((world * chunk,), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:raw.size].view(torch.from_numpy(a[:0].reshape(-1).copy()).dtype).view(a.shape)
+
+
+def upload_mesh_sharded(renderer, mesh, group=None):
+    """DeviceMesh of a scan every rank holds in host memory, each rank uploading 1/world of it (allgather_bytes)."""
+    from .utils.render3d import DeviceMesh, _PinnedStage
+
+    device = renderer.device
+    stage = None
+    if torch.device(device).type == "cuda":
+        ring = renderer.__dict__.setdefault("_shard_stages", [_PinnedStage() for _ in range(2)])
+        renderer._shard_i = getattr(renderer, "_shard_i", 0) + 1
+        stage = ring[renderer._shard_i % len(ring)]
+        if stage.done is not None:
+            stage.done.synchronize()  # the slot's previous transfer has left the host buffers
+    tex = mesh.texture
+    if isinstance(tex, torch.Tensor):  # decoded on the device already
+        if mesh.texture_ready is not None:
+            torch.cuda.current_stream().wait_event(mesh.texture_ready)
+        tex_d = tex
+    else:
+        tex_d = None if tex is None else allgather_bytes(tex, device, stage, "tex", group)
+    verts = allgather_bytes(mesh.verts, device, stage, "verts", group)
+    tris = allgather_bytes(mesh.tris, device, stage, "tris", group)
+    uvs = None if mesh.uvs is None else allgather_bytes(mesh.uvs, device, stage, "uvs", group)
+    if stage is not None:
+        stage.done = torch.cuda.Event()
+        stage.done.record()
+    return DeviceMesh.from_device(mesh, verts, tris, uvs, tex_d)
+
+
+def _mesh_bytes(mesh) -> int:
+    return sum(a.nbytes for a in (mesh.verts, mesh.tris, mesh.uvs, mesh.texture) if isinstance(a, np.ndarray))
+
+
 def predict_mesh_view_split(pipeline, mesh, transforms: np.ndarray, group=None) -> np.ndarray:
     """One scan whose views are split over the ranks of `group` (BASELINE.json config 4):
-    every rank holds the whole mesh, rasterises and runs the CNN on its block of views, the peaks are
-    all-gathered, and every rank finishes rays / consensus / snap redundantly (it is microseconds of
+    every rank holds the whole mesh (uploaded in `world` slices and all-gathered when it is large), rasterises and runs
+    the CNN on its block of views, the peaks are all-gathered, and every rank finishes rays / consensus / snap redundantly (it is microseconds of
     work and removes a broadcast of the result)."""
     from . import ops
 
@@ -62,7 +121,8 @@ def predict_mesh_view_split(pipeline, mesh, transforms: np.ndarray, group=None) 
     transforms = np.asarray(transforms)
     n_views = transforms.shape[0]
     start, count = split_views(n_views, rank, world)
-    dmesh = r.upload(mesh)
+    # every rank needs the whole mesh: large scans are uploaded 1/world per rank and all-gathered over NVLink
+    dmesh = upload_mesh_sharded(r, mesh, group) if world > 1 and _mesh_bytes(mesh) >= SHARDED_UPLOAD_MIN_BYTES else r.upload(mesh)
     local = r.render_device(dmesh, transforms[start:start + count])
     peaks_local = p.predict_landmarks_device(local["u8"])
     peaks = allgather_peaks(peaks_local, n_views, group)

@@ -124,6 +124,13 @@ class DeviceMesh:
             stage.done = torch.cuda.Event()
             stage.done.record()
 
+    @classmethod
+    def from_device(cls, mesh: Mesh, verts, tris, uvs, tex) -> "DeviceMesh":
+        """Wraps arrays that are on the device already (sharding.upload_mesh_sharded)."""
+        self = cls.__new__(cls)
+        self.mesh, self.verts, self.tris, self.uvs, self.tex = mesh, verts, tris, uvs, tex
+        return self
+
     def snap_grid(self):
         """Spatial index for the surface snap, built at most once per device mesh (None below ops.SNAP_GRID_MIN_TRIS,
         where the brute-force scan is faster than building the grid)."""

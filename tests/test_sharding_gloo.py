@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mvlm_b200.sharding import allgather_peaks, shard_scans, split_views
+from mvlm_b200.sharding import allgather_bytes, allgather_peaks, shard_scans, split_views
 
 
 def test_shard_and_split_arithmetic():
@@ -49,3 +49,32 @@ def test_allgather_peaks_world2_uneven():
         for p in procs:
             p.join(timeout=60)
         assert sorted(res) == [(0, True), (1, True)]
+
+
+def _bytes_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(3)
+    ok = True
+    # sizes that do not divide by world * 16, a tiny array (some ranks own nothing), uint8 / int32 / float32
+    for a in (rng.rand(1001, 3).astype(np.float32), rng.randint(0, 1 << 30, (777, 3)).astype(np.int32),
+              rng.randint(0, 256, (33, 17, 3)).astype(np.uint8), np.arange(5, dtype=np.float32)):
+        out = allgather_bytes(a, "cpu")
+        ok = ok and out.dtype == torch.from_numpy(a).dtype and tuple(out.shape) == a.shape and np.array_equal(out.numpy(), a)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_upload_reassembles_arrays():
+    """Each rank contributes 1/world of the bytes; every rank ends with the whole array (view-split mesh upload)."""
+    ctx = mp.get_context("spawn")
+    for world in (2, 3):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_bytes_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        assert sorted(res) == [(r, True) for r in range(world)]

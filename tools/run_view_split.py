@@ -14,7 +14,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from mvlm_b200 import build, synth  # noqa: E402
 from mvlm_b200.io_obj import Mesh  # noqa: E402
 from mvlm_b200.pipeline import create_pipeline  # noqa: E402
-from mvlm_b200.sharding import predict_mesh_view_split  # noqa: E402
+from mvlm_b200 import sharding  # noqa: E402
+from mvlm_b200.sharding import predict_mesh_view_split, upload_mesh_sharded  # noqa: E402
 from mvlm_b200.weights import seeded_state_dict  # noqa: E402
 
 views = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -41,13 +42,30 @@ for _ in range(5):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 5
 ok, checked = True, False
+# the sharded upload (1/world of the scan per rank + NVLink all-gather) delivers the host arrays bit for bit, and timing
+sharded = sharding._mesh_bytes(mesh) >= sharding.SHARDED_UPLOAD_MIN_BYTES and world > 1
+up = {}
+for name, fn in (("sharded", lambda: upload_mesh_sharded(dm.renderer_3d, mesh)), ("whole", lambda: dm.renderer_3d.upload(mesh))):
+    for _ in range(4):
+        d = fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
+    for _ in range(5):
+        d = fn()
+    torch.cuda.synchronize()
+    up[name] = (time.perf_counter() - t1) / 5 * 1e3
+    for a, b in ((d.verts, mesh.verts), (d.tris, mesh.tris), (d.uvs, mesh.uvs), (d.tex, mesh.texture)):
+        ok = ok and bool(np.array_equal(a.cpu().numpy(), b))
 if views * size * size <= 64 * 256 * 256:  # single-rank reference only when it fits comfortably
     single = dm.predict_mesh(mesh)
-    ok, checked = bool(np.array_equal(single, split)), True
+    ok, checked = ok and bool(np.array_equal(single, split)), True
 flag = torch.tensor([int(ok)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"view-split over {world} ranks: {views} views {size}^2, {len(t)} tris: {dt * 1e3:.2f} ms/scan, "
-          + (f"identical to single rank: {bool(flag.item())}" if checked else "single-rank comparison skipped at this size"))
+          + (f"identical to single rank: {bool(flag.item())}" if checked else "single-rank comparison skipped at this size")
+          + f"; scan upload {sharding._mesh_bytes(mesh) / 1e6:.0f} MB: whole per rank {up['whole']:.2f} ms, 1/{world} per rank + all-gather "
+          f"{up['sharded']:.2f} ms ({'used' if sharded else 'not used at this size'}), arrays identical: {bool(flag.item())}")
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)
