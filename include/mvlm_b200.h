@@ -135,8 +135,11 @@ int mvlm_raster_multiview(const float* verts, const float* uvs, const int32_t* t
 typedef struct mvlm_hourglass mvlm_hourglass;
 size_t mvlm_hourglass_workspace_bytes(int n_landmarks, int cin, int n_views, int h, int w);
 double mvlm_hourglass_flops_per_view(int n_landmarks, int cin, int h, int w);
-int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, int n_entries,
-                          int n_landmarks, int cin, int n_views, int h, int w, void* workspace,
+/* numels[i] = element count of tensor i (or NULL: unchecked).  Like load_state_dict (paulsenpredictor.py:102,108)
+ * a missing key or a tensor whose size does not fit this model's layer is an error (MVLM_E_INVALID), never a
+ * silent misread. */
+int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, const long long* numels,
+                          int n_entries, int n_landmarks, int cin, int n_views, int h, int w, void* workspace,
                           size_t workspace_bytes, mvlm_hourglass** out);
 int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                            float* out_heatmaps, float* out_peaks, void* stream);
@@ -145,6 +148,9 @@ int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const flo
 int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                                  float* out_heatmaps, float* out_peaks, void* stream);
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net);
+/* number of dataflow segments of the plan (csrc/conv_flow.cuh): runs of layers executed by one persistent launch
+ * over small view batches so that their intermediate tensors stay in L2; 0 = every layer is its own launch */
+int mvlm_hourglass_num_segments(const mvlm_hourglass* net);
 /* Debug aids: per-op mean milliseconds over `reps` passes (ms_out[num_launches], host memory; out_peaks (L,V,3)
  * device), optionally the conv kernel's per-role stall cycles (roles_out[num_launches*8] host doubles, layout of
  * mvlm_debug_conv_profile, mean over CTAs), and a one-line description of op `op`. */

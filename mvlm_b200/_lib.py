@@ -70,11 +70,12 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_raster_multiview": ([vp, vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_workspace_bytes": ([i32, i32, i32, i32, i32], C.c_size_t),
         "mvlm_hourglass_flops_per_view": ([i32, i32, i32, i32], f64),
-        "mvlm_hourglass_create": ([C.POINTER(C.c_char_p), C.POINTER(vp), i32, i32, i32, i32, i32, i32, vp,
-                                   C.c_size_t, C.POINTER(vp)], i32),
+        "mvlm_hourglass_create": ([C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_longlong), i32, i32, i32, i32,
+                                   i32, i32, vp, C.c_size_t, C.POINTER(vp)], i32),
         "mvlm_hourglass_forward": ([vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_forward_graph": ([vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_num_launches": ([vp], i32),
+        "mvlm_hourglass_num_segments": ([vp], i32),
         "mvlm_debug_hourglass_profile": ([vp, vp, vp, vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_double), i32,
                                          C.POINTER(C.c_longlong), vp], i32),
         "mvlm_debug_conv_profile_ints": ([], i32),

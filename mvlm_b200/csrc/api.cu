@@ -23,6 +23,18 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int sm_count() {
+  static std::atomic<int> cached[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return kNumSMs;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw,
                                         int cout_pad, int cin_pad, __nv_bfloat16* __restrict__ out) {
   const long long total = 1ll * cout_pad * kw * kh * cin_pad;
@@ -133,11 +145,17 @@ double mvlm_hourglass_flops_per_view(int n_landmarks, int cin, int h, int w) {
   return dry.flops_per_view();
 }
 
-int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, int n_entries, int n_landmarks, int cin,
-                          int n_views, int h, int w, void* workspace, size_t workspace_bytes, mvlm_hourglass** out) {
+int mvlm_hourglass_create(const char* const* names, const void* const* ptrs, const long long* numels, int n_entries,
+                          int n_landmarks, int cin, int n_views, int h, int w, void* workspace, size_t workspace_bytes,
+                          mvlm_hourglass** out) {
   MVLM_REQUIRE(names && ptrs && out, "mvlm_hourglass_create: null pointer");
-  std::map<std::string, const float*> sd;
-  for (int i = 0; i < n_entries; ++i) sd[names[i]] = static_cast<const float*>(ptrs[i]);
+  StateDict sd;
+  for (int i = 0; i < n_entries; ++i) {
+    SdEntry e;
+    e.p = static_cast<const float*>(ptrs[i]);
+    e.numel = numels ? numels[i] : -1;
+    sd[names[i]] = e;
+  }
   mvlm_hourglass* h_ = new mvlm_hourglass();
   const int rc = h_->net.build(&sd, n_landmarks, cin, n_views, h, w, workspace, workspace_bytes, false);
   if (rc != MVLM_OK) {
@@ -175,6 +193,8 @@ int mvlm_debug_hourglass_describe(const mvlm_hourglass* net, int op, char* buf, 
 }
 
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net) { return net ? net->net.n_ops() : 0; }
+
+int mvlm_hourglass_num_segments(const mvlm_hourglass* net) { return net ? net->net.n_segments() : 0; }
 
 int mvlm_hourglass_probe(const mvlm_hourglass* net, const char* name, const void** ptr, int* h, int* w, int* c) {
   MVLM_REQUIRE(net && name && ptr && h && w && c, "mvlm_hourglass_probe: null pointer");

@@ -43,7 +43,10 @@ void set_error(const char* fmt, ...);
 // gpu_launches).  Incremented by every launch wrapper.
 void count_launch(int n = 1);
 
-constexpr int kNumSMs = 148;
+constexpr int kNumSMs = 148;     // B200; sizes of debug buffers only -- launch grids use sm_count()
+constexpr int kMaxDevices = 64;  // per-device caches (function attributes, SM counts)
+// multiprocessor count of the current device (queried once per device)
+int sm_count();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

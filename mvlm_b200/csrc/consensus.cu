@@ -330,7 +330,7 @@ __global__ void consensus_finalize_kernel(ConsensusArgs g, Layout ws, int splits
 }
 
 int pick_splits(int l, int n_hyp) {
-  int splits = ceil_div(2 * kNumSMs, l);
+  int splits = ceil_div(2 * sm_count(), l);
   const int max_splits = ceil_div(n_hyp, 256);  // at least one hypothesis per thread
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -358,12 +358,11 @@ int consensus_launch(const ConsensusArgs& a, cudaStream_t s) {
   Layout ws = carve(a.workspace, a.l, a.v, splits);
   consensus_prepare_kernel<<<a.l, 256, 0, s>>>(a, ws);
   const size_t smem = static_cast<size_t>(a.v) * kLineDoubles * sizeof(double);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  // more than 48 KB (over 384 views): the opt-in attribute is per device, so it is set on every such launch
+  // (a host-side call of about a microsecond; the common cases stay below the limit)
+  if (smem > 48 * 1024)
     MVLM_CHECK_CUDA(cudaFuncSetAttribute(consensus_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-    configured = smem;
-  }
   consensus_hyp_kernel<<<dim3(a.l, splits), 256, smem, s>>>(a, ws, splits, chunk);
   consensus_finalize_kernel<<<ceil_div(a.l, 128), 128, 0, s>>>(a, ws, splits);
   count_launch(3);

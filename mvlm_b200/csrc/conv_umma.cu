@@ -28,27 +28,21 @@
 //
 // Accumulators: 2 pipeline stages x 256 fp32 columns of TMEM: the epilogue of tile i overlaps the
 // MMAs of tile i+1.
-#include "conv_umma.cuh"
+#include "conv_epilogue.cuh"
 
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 
 namespace mvlm {
 
 namespace {
 
-constexpr int kThreads = 352;                          // warps: 0 halo TMA, 1 MMA, 2..9 epilogue, 10 weight TMA
-constexpr int kEpiWarps = 8;
-constexpr int kTileW = 8;                               // output tile: 8 px wide ...
-constexpr int kMaxTileH = 32;                           // ... and up to 32 rows high (N = 256)
-constexpr int kMTile = 128;                             // output channels per CTA tile (UMMA M)
+using namespace epi;
 constexpr int kMaxHSlots = 4;                           // halo (activation) ring, depth chosen per layer
 constexpr int kMaxWSlots = 12;                          // weight ring (16 KB slots at M = 128, 8 KB at M = 64)
 constexpr int kPoolBytes = 198 * 1024;                  // both rings
-constexpr int kStageFloats = 32 * 20;                   // per-warp transpose buffer: 16 px x (32 ch + 4 pad) | 32 px x (16 + 4)
-constexpr int kMaxCout = 256;
-constexpr int kTraceTiles = 64;                        // debug timeline: tiles traced on CTA 0
 
 struct __align__(8) Barriers {
   uint64_t h_full[kMaxHSlots];
@@ -76,74 +70,6 @@ constexpr int kSmemBytes = kPoolBytes + kEpiWarps * kStageFloats * 4 + 512 + sta
                            1024 /*align*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-__device__ __forceinline__ uint32_t order_f32(float f) {
-  const uint32_t b = __float_as_uint(f);
-  // negative: ~b, else b | 0x80000000  ==  b ^ (sign-extended sign | 0x80000000)
-  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
-}
-
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
-  __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]);
-  __nv_bfloat162 d = __floats2bfloat162_rn(f[6], f[7]);
-  uint4 r;
-  r.x = *reinterpret_cast<uint32_t*>(&a);
-  r.y = *reinterpret_cast<uint32_t*>(&b);
-  r.z = *reinterpret_cast<uint32_t*>(&c);
-  r.w = *reinterpret_cast<uint32_t*>(&d);
-  return r;
-}
-// relu + round to bf16 in one instruction per pair (cvt.rn.relu.bf16x2.f32: first source -> upper half)
-__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// relu(f * s + t) -> bf16 x 8
-__device__ __forceinline__ uint4 affine_relu_pack8(const float (&f)[8], const float (&sc)[8], const float (&sh)[8]) {
-  uint4 r;
-  r.x = relu_bf16x2(fmaf(f[0], sc[0], sh[0]), fmaf(f[1], sc[1], sh[1]));
-  r.y = relu_bf16x2(fmaf(f[2], sc[2], sh[2]), fmaf(f[3], sc[3], sh[3]));
-  r.z = relu_bf16x2(fmaf(f[4], sc[4], sh[4]), fmaf(f[5], sc[5], sh[5]));
-  r.w = relu_bf16x2(fmaf(f[6], sc[6], sh[6]), fmaf(f[7], sc[7], sh[7]));
-  return r;
-}
-__device__ __forceinline__ void add8(const uint4& q, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 t = __bfloat1622float2(h[j]);
-    f[2 * j] += t.x;
-    f[2 * j + 1] += t.y;
-  }
-}
-__device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
-  uint4 r;
-  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) pr[j] = __hmax2(pa[j], pb[j]);
-  return r;
-}
-__device__ __forceinline__ void lds8(const float* src, float (&v)[8]) {
-  const float4 a = reinterpret_cast<const float4*>(src)[0];
-  const float4 b = reinterpret_cast<const float4*>(src)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
-// role timing: wait on an mbarrier and add the stalled cycles to `acc` when profiling is on
-__device__ __forceinline__ void timed_wait(uint64_t* b, uint32_t parity, bool prof, long long& acc) {
-  if (!prof) { ptx::mbar_wait(b, parity); return; }
-  const long long t0 = clock64();
-  ptx::mbar_wait(b, parity);
-  acc += clock64() - t0;
-}
-
-struct TileCoord {
-  int mt, tx, ty, img;
-};
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
   c.mt = t % p.n_nt;
@@ -154,14 +80,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   c.img = r / p.tiles_y;
   return c;
 }
-
-// Epilogue feature flags (template parameter F): code for a feature is only generated when its bit is set,
-// which keeps the per-row instruction count of the hot variants low (the epilogue is issue-bound).
-enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
-              F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */,
-              F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */,
-              F_M64 = 1024 /* cout <= 64: UMMA M = 64, 16 channels per TMEM lane group */ };
-constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 template <int F>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
@@ -385,295 +303,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
   } else {
     // ===================== epilogue =====================
-    // Accumulator column n = 8 * (row in tile) + (pixel in row).  One "unit" (one TMEM load, one transpose) =
-    //   M = 128: 16 columns = 2 image rows x 8 px of the warp's 32 channels,
-    //   M = 64 : 32 columns = 4 image rows x 8 px of the warp's 16 channels (lanes 0..15 of the lane group),
-    // i.e. 512 values either way.  The epilogue is latency-bound (two warps per scheduler, dependent
-    // TMEM -> shared -> registers -> global chain per unit), so fewer, fatter units matter.
-    constexpr int kChGrp = M64 ? 16 : 32;      // channels per TMEM lane group
-    constexpr int kPitch = M64 ? 20 : 36;      // floats per pixel row of the transpose buffer
-    constexpr int kCols = M64 ? 32 : 16;       // accumulator columns per unit
-    constexpr int kUnitRows = kCols / 8;       // image rows per unit
-    constexpr int kPassStep = M64 ? 2 : 1;     // image rows between my pixel in pass 0 and in pass 1
-    constexpr bool kFrag = M64 && (F & F_HEAD) == 0;  // M = 64 accumulators read with the 16x256b shape
-    static_assert(kCols * kPitch <= kStageFloats, "transpose buffer");
-    const int ew = warp - 2;
-    const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
-    const int n_cgrp = 4 / rep;      // distinct channel groups along M
-    const int cgrp = lane_grp % n_cgrp;
-    const int replica = lane_grp / n_cgrp;
-    const int n_units = max(1, p.tile_h / kUnitRows);
-    const int upw = max(1, n_units / (2 * rep));              // units per warp
-    const int u_begin = ((ew >> 2) * rep + replica) * upw;    // first unit handled by this warp
-    float* stage = stage_all + ew * kStageFloats;
+    // the per-tile work is epi::epilogue_tile (conv_epilogue.cuh), shared with the dataflow kernel
+    float* stage = stage_all + (warp - 2) * kStageFloats;
+    const ChannelParams cp = {ep->bias, ep->mid_s, ep->mid_t, ep->pre_s, ep->pre_t, ep->post_s, ep->post_t};
     int acc = 0;
     uint32_t pacc = 0;
-    // HEAD: lane = channel -> one running (ordered value, ~index) pair per thread
-    uint32_t best_hi = 0u, best_lo = 0u;
-    int cur_img = -1;
-    const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
-    // channel-major role (TMEM load, bias, transpose store): lane = channel; M = 64 -> lanes 0..15 only.
-    // pixel-major role after the transpose, two passes per unit:
-    //   M = 128: lane -> (pixel column pj = lane/4, channels (lane%4)*8 .. +7), unit row ip in pass ip
-    //   M = 64 : lane -> (pixel column pj = (lane/2)%8, channels (lane%2)*8 .. +7), unit row lane/16 + 2*ip in pass ip
-    const bool cm_lane = !M64 || lane < 16;
-    const int pj = M64 ? ((lane >> 1) & 7) : (lane >> 2);
-    const int my_i = M64 ? (lane >> 4) : 0;
-    const int cq = M64 ? (lane & 1) * 8 : (lane & 3) * 8;
-    constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
-    // byte strides of one image row in every tensor the epilogue touches: an access of unit r, pass ip is then
-    // (per-tile base pointer) + (kUnitRows * r + kPassStep * ip) * stride with a compile-time row offset
-    const uint32_t rs_pre = static_cast<uint32_t>(s.w * e.pre_cs) * 2u, rs_res1 = static_cast<uint32_t>(s.w * e.res1_cs) * 2u;
-    const uint32_t rs_res2 = static_cast<uint32_t>(s.w * e.res2_cs) * 2u;
-    const uint32_t rs_up = static_cast<uint32_t>((s.w >> 1) * e.up_cs) * 2u;
-    // F_POOL: raw / post live at half resolution
-    const uint32_t rs_raw = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.raw_cs) * 2u;
-    const uint32_t rs_post = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.post_cs) * 2u;
-    // Residual inputs do not depend on the accumulator: they are fetched in BATCHES before they are needed -- all
-    // units of a tile while its MMAs still run when they fit in ~64 registers, else half of them then and the other
-    // half once the first are consumed.  (Loads issued one by one while earlier ones are being consumed do not work:
-    // the few hardware scoreboards are shared, so every use then waits for the newest load; measured.)
-    constexpr bool kHasRes = (F & (F_RES1 | F_RES2 | F_UP)) != 0;
-    constexpr int kMaxUpw = M64 ? 4 : 8;  // units per warp at N = 256
-    constexpr int kResRegs = 4 * (2 * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + (M64 ? 2 : 1) * ((F & F_UP) ? 1 : 0));
-    constexpr int kPref = !kHasRes ? 1 : (kResRegs * kMaxUpw <= 64 ? kMaxUpw : kMaxUpw / 2);  // units per batch
-    uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1][M64 ? 2 : 1];
+    ArgmaxState am;
+    EpiTrace tr;
+    tr.trace = trace; tr.t0 = t_kernel0; tr.on = warp == 2 && lane == 0;
     for (int t = t_begin; t < t_end; t += t_step) {
       const TileCoord tc = decode_tile(p, t);
-      const int m0 = tc.mt * kM;
-      const int c_lane = m0 + cgrp * kChGrp + lane;       // channel-major role: my output channel
-      const int c0 = m0 + cgrp * kChGrp + cq;             // pixel-major role: first of my 8 channels
-      const bool grp_active = m0 + cgrp * kChGrp < s.cout_pad;
-      const int y_first = tc.ty * p.tile_h + kUnitRows * u_begin;  // first image row handled by this warp
-      const bool rows_active = u_begin < n_units && y_first < s.h;
-      const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
-      const int xa = tc.tx * kTileW + pj;
-      const bool vx = ch_ok && xa < s.w;
-      // element index of my pixel in pass 0 of the first unit: (img, y_first + my_i, xa); 32-bit: pixel count x
-      // channel stride < 2^31 (checked in conv_plan)
-      const uint32_t pix0 = (static_cast<uint32_t>(tc.img) * s.h + y_first + my_i) * s.w + xa;
-      // element index of the half-resolution pixel (img, y_first/2, xa/2): F_POOL outputs, F_UP input
-      const uint32_t ppix0 = (static_cast<uint32_t>(tc.img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
-      if ((F & F_ARGMAX) && tc.img != cur_img) {
-        if (cur_img >= 0 && best_hi != 0u && cm_lane && c_lane < e.cout_real)
-          atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
-                    (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
-        best_hi = 0u; best_lo = 0u;
-        cur_img = tc.img;
-      }
-      // per-tile base pointers of my (pixel, 8 channels) in the first unit
-      const uint32_t opix0 = (F & F_POOL) ? ppix0 : pix0;
-      uint8_t* const b_pre = (F & F_PRE) ? reinterpret_cast<uint8_t*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(pix0) * e.pre_cs) : nullptr;
-      uint8_t* const b_raw = (F & F_RAW) ? reinterpret_cast<uint8_t*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>(opix0) * e.raw_cs) : nullptr;
-      uint8_t* const b_post = (F & F_POST) ? reinterpret_cast<uint8_t*>(e.out_post + e.post_co + c0 + static_cast<size_t>(opix0) * e.post_cs) : nullptr;
-      // rows at / below my first pixel that exist in the image (0 when my pixel column / channels do not):
-      // unit r, pass ip is valid iff kUnitRows * r + kPassStep * ip < n_rows_ok
-      const int n_rows_ok = vx ? s.h - y_first - my_i : 0;
-      const uint8_t* const b_res1 = (F & F_RES1) ? reinterpret_cast<const uint8_t*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix0) * e.res1_cs) : nullptr;
-      const uint8_t* const b_res2 = (F & F_RES2) ? reinterpret_cast<const uint8_t*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix0) * e.res2_cs) : nullptr;
-      const uint8_t* const b_up = (F & F_UP) ? reinterpret_cast<const uint8_t*>(e.res_up + e.up_co + c0 + static_cast<size_t>(ppix0) * e.up_cs) : nullptr;
-      auto prefetch_batch = [&](int u0) {  // units u0 .. u0 + kPref - 1 (u0 compile-time after unrolling)
-#pragma unroll
-        for (int q = 0; q < kPref; ++q) {
-          const int u = u0 + q;
-          if (u < upw) {
-#pragma unroll
-            for (int ip = 0; ip < 2; ++ip) {
-              const int row = kUnitRows * u + kPassStep * ip;
-              if (row < n_rows_ok) {
-                if (F & F_RES1) r1[q][ip] = *reinterpret_cast<const uint4*>(b_res1 + static_cast<size_t>(row * rs_res1));
-                if (F & F_RES2) r2[q][ip] = *reinterpret_cast<const uint4*>(b_res2 + static_cast<size_t>(row * rs_res2));
-                // nearest x2: rows 2k, 2k+1 and columns xa, xa^1 all read low-res pixel (k, xa/2);
-                // M = 128: both passes share one low-res row per unit, M = 64: pass ip reads low-res row 2u + ip
-                if ((F & F_UP) && (M64 || ip == 0))
-                  ru[q][M64 ? ip : 0] = *reinterpret_cast<const uint4*>(b_up + static_cast<size_t>((row >> 1) * rs_up));
-              }
-            }
-          }
-        }
-      };
-      if (kHasRes && grp_active && rows_active) prefetch_batch(0);
-      // per-channel parameters of my 8 channels (pixel-major role) and my channel (channel-major role)
-      float pre_s[8], pre_t[8], post_s[8], post_t[8];
-      if (F & F_PRE) { lds8(ep->pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep->pre_t + (ch_ok ? c0 : 0), pre_t); }
-      if (F & F_POST) { lds8(ep->post_s + (ch_ok ? c0 : 0), post_s); lds8(ep->post_t + (ch_ok ? c0 : 0), post_t); }
-      const float bias_c = ep->bias[c_lane < kMaxCout ? c_lane : 0];
-      const float mid_s_c = ep->mid_s[c_lane < kMaxCout ? c_lane : 0], mid_t_c = ep->mid_t[c_lane < kMaxCout ? c_lane : 0];
-      timed_wait(&bar->t_full[acc], pacc, prof, w0);
-      ptx::tc_fence_after();
-      if (warp == 2 && lane == 0) MVLM_TRACE(5);
-      if (grp_active && rows_active) {
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
-                               static_cast<uint32_t>(acc * 256 + u_begin * kCols);
-        // one register buffer: the load of unit r+1 is issued as soon as unit r has left the registers
-        // M = 64 without channel-major consumers: the 16 data lanes of the lane group are read with the 16x256b shape,
-        // which spreads them over all 32 threads (2 channels x 16 pixels each): half the registers and, above all,
-        // full 32-lane transpose stores -- the shared-memory pipe is what bounds these layers
-        uint32_t vr[kFrag ? 16 : kCols];
-        auto tmem_load = [&](int u) {
-          if constexpr (kFrag) ptx::tmem_ld_16x256b_x4(taddr + u * kCols, vr);
-          else if constexpr (M64) ptx::tmem_ld32(taddr + u * kCols, vr);
-          else ptx::tmem_ld16(taddr + u * kCols, vr);
-        };
-        tmem_load(0);
-#pragma unroll
-        for (int r = 0; r < kMaxUpw; ++r) {
-          if (r < upw) {
-            if (kHasRes && kPref < kMaxUpw && r == kPref) prefetch_batch(kPref);  // second batch
-            const int y = y_first + kUnitRows * r;  // first image row of the unit
-            ptx::tmem_ld_wait();
-            if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(8 + 4 * r);
-            if (y < s.h) {
-              if (F & F_HEAD) {
-                // channel-major consumers: lane = channel c_lane, vr[j] = pixel (y + j/8, x0 + j%8)
-                const int x0 = tc.tx * kTileW;
-                const int nvx = s.w - x0;  // >= 8 for interior tiles
-                if (cm_lane && c_lane < e.cout_real) {
-#pragma unroll
-                  for (int i = 0; i < kUnitRows; ++i) {
-                    if (y + i < s.h) {
-                      const int oy = (y + i) * e.up_sy + e.up_py;
-                      const uint32_t idx0 = static_cast<uint32_t>(oy * ow + x0 * e.up_sx + e.up_px);
-                      if (F & F_ARGMAX) {
-                        // first maximum of the row's 8 pixels by a tournament over ordered keys (pixel index grows
-                        // with j, so "the later one only if strictly greater" keeps the first), then ONE merge with
-                        // the running best: a serial compare-select chain per pixel made this epilogue latency-bound
-                        uint32_t k8[8];
-                        uint32_t j8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                          k8[j] = j < nvx ? order_f32(__uint_as_float(vr[8 * i + j]) + bias_c) : 0u;
-                          j8[j] = static_cast<uint32_t>(j);
-                        }
-#pragma unroll
-                        for (int st = 1; st < 8; st *= 2) {
-#pragma unroll
-                          for (int j = 0; j < 8; j += 2 * st) {
-                            const bool take = k8[j + st] > k8[j];
-                            k8[j] = take ? k8[j + st] : k8[j];
-                            j8[j] = take ? j8[j + st] : j8[j];
-                          }
-                        }
-                        const uint32_t lo = 0xFFFFFFFFu - (idx0 + j8[0] * static_cast<uint32_t>(e.up_sx));
-                        if (k8[0] > best_hi || (k8[0] == best_hi && lo > best_lo)) {
-                          best_hi = k8[0];
-                          best_lo = lo;
-                        }
-                      }
-                      if (F & F_F32) {
-                        float* dst = e.out_f32 + (static_cast<size_t>(tc.img) * e.cout_real + c_lane) * oh * ow + idx0;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                          if (j < nvx) dst[j * e.up_sx] = __uint_as_float(vr[8 * i + j]) + bias_c;
-                      }
-                    }
-                  }
-                }
-              }
-              if (kBf16Out) {
-                // bias in the channel-major role (one register), then transpose the unit through shared memory:
-                // row = pixel, 36 (20)-float pitch (conflict-free STS.32; LDS.128 conflict-free at 36)
-                __syncwarp();
-                if constexpr (kFrag) {
-                  // register 4k + 2h + e = (channel lane/4 + 8h, pixel 8k + 2(lane%4) + e); conflict-free at pitch 20
-                  const int cb = m0 + cgrp * kChGrp + (lane >> 2);
-                  const int p0 = 2 * (lane & 3);
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    const int ch = (cb + 8 * h) < kMaxCout ? cb + 8 * h : 0;
-                    const float bias_h = ep->bias[ch];
-                    const float ms = (F & F_MID) ? ep->mid_s[ch] : 1.f, mt_ = (F & F_MID) ? ep->mid_t[ch] : 0.f;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                      for (int e2 = 0; e2 < 2; ++e2) {
-                        float f = __uint_as_float(vr[4 * k + 2 * h + e2]) + bias_h;
-                        if (F & F_MID) f = fmaxf(fmaf(f, ms, mt_), 0.f);
-                        stage[(8 * k + p0 + e2) * kPitch + (lane >> 2) + 8 * h] = f;
-                      }
-                    }
-                  }
-                } else if (cm_lane) {
-#pragma unroll
-                  for (int j = 0; j < kCols; ++j) {
-                    float f = __uint_as_float(vr[j]) + bias_c;
-                    if (F & F_MID) f = fmaxf(fmaf(f, mid_s_c, mid_t_c), 0.f);
-                    stage[j * kPitch + lane] = f;
-                  }
-                }
-              }
-            }
-            if (r + 1 < upw) tmem_load(r + 1);  // next unit in flight while this one is post-processed
-            if (y < s.h) {
-              if (kBf16Out) {
-                __syncwarp();
-                if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(9 + 4 * r);
-                uint4 pool_cur[2];
-#pragma unroll
-                for (int ip = 0; ip < 2; ++ip) {
-                  const int row = kUnitRows * r + kPassStep * ip;  // my image row in this pass, relative to my first
-                  const bool valid = row < n_rows_ok;
-                  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                  if (valid) {
-                    lds8(stage + (pj + 8 * (my_i + kPassStep * ip)) * kPitch + cq, f);
-                    if (F & F_PRE)
-                      *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>(row * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
-                    if (F & F_RES1) add8(r1[r % kPref][ip], f);
-                    if (F & F_RES2) add8(r2[r % kPref][ip], f);
-                    if (F & F_UP) add8(ru[r % kPref][M64 ? ip : 0], f);
-                  }
-                  if (F & F_POOL) {
-                    pool_cur[ip] = pack8(f);
-                  } else if (valid) {
-                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(row * rs_raw)) = pack8(f);
-                    if (F & F_POST)
-                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(row * rs_post)) = affine_relu_pack8(f, post_s, post_t);
-                  }
-                }
-                if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(10 + 4 * r);
-                if (F & F_POOL) {
-                  // 2x2 max-pool of the bf16-rounded values; shuffles run on all lanes.
-                  //   M = 128: vertical partner = my other pass, horizontal (pixel column pj ^ 1) = lane ^ 4,
-                  //            one pooled row per unit;
-                  //   M = 64 : vertical partner = lane ^ 16 (same pass), horizontal = lane ^ 2, pass ip is pooled row
-                  //            2r + ip of my part of the tile.
-#pragma unroll
-                  for (int pp = 0; pp < (M64 ? 2 : 1); ++pp) {
-                    uint4 m = pool_cur[pp];
-                    if (M64) {
-                      uint4 o;
-                      o.x = __shfl_xor_sync(0xffffffffu, m.x, 16);
-                      o.y = __shfl_xor_sync(0xffffffffu, m.y, 16);
-                      o.z = __shfl_xor_sync(0xffffffffu, m.z, 16);
-                      o.w = __shfl_xor_sync(0xffffffffu, m.w, 16);
-                      m = max_bf16x8(m, o);
-                    } else {
-                      m = max_bf16x8(m, pool_cur[1]);
-                    }
-                    uint4 o;
-                    o.x = __shfl_xor_sync(0xffffffffu, m.x, M64 ? 2 : 4);
-                    o.y = __shfl_xor_sync(0xffffffffu, m.y, M64 ? 2 : 4);
-                    o.z = __shfl_xor_sync(0xffffffffu, m.z, M64 ? 2 : 4);
-                    o.w = __shfl_xor_sync(0xffffffffu, m.w, M64 ? 2 : 4);
-                    m = max_bf16x8(m, o);
-                    // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
-                    const int prow = (kUnitRows / 2) * r + pp;  // pooled row relative to y_first / 2
-                    if (2 * prow < n_rows_ok && my_i == 0 && (pj & 1) == 0) {
-                      if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(prow * rs_raw)) = m;
-                      if (F & F_POST) {
-                        float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        add8(m, g);
-                        *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(prow * rs_post)) = affine_relu_pack8(g, post_s, post_t);
-                      }
-                    }
-                  }
-                }
-                if (r < 2 && warp == 2 && lane == 0) MVLM_TRACE(11 + 4 * r);
-              }
-            }
-          }
-        }
-      }
+      const ImageSlots is = {tc.img, tc.img, tc.img, tc.img, tc.img, tc.img};
+      tr.trace_i = trace_i;
+      epilogue_tile<F, false>(s, e, p.tile_h, cp, tc, is, &bar->t_full[acc], pacc,
+                              tmem_base + static_cast<uint32_t>(acc * 256), stage, warp, lane, am, prof, w0, tr);
       // all tcgen05.ld of this accumulator stage have completed (wait::ld above)
       ptx::tc_fence_before();
       __syncwarp();
@@ -682,12 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       ++trace_i;
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    if ((F & F_ARGMAX) && cur_img >= 0 && best_hi != 0u) {
-      const int c_lane = cgrp * kChGrp + lane;  // arg-max convs have a single M tile
-      if (cm_lane && c_lane < e.cout_real)
-        atomicMax(e.argmax_keys + static_cast<size_t>(cur_img) * e.cout_real + c_lane,
-                  (static_cast<unsigned long long>(best_hi) << 32) | best_lo);
-    }
+    epilogue_argmax_flush<F>(s, e, warp, lane, am);
     if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = w0; p.prof[blockIdx.x * 8 + 6] = clock64() - t_kernel0; }
   }
 
@@ -722,12 +360,16 @@ const bool g_pdl = getenv("MVLM_CONV_NO_PDL") == nullptr;
 
 template <int F>
 int launch_t(const ConvParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device (and per kernel instantiation): one flag per device ordinal
+  static std::atomic<bool> configured[kMaxDevices];
+  int dev = 0;
+  MVLM_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev].load(std::memory_order_acquire)) {
     MVLM_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
   }
-  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  const int n_sms = sm_count();
+  const int grid = p.total_tiles < n_sms ? p.total_tiles : n_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);

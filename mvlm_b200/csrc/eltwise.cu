@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) bn_relu_kernel(const uint4* __restrict__ 
 
 inline int grid_for(size_t total) {
   const size_t b = (total + 255) / 256;
-  const size_t cap = static_cast<size_t>(kNumSMs) * 16;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
   return static_cast<int>(b < cap ? (b ? b : 1) : cap);
 }
 

@@ -17,6 +17,9 @@
 #include "hourglass.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 namespace mvlm {
 
@@ -115,6 +118,18 @@ void* HourglassNet::ws_alloc(size_t bytes) {
   return p;
 }
 
+void HourglassNet::push_op(const NetOp& op) {
+  ops_.push_back(op);
+  op_seg_.push_back(cur_seg_);
+}
+
+void HourglassNet::seg_begin(int res) {
+  if (cur_seg_ >= 0 || !flow_on_ || res < flow_min_h_ || res < 32) return;
+  cur_seg_ = n_segs_++;
+}
+
+void HourglassNet::seg_end() { cur_seg_ = -1; }
+
 HourglassNet::T HourglassNet::alloc(int h, int w, int c) {
   T t;
   t.h = h; t.w = w; t.c = c;
@@ -132,6 +147,17 @@ HourglassNet::T HourglassNet::scratch(int h, int w, int c, int slot) {
   return t;
 }
 
+int HourglassNet::sd_get(const std::string& name, long long numel, const float** out) const {
+  auto f = sd_->find(name);
+  MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s", name.c_str());
+  MVLM_REQUIRE(f->second.p != nullptr, "hourglass: null tensor for state_dict key %s", name.c_str());
+  MVLM_REQUIRE(f->second.numel < 0 || f->second.numel == numel,
+               "hourglass: size mismatch for %s: the checkpoint has %lld elements, this model (%d landmarks, %d image "
+               "channels) needs %lld", name.c_str(), f->second.numel, L_, cin_, numel);
+  *out = f->second.p;
+  return MVLM_OK;
+}
+
 int HourglassNet::bn(const std::string& name, int c, const float** scale, const float** shift) {
   *scale = *shift = nullptr;
   if (dry_) return MVLM_OK;
@@ -140,9 +166,8 @@ int HourglassNet::bn(const std::string& name, int c, const float** scale, const 
     const char* suffix[4] = {".weight", ".bias", ".running_mean", ".running_var"};
     const float* src[4];
     for (int k = 0; k < 4; ++k) {
-      auto f = sd_->find(name + suffix[k]);
-      MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s%s", name.c_str(), suffix[k]);
-      src[k] = f->second;
+      const int rc = sd_get(name + suffix[k], c, &src[k]);
+      if (rc) return rc;
     }
     float* buf = nullptr;
     MVLM_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * 2 * c));
@@ -160,13 +185,14 @@ int HourglassNet::packed(const std::string& name, int cout, int cin, int k, int 
                          const __nv_bfloat16** out) {
   *out = nullptr;
   if (dry_) return MVLM_OK;
-  auto f = sd_->find(name);
-  MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s", name.c_str());
+  const float* src = nullptr;
+  const int rc = sd_get(name, 1ll * cout * cin * k * k, &src);
+  if (rc) return rc;
   __nv_bfloat16* buf = nullptr;
   const size_t n = static_cast<size_t>(cout_pad) * k * k * cin_pad;
   MVLM_CHECK_CUDA(cudaMalloc(&buf, n * sizeof(__nv_bfloat16)));
   owned_.push_back(buf);
-  pack_weight_kernel<<<256, 256>>>(f->second, cout, cin, k, cout_pad, cin_pad, buf);
+  pack_weight_kernel<<<256, 256>>>(src, cout, cin, k, cout_pad, cin_pad, buf);
   MVLM_CHECK_CUDA(cudaGetLastError());
   *out = buf;
   return MVLM_OK;
@@ -175,12 +201,13 @@ int HourglassNet::packed(const std::string& name, int cout, int cin, int k, int 
 int HourglassNet::bias(const std::string& name, int cout, int cout_pad, const float** out) {
   *out = nullptr;
   if (dry_) return MVLM_OK;
-  auto f = sd_->find(name);
-  MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s", name.c_str());
+  const float* src = nullptr;
+  const int rc = sd_get(name, cout, &src);
+  if (rc) return rc;
   float* buf = nullptr;
   MVLM_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * cout_pad));
   owned_.push_back(buf);
-  pad_bias_kernel<<<ceil_div(cout_pad, 128), 128>>>(f->second, cout, cout_pad, buf);
+  pad_bias_kernel<<<ceil_div(cout_pad, 128), 128>>>(src, cout, cout_pad, buf);
   MVLM_CHECK_CUDA(cudaGetLastError());
   *out = buf;
   return MVLM_OK;
@@ -209,7 +236,7 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
     rc = conv_plan(s, e, &op.conv);
     if (rc) return rc;
   }
-  ops_.push_back(op);
+  push_op(op);
   return MVLM_OK;
 }
 
@@ -277,7 +304,7 @@ int HourglassNet::emit_pool(T in, T out_raw, const char* bn_name, T out_act) {
     int rc = bn(bn_name, in.c, &op.scale, &op.shift);
     if (rc) return rc;
   }
-  ops_.push_back(op);
+  push_op(op);
   return MVLM_OK;
 }
 
@@ -295,14 +322,19 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
   for (int lvl = 0; lvl < 5; ++lvl) {
     const std::string lb = p + ".rb" + std::to_string(low_blocks[lvl]);
     T pooled = alloc(cur.h / 2, cur.w / 2, F), a = alloc(cur.h / 2, cur.w / 2, F);
+    // the pool closes the dataflow segment of the level above (it reads that level's output); the level's own
+    // down-path block opens the next one
     rc = emit_pool(cur, pooled, (lb + ".bn1").c_str(), a);
     if (rc) return rc;
+    seg_end();
+    seg_begin(pooled.h);
     const int nxt = lvl < 4 ? skip_blocks[lvl] : 11;
     const std::string post = p + ".rb" + std::to_string(nxt) + ".bn1";
     rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_lows[lvl], &lows[lvl]);
     if (rc) return rc;
     cur = lows[lvl];
   }
+  seg_end();
   T low2, a2, low3;
   rc = rb(p + ".rb11", cur, a_lows[4], none, F, F, (p + ".rb12.bn1").c_str(), &a2, &low2);
   if (rc) return rc;
@@ -315,6 +347,7 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
     const std::string b1 = p + ".rb" + std::to_string(ups[lvl][0]);
     const std::string b2 = p + ".rb" + std::to_string(ups[lvl][1]);
     T s, a;
+    seg_begin(lows[3 - lvl].h);  // skip block + the two up-path blocks of one level
     rc = rb(sb, lows[3 - lvl], a_lows[3 - lvl], none, F, F, (b1 + ".bn1").c_str(), &a, &s, nullptr, &cur);
     if (rc) return rc;
     T l1, a1, l2;
@@ -322,8 +355,11 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
     if (rc) return rc;
     rc = rb(b2, l1, a1, none, F, F, nullptr, nullptr, &l2);
     if (rc) return rc;
+    seg_end();
     cur = l2;
   }
+  // rb1 opens the segment of the full-resolution trunk that follows the hourglass (closed by the caller)
+  seg_begin(x.h);
   T add5;
   rc = rb(p + ".rb1", x, a_x, none, F, F, nullptr, nullptr, &add5, nullptr, &cur);
   if (rc) return rc;
@@ -331,7 +367,7 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
   return MVLM_OK;
 }
 
-int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_landmarks, int cin, int n_views, int h,
+int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_views, int h,
                         int w, void* workspace, size_t workspace_bytes, bool dry) {
   MVLM_REQUIRE(n_landmarks > 0 && n_landmarks <= 128, "hourglass: n_landmarks=%d unsupported", n_landmarks);
   MVLM_REQUIRE(cin >= 1 && cin <= 4, "hourglass: image channels=%d unsupported", cin);
@@ -346,6 +382,12 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
   if (Lp_ == 16) Lp_ = 32;
   ws_ = static_cast<uint8_t*>(workspace); ws_size_ = workspace_bytes; ws_off_ = 0;
   ops_.clear(); flops_ = 0.0;
+  op_seg_.clear(); segs_.clear(); seg_info_.clear(); cur_seg_ = -1; n_segs_ = 0;
+  // experiment knobs of the dataflow plan (defaults in hourglass.cuh)
+  if (const char* v = getenv("MVLM_FLOW")) flow_on_ = atoi(v) != 0;
+  if (const char* v = getenv("MVLM_FLOW_MIN_H")) flow_min_h_ = std::max(32, atoi(v));
+  if (const char* v = getenv("MVLM_FLOW_TILES")) flow_tiles_ = std::max(1, atoi(v));
+  if (const char* v = getenv("MVLM_FLOW_K")) flow_interleave_ = std::max(1, atoi(v));
   int rc;
   const int F = 256, h2 = h / 2, w2 = w / 2;
 
@@ -357,18 +399,19 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
     NetOp op;
     op.kind = NetOp::STEM;
     op.out_raw = img16.p; op.h = h; op.w = w; op.c = cin;
-    ops_.push_back(op);
+    push_op(op);
     flops_ += 2.0 * 64 * cin * 9 * h * w;
+    seg_begin(h2);  // trunk segment: conv1 .. conv4 block and the first hourglass's first pool
     NetOp cv;
     cv.kind = NetOp::CONV;
     cv.tag = "conv1";
     if (!dry_) {
-      auto fw = sd_->find("conv1.weight");
-      MVLM_REQUIRE(fw != sd_->end(), "hourglass: missing conv1.weight");
+      const float* w1 = nullptr;
+      if ((rc = sd_get("conv1.weight", 64ll * cin * 9, &w1))) return rc;
       __nv_bfloat16* wp = nullptr;
       MVLM_CHECK_CUDA(cudaMalloc(&wp, sizeof(__nv_bfloat16) * 64 * 9 * 16));
       owned_.push_back(wp);
-      pack_stem_weight_kernel<<<36, 256>>>(fw->second, 64, cin, 64, wp);
+      pack_stem_weight_kernel<<<36, 256>>>(w1, 64, cin, 64, wp);
       MVLM_CHECK_CUDA(cudaGetLastError());
       ConvShape s;
       s.in = img16.p; s.n = V_; s.h = h; s.w = w; s.cin = 16; s.in_cs = 16;
@@ -382,7 +425,7 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
       e.out_post = ar_c2.p; e.post_cs = 64; e.post_co = 0;
       if ((rc = conv_plan(s, e, &cv.conv))) return rc;
     }
-    ops_.push_back(cv);
+    push_op(cv);
   }
   T none, y2, y3, r3, a3, a4, a_h1, ar4;
   // conv2 block: its output is only consumed through the max-pool (:411) -> pooled outputs straight from the epilogues
@@ -397,7 +440,7 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
     op.kind = NetOp::BNRELU;
     op.in0 = y3.p; op.out_act = ar4.p; op.h = h2; op.w = w2; op.c = 128;
     if ((rc = bn("conv4.resample.0", 128, &op.scale, &op.shift))) return rc;
-    ops_.push_back(op);
+    push_op(op);
   }
   if ((rc = rb("conv4", y3, a4, ar4, 128, F, "hg1.rb1.bn1", &a_h1, &r3))) return rc;
   probes["r3"] = {r3.p, r3.h, r3.w, r3.c};
@@ -447,13 +490,14 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
     if ((rc = emit_conv("conv10", ll2, F, "conv10", L_, Lp_, Lp_, 3, e, true))) return rc;
   }
   probes["x10"] = {x10.p, x10.h, x10.w, x10.c};
+  seg_end();
   // ---- conv11 on nearest-x2(conv10) (:428-429) as four 2x2 phase convs with fused arg-max
   keys_ = static_cast<unsigned long long*>(ws_alloc(sizeof(unsigned long long) * V_ * L_));
   {
     NetOp op;
     op.kind = NetOp::MEMSET;
     op.ptr = keys_; op.bytes = sizeof(unsigned long long) * V_ * L_;
-    ops_.push_back(op);
+    push_op(op);
   }
   flops_ += 2.0 * L_ * L_ * 9 * h * w;  // algorithmic FLOPs of the reference's conv11
   const float* b11 = nullptr;
@@ -465,12 +509,12 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
       op.is_head = true;
       op.tag = "conv11.phase";
       if (!dry_) {
-        auto f = sd_->find("conv11.weight");
-        MVLM_REQUIRE(f != sd_->end(), "hourglass: missing conv11.weight");
+        const float* w11 = nullptr;
+        if ((rc = sd_get("conv11.weight", 9ll * L_ * L_, &w11))) return rc;
         __nv_bfloat16* wp = nullptr;
         MVLM_CHECK_CUDA(cudaMalloc(&wp, sizeof(__nv_bfloat16) * Lp_ * 4 * Lp_));
         owned_.push_back(wp);
-        pack_phase_weight_kernel<<<64, 256>>>(f->second, L_, L_, a, b, Lp_, Lp_, wp);
+        pack_phase_weight_kernel<<<64, 256>>>(w11, L_, L_, a, b, Lp_, Lp_, wp);
         MVLM_CHECK_CUDA(cudaGetLastError());
         ConvShape s;
         s.in = x10.p; s.n = V_; s.h = h2; s.w = w2; s.cin = Lp_; s.in_cs = Lp_;
@@ -483,17 +527,80 @@ int HourglassNet::build(const std::map<std::string, const float*>* sd, int n_lan
         e.up_sy = 2; e.up_sx = 2; e.up_py = a; e.up_px = b;
         if ((rc = conv_plan(s, e, &op.conv))) return rc;
       }
-      ops_.push_back(op);
+      push_op(op);
     }
   }
   {
     NetOp op;
     op.kind = NetOp::PEAKS;
-    ops_.push_back(op);
+    push_op(op);
   }
   if (!dry_) {
     MVLM_REQUIRE(ws_off_ <= ws_size_, "hourglass: workspace too small (%zu needed, %zu given)", ws_off_, ws_size_);
+    if ((rc = build_segments())) return rc;
     MVLM_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  return MVLM_OK;
+}
+
+int HourglassNet::build_segments() {
+  segs_.assign(n_segs_, FlowSegment());
+  seg_info_.assign(n_segs_, SegInfo());
+  if (n_segs_ == 0) return MVLM_OK;
+  {
+    std::vector<float> host(2 * epi::kMaxCout, 0.f);
+    for (int i = 0; i < epi::kMaxCout; ++i) host[epi::kMaxCout + i] = 1.f;
+    MVLM_CHECK_CUDA(cudaMalloc(&zeros_, sizeof(float) * host.size()));
+    owned_.push_back(zeros_);
+    ones_ = zeros_ + epi::kMaxCout;
+    MVLM_CHECK_CUDA(cudaMemcpy(zeros_, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
+  }
+  for (int sgm = 0; sgm < n_segs_; ++sgm) {
+    std::vector<FlowLayerDesc> layers;
+    int min_tiles = 1 << 30;
+    for (size_t i = 0; i < ops_.size(); ++i) {
+      if (op_seg_[i] != sgm) continue;
+      if (seg_info_[sgm].first_op < 0) seg_info_[sgm].first_op = static_cast<int>(i);
+      const NetOp& op = ops_[i];
+      FlowLayerDesc d;
+      memset(&d.layer, 0, sizeof(d.layer));
+      FlowLayer& L = d.layer;
+      L.ring_in = L.ring_pre = L.ring_raw = L.ring_post = L.ring_res1 = L.ring_res2 = L.ring_up = V_;
+      L.cp = {zeros_, ones_, zeros_, zeros_, zeros_, zeros_, zeros_};
+      if (op.kind == NetOp::CONV) {
+        MVLM_REQUIRE(!op.is_head, "hourglass: head conv inside a dataflow segment");
+        L.p = op.conv;
+        L.kind = FLOW_CONV;
+        const ConvEpilogue& e = op.conv.e;
+        L.f = epi::feature_mask(e) | (op.conv.s.cout_pad <= 64 ? epi::F_M64 : 0);
+        if (e.bias) L.cp.bias = e.bias;
+        if (e.mid_scale) { L.cp.mid_s = e.mid_scale; L.cp.mid_t = e.mid_shift; }
+        if (e.out_pre) { L.cp.pre_s = e.pre_scale; L.cp.pre_t = e.pre_shift; }
+        if (e.out_post) { L.cp.post_s = e.post_scale; L.cp.post_t = e.post_shift; }
+        d.tiles_x = op.conv.tiles_x; d.tiles_y = op.conv.tiles_y; d.n_nt = op.conv.n_nt;
+        min_tiles = std::min(min_tiles, d.tiles_x * d.tiles_y * d.n_nt);
+      } else if (op.kind == NetOp::POOL || op.kind == NetOp::BNRELU) {
+        const bool pool = op.kind == NetOp::POOL;
+        L.kind = pool ? FLOW_POOL : FLOW_BNRELU;
+        L.p.s.in = op.in0; L.p.s.n = V_; L.p.s.h = op.h; L.p.s.w = op.w; L.p.s.cin = op.c; L.p.s.in_cs = op.c;
+        L.p.e.out_raw = op.out_raw;
+        L.p.e.out_post = op.out_act;
+        if (op.out_act) { L.cp.post_s = op.scale; L.cp.post_t = op.shift; }
+        L.p.tile_h = epi::kMaxTileH;
+        d.tiles_x = ceil_div(pool ? op.w / 2 : op.w, epi::kTileW);
+        d.tiles_y = ceil_div(pool ? op.h / 2 : op.h, epi::kMaxTileH);
+        d.n_nt = 1;
+      } else {
+        MVLM_REQUIRE(false, "hourglass: op kind %d cannot run inside a dataflow segment", static_cast<int>(op.kind));
+      }
+      layers.push_back(d);
+    }
+    MVLM_REQUIRE(!layers.empty() && min_tiles < (1 << 30), "hourglass: empty dataflow segment %d", sgm);
+    const int batch = std::min(V_, ceil_div(flow_tiles_, min_tiles));
+    seg_info_[sgm].batch = batch;
+    seg_info_[sgm].n_layers = static_cast<int>(layers.size());
+    const int rc = flow_build_segment(layers, V_, batch, flow_interleave_, &owned_, &segs_[sgm]);
+    if (rc) return rc;
   }
   return MVLM_OK;
 }
@@ -528,10 +635,20 @@ int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, flo
                           cudaStream_t stream) {
   MVLM_REQUIRE(!dry_, "hourglass: forward on a dry plan");
   MVLM_REQUIRE(out_peaks || out_heatmaps, "hourglass: no output requested");
-  for (NetOp& op : ops_) {
-    const int rc = run_op(op, img_u8, img_f32, out_heatmaps, out_peaks, stream);
+  for (size_t i = 0; i < ops_.size(); ++i) {
+    const int rc = run_step(i, img_u8, img_f32, out_heatmaps, out_peaks, stream);
     if (rc != MVLM_OK) return rc;
   }
+  return MVLM_OK;
+}
+
+// op i as the plan executes it: the first op of a dataflow segment launches the whole segment, its other ops
+// are part of that launch
+int HourglassNet::run_step(size_t i, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps,
+                           float* out_peaks, cudaStream_t stream) {
+  const int sgm = op_seg_[i];
+  if (sgm < 0) return run_op(ops_[i], img_u8, img_f32, out_heatmaps, out_peaks, stream);
+  if (seg_info_[sgm].first_op == static_cast<int>(i)) return flow_launch(segs_[sgm], stream);
   return MVLM_OK;
 }
 
@@ -547,7 +664,7 @@ int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32,
   for (int r = 0; r < reps && rc == MVLM_OK; ++r) {
     MVLM_CHECK_CUDA(cudaEventRecord(ev[0], stream));
     for (size_t i = 0; i < n && rc == MVLM_OK; ++i) {
-      rc = run_op(ops_[i], img_u8, img_f32, nullptr, out_peaks, stream);
+      rc = run_step(i, img_u8, img_f32, nullptr, out_peaks, stream);
       MVLM_CHECK_CUDA(cudaEventRecord(ev[i + 1], stream));
     }
     MVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -565,6 +682,10 @@ int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32,
     std::vector<long long> host(kConvProfInts);
     for (size_t i = 0; i < n && rc == MVLM_OK; ++i) {
       for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] = 0.0;
+      if (op_seg_[i] >= 0) {  // dataflow segments carry no role counters
+        rc = run_step(i, img_u8, img_f32, nullptr, out_peaks, stream);
+        continue;
+      }
       if (ops_[i].kind == NetOp::CONV) {
         MVLM_CHECK_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * kConvProfInts, stream));
         conv_set_profile_buffer(dev);
@@ -594,17 +715,24 @@ std::string HourglassNet::describe_op(int i) const {
   if (i < 0 || i >= static_cast<int>(ops_.size())) return "";
   const NetOp& op = ops_[i];
   char buf[256];
+  if (op_seg_[i] >= 0 && seg_info_.size() > static_cast<size_t>(op_seg_[i]) && seg_info_[op_seg_[i]].first_op == i) {
+    const SegInfo& si = seg_info_[op_seg_[i]];
+    snprintf(buf, sizeof(buf), "flow segment %d: %d layers, %d view(s) per batch, %d batches in lock step, %d items",
+             op_seg_[i], si.n_layers, si.batch, flow_interleave_, segs_[op_seg_[i]].n_items);
+    return buf;
+  }
+  const char* in_seg = op_seg_[i] >= 0 ? "  (in segment) " : "";
   switch (op.kind) {
     case NetOp::CONV: {
       const ConvShape& s = op.conv.s;
       const ConvEpilogue& e = op.conv.e;
-      snprintf(buf, sizeof(buf), "conv %s %dx%d %d->%d k%d%s%s%s%s%s%s%s%s", op.tag, s.h, s.w, s.cin, s.cout_pad, s.kh,
+      snprintf(buf, sizeof(buf), "%sconv %s %dx%d %d->%d k%d%s%s%s%s%s%s%s%s", in_seg, op.tag, s.h, s.w, s.cin, s.cout_pad, s.kh,
                e.out_pre ? " pre" : "", e.res1 ? " res1" : "", e.res2 ? " res2" : "", e.res_up ? " up" : "", e.out_raw ? " raw" : "",
                e.out_post ? " post" : "", e.pool2 ? " pool" : "", e.argmax_keys ? " argmax" : "");
       break;
     }
-    case NetOp::POOL: snprintf(buf, sizeof(buf), "pool %dx%dx%d", op.h, op.w, op.c); break;
-    case NetOp::BNRELU: snprintf(buf, sizeof(buf), "bnrelu %dx%dx%d", op.h, op.w, op.c); break;
+    case NetOp::POOL: snprintf(buf, sizeof(buf), "%spool %dx%dx%d", in_seg, op.h, op.w, op.c); break;
+    case NetOp::BNRELU: snprintf(buf, sizeof(buf), "%sbnrelu %dx%dx%d", in_seg, op.h, op.w, op.c); break;
     case NetOp::STEM: snprintf(buf, sizeof(buf), "stem-stage %dx%dx%d", op.h, op.w, op.c); break;
     case NetOp::MEMSET: snprintf(buf, sizeof(buf), "memset %zu", op.bytes); break;
     case NetOp::PEAKS: snprintf(buf, sizeof(buf), "peaks"); break;

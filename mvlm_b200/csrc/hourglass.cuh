@@ -4,10 +4,18 @@
 #include <string>
 #include <vector>
 
+#include "conv_flow.cuh"
 #include "conv_umma.cuh"
 #include "stages.cuh"
 
 namespace mvlm {
+
+// one state_dict entry: fp32 device tensor + its element count (checked against the layer's shape)
+struct SdEntry {
+  const float* p = nullptr;
+  long long numel = -1;  // -1: unknown (not checked)
+};
+typedef std::map<std::string, SdEntry> StateDict;
 
 struct NetOp {
   enum Kind { CONV, POOL, BNRELU, STEM, MEMSET, PEAKS } kind;  // STEM = image -> hi/lo bf16 staging
@@ -31,12 +39,14 @@ class HourglassNet {
   HourglassNet() = default;
   ~HourglassNet();
   // dry == true: only computes the workspace size (no CUDA calls).
-  int build(const std::map<std::string, const float*>* sd, int n_landmarks, int cin, int n_views, int h, int w,
+  int build(const StateDict* sd, int n_landmarks, int cin, int n_views, int h, int w,
             void* workspace, size_t workspace_bytes, bool dry);
   int forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
               cudaStream_t stream);
   int run_op(NetOp& op, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
              cudaStream_t stream);
+  int run_step(size_t i, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
+               cudaStream_t stream);
   // Captures the launch sequence of forward() into a CUDA graph per distinct argument tuple and replays it
   // (the plan is static: ~155 launches per call).  Falls back to plain launches if capture is unavailable.
   int forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
@@ -57,6 +67,7 @@ class HourglassNet {
   int width() const { return W_; }
   double flops_per_view() const { return flops_; }
   int n_ops() const { return static_cast<int>(ops_.size()); }
+  int n_segments() const { return n_segs_; }
   const std::vector<NetOp>& ops() const { return ops_; }
   // intermediate tensors exposed for layer-wise parity tests: name -> (ptr, h, w, c)
   struct Probe { const __nv_bfloat16* p; int h, w, c; };
@@ -81,7 +92,28 @@ class HourglassNet {
   int hourglass(const std::string& p, T x, T a_x, T* out);
   int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
 
-  const std::map<std::string, const float*>* sd_ = nullptr;
+  // ---- dataflow segments (conv_flow.cuh): consecutive ops executed by ONE persistent launch over small view
+  // batches, so that their intermediate tensors stay in L2.  Ops emitted between seg_begin() / seg_end() belong
+  // to the segment; op_seg_[i] = segment of op i or -1 (per-layer launch).
+  void push_op(const NetOp& op);
+  void seg_begin(int res);
+  void seg_end();
+  int build_segments();
+  bool flow_on_ = true;
+  int flow_min_h_ = 64;      // hourglass levels at least this high run as dataflow segments
+  int flow_tiles_ = 64;      // views per batch = smallest count giving every conv group this many tiles
+  int flow_interleave_ = 3;  // batches advanced in lock step
+  int cur_seg_ = -1, n_segs_ = 0;
+  std::vector<int> op_seg_;
+  std::vector<FlowSegment> segs_;
+  struct SegInfo { int batch = 1, n_layers = 0, first_op = -1; };
+  std::vector<SegInfo> seg_info_;
+  float* zeros_ = nullptr;  // kMaxCout zeros / ones: stand-ins for absent per-channel parameters
+  float* ones_ = nullptr;
+
+  const StateDict* sd_ = nullptr;
+  // state_dict entry `name` with exactly `numel` elements (a checkpoint of another model must not be misread)
+  int sd_get(const std::string& name, long long numel, const float** out) const;
   bool dry_ = true;
   int V_ = 0, H_ = 0, W_ = 0, L_ = 0, Lp_ = 0, cin_ = 0;
   uint8_t* ws_ = nullptr;

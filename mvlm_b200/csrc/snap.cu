@@ -148,7 +148,7 @@ __global__ void snap_finalize_kernel(const double* __restrict__ part, int L, int
 }
 
 int snap_splits(int l, int nt) {
-  int s = ceil_div(4 * kNumSMs, l);
+  int s = ceil_div(4 * sm_count(), l);
   const int max_s = ceil_div(nt, 256);
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;
@@ -567,7 +567,7 @@ int snap_grid_build(const float* verts, const int* tris, int nt, void* grid, siz
   int* sorted = reinterpret_cast<int*>(base + g.sorted);
   int* over = reinterpret_cast<int*>(base + g.over);
   MVLM_CHECK_CUDA(cudaMemsetAsync(base, 0, g.cell_start, s));  // header + counts
-  const int blocks = min(ceil_div(nt, 256), 4 * kNumSMs);
+  const int blocks = min(ceil_div(nt, 256), 4 * sm_count());
   const int nb = g.cap_cells / kScanItems;
   grid_bounds_kernel<<<blocks, 256, 0, s>>>(verts, tris, nt, hdr);
   grid_setup_kernel<<<1, 1, 0, s>>>(hdr, nt, g.cap_cells);

@@ -46,7 +46,7 @@ int image_to_hilo16(const unsigned char* u8, const float* f32, int cin, size_t n
   MVLM_REQUIRE((u8 != nullptr) != (f32 != nullptr), "stem: exactly one of img_u8 / img_f32");
   MVLM_REQUIRE(cin >= 1 && cin <= 4 && out, "stem: bad arguments");
   const size_t blocks = (npix + 255) / 256;
-  const int grid = static_cast<int>(blocks < static_cast<size_t>(kNumSMs) * 16 ? blocks : static_cast<size_t>(kNumSMs) * 16);
+  const int grid = static_cast<int>(blocks < static_cast<size_t>(sm_count()) * 16 ? blocks : static_cast<size_t>(sm_count()) * 16);
   image_to_hilo16_kernel<<<grid, 256, 0, s>>>(u8, f32, cin, npix, reinterpret_cast<uint4*>(out));
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());

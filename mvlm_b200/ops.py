@@ -119,12 +119,14 @@ class Hourglass:
         names = list(self._sd.keys())
         arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
         arr_p = (C.c_void_p * len(names))(*[self._sd[n].data_ptr() for n in names])
+        arr_k = (C.c_longlong * len(names))(*[self._sd[n].numel() for n in names])
         handle = C.c_void_p()
-        check(lib.mvlm_hourglass_create(arr_n, arr_p, len(names), n_landmarks, cin, n_views, h, w,
+        check(lib.mvlm_hourglass_create(arr_n, arr_p, arr_k, len(names), n_landmarks, cin, n_views, h, w,
                                         self.workspace.data_ptr(), nbytes, C.byref(handle)), "mvlm_hourglass_create")
         self._h = handle
         self.flops_per_view = lib.mvlm_hourglass_flops_per_view(n_landmarks, cin, h, w)
         self.num_launches = lib.mvlm_hourglass_num_launches(handle)
+        self.num_segments = lib.mvlm_hourglass_num_segments(handle)
 
     def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False):
         """img: (V,H,W,4) uint8 (rasteriser output) or (V,H,W,cin) float32; returns (peaks (L,V,3) f32, heatmaps|None).

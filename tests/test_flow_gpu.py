@@ -1,0 +1,66 @@
+"""Dataflow segments (csrc/conv_flow.cu) vs the per-layer plan (csrc/conv_umma.cu).
+
+Both run the same tiles through the same tcgen05 pipeline and the same epilogue code
+(csrc/conv_epilogue.cuh), so every intermediate tensor, the heat maps and the fused peaks must be
+BIT-identical; only the order in which tiles of different layers / views are executed differs.  The
+per-layer plan is in turn checked against the reference-pinned oracle in tests/test_hourglass_gpu.py.
+"""
+import os
+
+import pytest
+import torch
+
+from mvlm_b200.weights import IMAGE_CHANNELS, seeded_state_dict
+
+pytestmark = pytest.mark.gpu
+
+PROBES = ("x1", "y3", "r3", "hg1", "sum_temp", "x10")
+
+
+def _build(env, *args):
+    from mvlm_b200 import ops
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return ops.Hourglass(*args)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("n_landmarks,mode,size,views,min_h,tiles,k", [
+    (73, "RGB+depth", 128, 7, 32, 64, 3),    # trunk + two hourglass levels as segments, ragged last batch
+    (84, "geometry+depth", 128, 3, 64, 16, 2),
+    (73, "RGB+depth", 256, 5, 64, 64, 3),    # the headline geometry (segment layout of the 100-view plan)
+    (73, "RGB", 256, 4, 32, 128, 1),         # no interleave: every group waits for the one right before it
+])
+def test_flow_equals_per_layer_plan(lib, n_landmarks, mode, size, views, min_h, tiles, k):
+    sd = seeded_state_dict(n_landmarks, mode, seed=1234)
+    cin = IMAGE_CHANNELS[mode]
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (views, size, size, 4), generator=g, dtype=torch.uint8)
+    img[..., cin:] = 0
+    img = img.cuda()
+    args = (sd, n_landmarks, cin, views, size, size)
+    ref = _build({"MVLM_FLOW": "0"}, *args)
+    flow = _build({"MVLM_FLOW": "1", "MVLM_FLOW_MIN_H": str(min_h), "MVLM_FLOW_TILES": str(tiles),
+                   "MVLM_FLOW_K": str(k)}, *args)
+    assert flow.num_segments > 0 and ref.num_segments == 0
+    pk_ref, hm_ref = ref.forward(img, want_heatmaps=True)
+    for rep in range(3):  # counters are reset per launch: repeated calls must agree too
+        pk, hm = flow.forward(img, want_heatmaps=True)
+        torch.cuda.synchronize()
+        for name in PROBES:
+            a, b = ref.probe(name), flow.probe(name)
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (name, rep)
+        assert torch.equal(hm.view(torch.int32), hm_ref.view(torch.int32)), rep
+        assert torch.equal(pk.view(torch.int32), pk_ref.view(torch.int32)), rep
+    # CUDA-graph replay of the segmented plan
+    pk_g, _ = flow.forward(img, graph=True)
+    pk_g2, _ = flow.forward(img, graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(pk_g2.view(torch.int32), pk_ref.view(torch.int32))
