@@ -14,7 +14,8 @@ weights); scans shard over ranks with no data-path collective (weak scaling).
           pinned-host -> device copies of every scan and the device -> host read of its (L,3) landmarks inside
           the timed region; sync_value = the same through one blocking predict_mesh call per scan
   roofline     : CNN stage (tensor-bound): algorithmic FLOPs (146.106 GFLOP/view) / event time
-  cpu_baseline : the oracle port of the same path on the host cores, bounded sample, scaled to one scan
+  cpu_baseline : the oracle port of the same path on the host cores, bounded sample, scaled to one scan (N = 1 only)
+  --impl reference : the same port, every step one FULL scan on all host threads (nothing extrapolated)
 """
 from __future__ import annotations
 
@@ -33,8 +34,31 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_LANDMARKS = 73
-CNN_DRAM_BYTES_PER_STEP = 50.6e9  # measured with ncu, see profiles/r1_dram_per_launch.csv (30.3 GB read + 20.3 GB written)
 IMAGE_MODE = "RGB+depth"
+CPU_BUDGET_S = 45.0  # --impl reference: full scans are timed until this much CPU wall time is spent (at least one)
+
+
+def config_dict(args, mesh, world):
+    """The workload description; identical in both arms (the driver compares the dicts)."""
+    return {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, "
+                        "one scan per step per GPU",
+            "n_landmarks": N_LANDMARKS, "ransac_hypotheses": args.hyp, "weights": "seeded random init",
+            "l2": "per-step inputs + activations far exceed the 126 MB L2 (scan 5.4 MB, image stack 26 MB, CNN activations "
+                  "of 100 views several GB); no explicit flush",
+            "parallelism": f"scans sharded over {world} GPU(s), no collective"}
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use the whole host."""
+    import torch
+
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 def parse():
@@ -49,6 +73,7 @@ def parse():
     ap.add_argument("--hyp", type=int, default=1, help="RANSAC hypotheses per landmark (reference: 1)")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="ncu mode: exact --warmup, no e2e / cpu legs")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child run that measures the CNN's DRAM bytes")
     return ap.parse_args()
 
 
@@ -163,6 +188,63 @@ def cpu_path_seconds_per_scan(args, mesh, sample_views: int):
     return sum(t.values()), t, torch.get_num_threads()
 
 
+def measure_cnn_dram_traffic(args, timeout_s=300):
+    """DRAM bytes the CNN stage moves per scan, MEASURED for this build: a child run of this script
+    (--profile: one warm-up + one timed step, no other legs) under `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum`; the bytes of every CNN kernel are summed and divided by the number of
+    network passes the child executed (= launches of the peak kernel that ends each pass).
+    Returns (bytes_per_scan | None, note)."""
+    import csv
+    import shutil
+    import tempfile
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not Path(ncu).exists():
+        return None, "ncu not found"
+    with tempfile.TemporaryDirectory() as tmp:
+        log = Path(tmp) / "dram.csv"
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+               "--log-file", str(log), sys.executable, str(ROOT / "bench.py"), "--profile", "--steps", "1", "--warmup", "1",
+               "--views", str(args.views), "--size", str(args.size), "--grid", str(args.grid), "--hyp", str(args.hyp)]
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        except subprocess.TimeoutExpired:
+            return None, f"ncu child run exceeded {timeout_s} s"
+        if r.returncode != 0 or not log.exists():
+            return None, f"ncu child run failed (rc {r.returncode})"
+        rows = [ln for ln in log.read_text().splitlines() if ln.startswith('"')]
+        rd = csv.DictReader(rows)
+        cnn = ("conv_umma_kernel", "conv_flow_kernel", "pool2_act_kernel", "bn_relu_kernel", "image_to_hilo16_kernel",
+               "peaks_from_keys_kernel")
+        total = {"read": 0.0, "write": 0.0}
+        passes = 0
+        unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        seen_peaks = set()
+        for row in rd:
+            name = row.get("Kernel Name", "")
+            if not any(k in name for k in cnn):
+                continue
+            try:
+                val = float(row["Metric Value"].replace(",", "")) * unit_scale.get(row.get("Metric Unit", "byte"), 1.0)
+            except (KeyError, ValueError):
+                continue
+            if row["Metric Name"] == "dram__bytes_read.sum":
+                total["read"] += val
+            elif row["Metric Name"] == "dram__bytes_write.sum":
+                total["write"] += val
+            if "peaks_from_keys_kernel" in name and row.get("ID") not in seen_peaks:
+                seen_peaks.add(row.get("ID"))
+                passes += 1
+        if passes == 0:
+            return None, "no CNN pass found in the ncu log"
+        per = (total["read"] + total["write"]) / passes
+        return per, (f"ncu child run of this command: {total['read'] / passes / 1e9:.2f} GB read + {total['write'] / passes / 1e9:.2f} GB "
+                     f"written per scan over {passes} network passes")
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path (oracle port; the reference tree and VTK
     are not present on the GPU box), all host threads, each step a bounded sample of the workload."""
@@ -172,25 +254,30 @@ def run_reference(args):
     from oracle import native
 
     native.build()
+    cores = use_all_host_threads()
     mesh = make_scan(args)
-    sample = 4
-    for _ in range(min(args.warmup, 1)):
-        cpu_path_seconds_per_scan(args, mesh, 2)
-    secs = []
-    for _ in range(max(1, min(args.steps, 3))):
-        s, parts, cores = cpu_path_seconds_per_scan(args, mesh, sample)
+    n_warm = min(args.warmup, 1)
+    for _ in range(n_warm):
+        cpu_path_seconds_per_scan(args, mesh, 2)  # a short warm-up (thread pools, allocator), not a full scan
+    # every timed step is ONE FULL scan (all views through raster / CNN / peaks, no extrapolation); full scans are
+    # repeated until CPU_BUDGET_S is spent (about 15 s each on a 32-core host), at most --steps of them
+    secs, parts = [], {}
+    t_begin = time.perf_counter()
+    while len(secs) < max(1, args.steps) and (not secs or time.perf_counter() - t_begin + secs[-1] < CPU_BUDGET_S):
+        s, parts, _ = cpu_path_seconds_per_scan(args, mesh, args.views)
         secs.append(s)
-    sec = float(np.median(secs))
+    sec = float(np.mean(secs))
     val = 1.0 / sec
     line = {
         "impl": "reference", "metric": "scans/sec", "value": val, "unit": "scans/s", "n_gpus": args.gpus,
-        "steps": len(secs), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": len(secs), "warmup": n_warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, one scan per step per GPU",
-                   "n_landmarks": N_LANDMARKS, "ransac_hypotheses": args.hyp},
+        "config": config_dict(args, mesh, args.gpus),
         "cpu_baseline": {"value": val, "unit": "scans/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {args.views} views for raster/CNN/peaks (scaled linearly), full size for rays/consensus/snap; "
-                                   f"stage seconds per scan: " + ", ".join(f"{k} {v:.2f}" for k, v in parts.items())},
+                         "sample": f"{len(secs)} full scan(s) of {args.views} views, nothing extrapolated; the oracle port (torch-CPU "
+                                   "restatement of MVLMModel, numpy peaks / rays / consensus restating the reference, C restatements "
+                                   "of the two VTK stages: /root/reference and VTK do not exist on this box); stage seconds per scan: "
+                                   + ", ".join(f"{k} {v:.2f}" for k, v in parts.items())},
         "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -370,11 +457,8 @@ def run_ours(args):
             "metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"DTU3D RGB+depth, {args.views} views {args.size}^2, {len(mesh.verts)} verts / {len(mesh.tris)} tris, one scan per step per GPU",
-                       "n_landmarks": N_LANDMARKS, "ransac_hypotheses": args.hyp, "weights": "seeded random init",
-                       "l2": "per-step activations (%.1f GB workspace at %d views) exceed the 126 MB L2; no explicit flush" % (
-                           lib.mvlm_hourglass_workspace_bytes(N_LANDMARKS, 4, args.views, args.size, args.size) / 1e9, args.views),
-                       "parallelism": f"scans sharded over {world} GPU(s), no collective"},
+            "config": config_dict(args, mesh, world),
+            "cnn_workspace_gb": lib.mvlm_hourglass_workspace_bytes(N_LANDMARKS, 4, args.views, args.size, args.size) / 1e9,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "Pipeline.predict_meshes(host meshes): up to two scans in flight on one stream",
                     "sync_value": e2e_sync_value,
@@ -384,24 +468,28 @@ def run_ours(args):
                                   "multi-threaded parser, 2-deep prefetch; informational, not the contract's e2e"},
             "gpu_launches": int(launches),
             "stages_ms": stage_ms,
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (CNN stage incl. its stem/pool/upsample glue launches)",
-                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum summed over the 154 CNN launches of one step
-                         # (ncu capture of this command, profiles/r1_dram_per_launch.csv: 30.3 GB read + 20.3 GB written)
-                         "traffic": CNN_DRAM_BYTES_PER_STEP if (args.views, args.size) == (100, 256) else None,
-                         "traffic_note": "bytes per step over all CNN launches; = %.0f%% of measured HBM peak at this step time" % (
-                             100 * CNN_DRAM_BYTES_PER_STEP / (stage_ms["cnn"] / 1e3) / 1e9 / pk["hbm_gbs"]),
+            "roofline": {"bound": "tensor", "kernel": "conv_flow_kernel + conv_umma_kernel (CNN stage: all its launches)",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                          "peak_source": f"{pk_kind} bf16_tflops_sustained", "flops_per_scan": flops_scan},
             "clocks": clocks,
         }
-        if not args.skip_cpu and not args.profile:
+        if world == 1 and not args.profile and not args.no_traffic:
+            # dram__bytes_read.sum + dram__bytes_write.sum over every CNN launch of one scan, measured now by an ncu
+            # child run of this same script (never a constant carried over from an older build)
+            traffic, note = measure_cnn_dram_traffic(args)
+            line["roofline"]["traffic"] = traffic
+            line["roofline"]["traffic_note"] = note + ("" if traffic is None else "; = %.0f%% of the measured HBM peak at this "
+                                                       "stage time" % (100 * traffic / (stage_ms["cnn"] / 1e3) / 1e9 / pk["hbm_gbs"]))
+        if world == 1 and not args.skip_cpu and not args.profile:
             try:
-                sec, parts, cores = cpu_path_seconds_per_scan(args, mesh, 4)
+                cores = use_all_host_threads()
+                n_sample = 8
+                sec, parts, _ = cpu_path_seconds_per_scan(args, mesh, n_sample)
                 line["cpu_baseline"] = {
                     "value": 1.0 / sec, "unit": "scans/s", "cores": cores, "kind": "port",
-                    "sample": "4 of %d views for raster/CNN/peaks (scaled linearly), full size for rays/consensus/snap; "
+                    "sample": "%d of %d views for raster/CNN/peaks (scaled linearly), full size for rays/consensus/snap; "
                               "VTK stages restated in C, not executed; stage s/scan: %s" % (
-                                  args.views, ", ".join(f"{k} {v:.2f}" for k, v in parts.items()))}
+                                  n_sample, args.views, ", ".join(f"{k} {v:.2f}" for k, v in parts.items()))}
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "scans/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         print(json.dumps(line), flush=True)

@@ -16,6 +16,7 @@ using namespace epi;
 
 // fixed operand rings (the per-layer kernel sizes them per layer; here tiles of different layers follow each
 // other through the same slots): 2 halo slots of (8+2) x (32+2) px x 128 B, 7 weight slots of 128 rows x 128 B
+constexpr int kFlowThreads = kThreads + 32;  // warp 11: completion signaller
 constexpr int kHSlots = 2;
 constexpr int kWSlots = 7;
 constexpr int kHSlotBytes = 44032;
@@ -32,6 +33,7 @@ struct __align__(8) Barriers {
   uint64_t t_empty[2];
   uint32_t tmem_base;
   int deps_ok;  // ordinal (1-based) of the last item of this CTA whose dependencies the producer has seen satisfied
+  int epi_count[kEpiWarps];  // items of this CTA each epilogue warp has finished (all its stores issued)
 };
 static_assert(sizeof(Barriers) <= 512, "barrier block");
 
@@ -130,35 +132,58 @@ __device__ __forceinline__ void elt_tile(const LayerSm& L, const Item& it, const
   const int img_in = it.img % L.ring_in;
   const int img_raw = it.img % L.ring_raw, img_act = it.img % L.ring_post;
   const int n_vec = kTileW * kMaxTileH * c8;
-  for (int v = tid; v < n_vec; v += kEpiWarps * 32) {
-    const int cv = v % c8;
-    const int px = v / c8;
-    const int x = it.tx * kTileW + (px & 7);
-    const int y = it.ty * kMaxTileH + (px >> 3);
-    if (x >= wo || y >= ho) continue;
-    float m[8];
-    if (pool) {
-      const size_t base = ((static_cast<size_t>(img_in) * hi + 2 * y) * wi + 2 * x) * c8 + cv;
-      float a[8], b[8];
-      unpack8(__ldcg(in + base), m);
-      unpack8(__ldcg(in + base + c8), a);
+  constexpr int kU = 4;  // vectors per thread in flight: the loop is latency-bound (L2 round trips) otherwise
+  for (int v0 = tid; v0 < n_vec; v0 += kU * kEpiWarps * 32) {
+    uint4 q[kU][4];
+    size_t o_idx[kU];
+    bool ok[kU];
+    int cvs[kU];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], a[j]);
-      unpack8(__ldcg(in + base + static_cast<size_t>(wi) * c8), a);
-      unpack8(__ldcg(in + base + static_cast<size_t>(wi) * c8 + c8), b);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaxf(a[j], b[j]));
-    } else {
-      unpack8(__ldcg(in + ((static_cast<size_t>(img_in) * hi + y) * wi + x) * c8 + cv), m);
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * kEpiWarps * 32;
+      const int cv = v % c8;
+      const int px = v / c8;
+      const int x = it.tx * kTileW + (px & 7);
+      const int y = it.ty * kMaxTileH + (px >> 3);
+      ok[u] = v < n_vec && x < wo && y < ho;
+      cvs[u] = cv;
+      o_idx[u] = (static_cast<size_t>(y) * wo + x) * c8 + cv;
+      if (!ok[u]) continue;
+      if (pool) {
+        const size_t base = ((static_cast<size_t>(img_in) * hi + 2 * y) * wi + 2 * x) * c8 + cv;
+        q[u][0] = __ldcg(in + base);
+        q[u][1] = __ldcg(in + base + c8);
+        q[u][2] = __ldcg(in + base + static_cast<size_t>(wi) * c8);
+        q[u][3] = __ldcg(in + base + static_cast<size_t>(wi) * c8 + c8);
+      } else {
+        q[u][0] = __ldcg(in + ((static_cast<size_t>(img_in) * hi + y) * wi + x) * c8 + cv);
+      }
     }
-    if (out_raw) out_raw[((static_cast<size_t>(img_raw) * ho + y) * wo + x) * c8 + cv] = pack8(m);
-    if (out_act) {
-      float sc[8], sh[8], o[8];
-      lds8(L.cp.post_s + cv * 8, sc);
-      lds8(L.cp.post_t + cv * 8, sh);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(m[j], sc[j], sh[j]), 0.f);
-      out_act[((static_cast<size_t>(img_act) * ho + y) * wo + x) * c8 + cv] = pack8(o);
+    for (int u = 0; u < kU; ++u) {
+      if (!ok[u]) continue;
+      float m[8];
+      unpack8(q[u][0], m);
+      if (pool) {
+        float a[8], b[8];
+        unpack8(q[u][1], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], a[j]);
+        unpack8(q[u][2], a);
+        unpack8(q[u][3], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaxf(a[j], b[j]));
+      }
+      const size_t plane = static_cast<size_t>(ho) * wo * c8;
+      if (out_raw) out_raw[img_raw * plane + o_idx[u]] = pack8(m);
+      if (out_act) {
+        float sc[8], sh[8], o[8];
+        lds8(L.cp.post_s + cvs[u] * 8, sc);
+        lds8(L.cp.post_t + cvs[u] * 8, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(m[j], sc[j], sh[j]), 0.f);
+        out_act[img_act * plane + o_idx[u]] = pack8(o);
+      }
     }
   }
 }
@@ -168,23 +193,24 @@ __device__ __forceinline__ void elt_tile(const LayerSm& L, const Item& it, const
 template <int F>
 __device__ __noinline__ void flow_epilogue(const LayerSm* L, const int mt, const int tx, const int ty, const int img,
                                            uint64_t* t_full, const uint32_t parity, const uint32_t tmem_acc,
-                                           float* stage, const int warp, const int lane) {
+                                           float* stage, const int warp, const int lane, long long* wait_cycles) {
   const TileCoord tc = {mt, tx, ty, img};
   const ImageSlots is = {img % L->ring_pre, img % L->ring_raw, img % L->ring_post,
                          img % L->ring_res1, img % L->ring_res2, img % L->ring_up};
   ArgmaxState am;
   EpiTrace tr;
   long long w0 = 0;
-  epilogue_tile<F, true>(L->s, L->e, L->tile_h, L->cp, tc, is, t_full, parity, tmem_acc, stage, warp, lane, am, false,
-                         w0, tr);
+  epilogue_tile<F, true>(L->s, L->e, L->tile_h, L->cp, tc, is, t_full, parity, tmem_acc, stage, warp, lane, am,
+                         wait_cycles != nullptr, w0, tr);
+  if (wait_cycles) *wait_cycles += w0;
 }
 
-// 11 warps x 184 registers = 64768 of the SM's 65536 (launch bounds would round the block up to 384 threads and
-// cap the kernel at 168, which spills in the widest epilogue variants)
-__global__ void __maxnreg__(184)
+// (352 threads are allocated as 12 warps, so 168 registers per thread is the most this block shape can have)
+__global__ void __launch_bounds__(kFlowThreads, 1)
 conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ layers_sm, const int n_layers,
                  const int4* __restrict__ items,
-                 const int n_items, const FlowGroup* __restrict__ groups, unsigned int* __restrict__ done) {
+                 const int n_items, const FlowGroup* __restrict__ groups, unsigned int* __restrict__ done,
+                 long long* __restrict__ prof_buf, const int debug_flags) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: TMA and UMMA agree on the SWIZZLE_128B XOR pattern through the absolute address
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -203,7 +229,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
     const uint32_t* src = reinterpret_cast<const uint32_t*>(layers_sm);
     uint32_t* dst = reinterpret_cast<uint32_t*>(lsm);
     const int n_words = n_layers * static_cast<int>(sizeof(LayerSm) / 4);
-    for (int i = threadIdx.x; i < n_words; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < n_words; i += kFlowThreads) dst[i] = __ldg(src + i);
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kHSlots; ++i) {
@@ -219,6 +245,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
       ptx::mbar_init(&bar->t_empty[i], kEpiWarps);
     }
     bar->deps_ok = 0;
+    for (int i = 0; i < kEpiWarps; ++i) bar->epi_count[i] = 0;
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -233,6 +260,13 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = bar->tmem_base;
   const int step = static_cast<int>(gridDim.x);
+  // optional role counters, 8 x int64 per CTA (cycles): [0] tracker: dependency waits, [1] tracker: halo slot waits,
+  // [2] MMA: operand waits, [3] MMA: accumulator waits, [4] MMA: loop total, [5] epilogue warp 2: accumulator-ready
+  // waits, [6] epilogue warp 2: dependency-flag waits, [7] epilogue warp 2: loop total
+  const bool prof = prof_buf != nullptr;
+  long long* const pc = prof ? prof_buf + blockIdx.x * 8 : nullptr;
+  const long long t_kernel0 = clock64();
+  long long w0 = 0, w1 = 0;
 
   if (warp == 0) {
     // ===================== dependency tracker + TMA producer: activations =====================
@@ -245,7 +279,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
       for (int i = blockIdx.x; i < n_items; i += step) {
         const Item it = decode_item(nxt);
         if (i + step < n_items) nxt = __ldg(items + i + step);
-        if (it.group != g_ok) {
+        if (it.group != g_ok && !(debug_flags & 1)) {
           // all tiles of the groups this one depends on have been stored (and their stores made visible at GPU
           // scope before the count): producers of my inputs / residuals, earlier readers and writers of my outputs
           const FlowGroup& G = groups[it.group];
@@ -256,6 +290,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
             if (ld_acquire_gpu(ctr) < need) {
               const long long t0 = clock64();
               while (ld_acquire_gpu(ctr) < need) MVLM_FLOW_SPIN_GUARD(t0, "dependency wait");
+              w0 += clock64() - t0;
             }
           }
           g_ok = it.group;
@@ -277,13 +312,14 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
           // the last chunk may be a narrow tail (16 / 32 channels) with its own tensor map: rows of 32 / 64 bytes
           const bool is_tail = L.tail != 0 && c == n_chunks - 1;
           const uint32_t row_b = is_tail ? static_cast<uint32_t>(L.tail) * 2u : 128u;  // bytes per pixel
-          ptx::mbar_wait(&bar->h_empty[sh], ph ^ 1);
+          timed_wait(&bar->h_empty[sh], ph ^ 1, prof, w1);
           ptx::mbar_expect_tx(&bar->h_full[sh], static_cast<uint32_t>(halo_rows * halo_px) * row_b);
           // one halo tile for all KW x KH taps of this chunk
           ptx::tma_load_4d(is_tail ? &GL.p.tm_a2 : &GL.p.tm_a, &bar->h_full[sh], h_slots + sh * kHSlotBytes, c * 64, x0, y0, img_in);
           if (++sh == kHSlots) { sh = 0; ph ^= 1; }
         }
       }
+      if (prof) { pc[0] = w0; pc[1] = w1; }
     }
   } else if (warp == 10) {
     // ===================== TMA producer: weights =====================
@@ -336,7 +372,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         const uint32_t idesc = ptx::umma_idesc_bf16(kM, L.tile_h * kTileW);
         const int n_chunks = (s.cin + 63) >> 6;
         const int halo_px = kTileW + s.kw - 1;
-        ptx::mbar_wait(&bar->t_empty[acc], pacc ^ 1);
+        timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
         uint32_t accumulate = 0;
@@ -349,11 +385,11 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
           const uint32_t swz = !is_tail ? 2u : (L.tail == 16 ? 6u : 4u);
           const uint64_t a_hi = static_cast<uint64_t>(((8u * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
           const uint64_t b_hi = static_cast<uint64_t>(((static_cast<uint32_t>(halo_px) * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
-          ptx::mbar_wait(&bar->h_full[sh], ph);
+          timed_wait(&bar->h_full[sh], ph, prof, w0);
           const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * kHSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
           for (int kx = 0; kx < s.kw; ++kx) {
             for (int ky = 0; ky < s.kh; ++ky) {
-              ptx::mbar_wait(&bar->w_full[sw], pw);
+              timed_wait(&bar->w_full[sw], pw, prof, w0);
               ptx::tc_fence_after();
               const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * kWSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
               // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
@@ -377,6 +413,39 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         ptx::umma_commit(&bar->t_full[acc]);
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
+      if (prof) { pc[2] = w0; pc[3] = w1; pc[4] = clock64() - t_kernel0; }
+    }
+  } else if (warp == 11) {
+    // ===================== completion signaller =====================
+    // An epilogue warp only notes (CTA scope) that it has issued the stores of its part of an item.  This thread
+    // waits until all eight have, makes those stores visible at GPU scope with ONE fence (cumulative over what it
+    // observed through the CTA-scope acquire) and counts the tile on its group's counter.  A fence + atomic in every
+    // epilogue warp (first version) stalls each of them for the write-acknowledge latency once per tile: the
+    // segments ran 2.3x slower than the per-layer launches.
+    if (ptx::elect_one()) {
+      int k = 0;
+      int4 nxt = blockIdx.x < n_items ? __ldg(items + blockIdx.x) : make_int4(0, 0, 0, 0);
+      for (int i = blockIdx.x; i < n_items; i += step) {
+        const int group = nxt.z;
+        if (i + step < n_items) nxt = __ldg(items + i + step);
+        ++k;
+        const long long t0 = clock64();
+        for (;;) {
+          int lo = k;
+#pragma unroll
+          for (int w = 0; w < kEpiWarps; ++w) lo = min(lo, ld_acquire_cta_shared(&bar->epi_count[w]));
+          if (lo >= k) break;
+          __nanosleep(100);
+          MVLM_FLOW_SPIN_GUARD(t0, "signaller wait");
+        }
+        if (debug_flags & 1) continue;  // timing experiment: no publication (and no dependency waits above)
+        if (debug_flags & 2) {
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + group) : "memory");
+        } else {
+          __threadfence();
+          atomicAdd(done + group, 1u);
+        }
+      }
     }
   } else {
     // ===================== epilogue / element-wise items =====================
@@ -393,6 +462,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
       if (ld_acquire_cta_shared(&bar->deps_ok) < k) {
         const long long t0 = clock64();
         while (ld_acquire_cta_shared(&bar->deps_ok) < k) MVLM_FLOW_SPIN_GUARD(t0, "epilogue dependency wait");
+        w1 += clock64() - t0;
       }
       const LayerSm& L = lsm[it.layer];
       if (L.kind == FLOW_CONV) {
@@ -400,7 +470,8 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         switch (L.f) {
 #define MVLM_FLOW_CASE(FLAGS)                                                                                      \
   case (FLAGS):                                                                                                    \
-    flow_epilogue<(FLAGS)>(&L, it.mt, it.tx, it.ty, it.img, &bar->t_full[acc], pacc, tmem_acc, stage, warp, lane); \
+    flow_epilogue<(FLAGS)>(&L, it.mt, it.tx, it.ty, it.img, &bar->t_full[acc], pacc, tmem_acc, stage, warp, lane, \
+                           prof ? &w0 : nullptr);                                                                   \
     break;
 #define MVLM_FLOW_CASE_M64(FLAGS) MVLM_FLOW_CASE((FLAGS) | F_M64)
           MVLM_FLOW_VARIANTS_BOTH(MVLM_FLOW_CASE)
@@ -423,12 +494,11 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         elt_tile(L, it, (warp - 2) * 32 + lane);
         __syncwarp();
       }
-      // publish: this warp's stores of the tile, then one count per warp on the group's counter
-      if (lane == 0) {
-        __threadfence();
-        atomicAdd(done + it.group, 1u);
-      }
+      // this warp's part of the item is stored (the signaller publishes the item once all eight say so)
+      __syncwarp();
+      if (lane == 0) st_release_cta_shared(&bar->epi_count[warp - 2], k);
     }
+    if (prof && warp == 2 && lane == 0) { pc[5] = w0; pc[6] = w1; pc[7] = clock64() - t_kernel0; }
   }
 
   ptx::tc_fence_before();
@@ -532,7 +602,7 @@ int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, in
                 ++count;
               }
         gid[static_cast<size_t>(l) * n_batches + b] = g;
-        gneed[static_cast<size_t>(l) * n_batches + b] = count * kEpiWarps;
+        gneed[static_cast<size_t>(l) * n_batches + b] = count;
         groups.push_back(G);
       }
     }
@@ -584,6 +654,14 @@ int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, in
   return MVLM_OK;
 }
 
+namespace {
+long long* g_flow_prof = nullptr;
+// experiment switches (MVLM_FLOW_DEBUG): 1 = no dependency waits / no publication (timing only, results invalid),
+// 2 = red.release instead of fence + atomicAdd
+const int g_flow_debug = getenv("MVLM_FLOW_DEBUG") ? atoi(getenv("MVLM_FLOW_DEBUG")) : 0;
+}
+void flow_set_profile_buffer(long long* dev_buf) { g_flow_prof = dev_buf; }
+
 int flow_launch(const FlowSegment& seg, cudaStream_t stream) {
   MVLM_REQUIRE(seg.layers && seg.items && seg.groups && seg.done && seg.n_items > 0, "flow_launch: empty segment");
   // the attribute is per device: one flag per device ordinal
@@ -601,13 +679,13 @@ int flow_launch(const FlowSegment& seg, cudaStream_t stream) {
   const int grid = seg.n_items < n_sms ? seg.n_items : n_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kFlowThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
   MVLM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_flow_kernel, static_cast<const FlowLayer*>(seg.layers),
                                      static_cast<const void*>(seg.layers_sm), seg.n_layers,
                                      reinterpret_cast<const int4*>(seg.items), seg.n_items,
-                                     static_cast<const FlowGroup*>(seg.groups), seg.done));
+                                     static_cast<const FlowGroup*>(seg.groups), seg.done, g_flow_prof, g_flow_debug));
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;

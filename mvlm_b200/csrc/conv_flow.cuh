@@ -49,7 +49,7 @@ struct FlowItem {
 struct FlowGroup {
   int n_deps;
   int dep[kFlowMaxDeps];       // group indices (counter slots) this group waits for ...
-  int dep_need[kFlowMaxDeps];  // ... until done[dep] reaches this count (8 epilogue warps x tiles of that group)
+  int dep_need[kFlowMaxDeps];  // ... until done[dep] reaches this count (the tiles of that group)
 };
 
 struct FlowSegment {
@@ -75,5 +75,8 @@ struct FlowLayerDesc {
 int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, int batch, int interleave,
                        std::vector<void*>* owned, FlowSegment* out);
 int flow_launch(const FlowSegment& seg, cudaStream_t stream);
+// Debug: when non-null, the next flow_launch calls record per-CTA role counters there (148 x 8 int64, see
+// conv_flow.cu).
+void flow_set_profile_buffer(long long* dev_buf);
 
 }  // namespace mvlm

@@ -682,8 +682,25 @@ int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32,
     std::vector<long long> host(kConvProfInts);
     for (size_t i = 0; i < n && rc == MVLM_OK; ++i) {
       for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] = 0.0;
-      if (op_seg_[i] >= 0) {  // dataflow segments carry no role counters
+      if (op_seg_[i] >= 0) {  // dataflow segments: their own counters (conv_flow.cu), reported by the first op
+        const bool first = seg_info_[op_seg_[i]].first_op == static_cast<int>(i);
+        if (first) {
+          MVLM_CHECK_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * kConvProfInts, stream));
+          flow_set_profile_buffer(dev);
+        }
         rc = run_step(i, img_u8, img_f32, nullptr, out_peaks, stream);
+        flow_set_profile_buffer(nullptr);
+        if (first && rc == MVLM_OK) {
+          MVLM_CHECK_CUDA(cudaStreamSynchronize(stream));
+          MVLM_CHECK_CUDA(cudaMemcpy(host.data(), dev, sizeof(long long) * kConvProfInts, cudaMemcpyDeviceToHost));
+          int ctas = 0;
+          for (int c = 0; c < kNumSMs; ++c) {
+            if (host[c * 8 + 7] == 0) continue;
+            ++ctas;
+            for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] += static_cast<double>(host[c * 8 + k]);
+          }
+          for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] /= ctas > 0 ? ctas : 1;
+        }
         continue;
       }
       if (ops_[i].kind == NetOp::CONV) {

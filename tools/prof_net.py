@@ -54,4 +54,7 @@ print("roles (kcycles per CTA per op): prod-wait-A/B-empty | mma-wait-operands /
 for d, (cnt, t, r) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     r = [x / cnt / 1e3 for x in r]
     rs = f"  P {r[0]:6.0f} {r[1]:6.0f} | M {r[2]:6.0f} {r[3]:6.0f} {r[4]:6.0f} | E {r[5]:6.0f} {r[6]:6.0f}" if d.startswith("conv") else ""
+    if d.startswith("flow segment"):
+        rs = (f"\n      tracker: dep-wait {r[0]:6.0f} halo-slot-wait {r[1]:6.0f} | MMA: operand-wait {r[2]:6.0f} acc-wait {r[3]:6.0f} "
+              f"total {r[4]:6.0f} | epilogue w2: acc-ready-wait {r[5]:6.0f} dep-flag-wait {r[6]:6.0f} total {r[7]:6.0f} (kcycles)")
     print(f"{t:8.3f} ms {100 * t / total:5.1f}%  x{cnt:3d}  {t / cnt * 1000:8.1f} us/op  {d:62s}{rs}")
