@@ -5,6 +5,10 @@
 #pragma once
 #include "conv_umma.cuh"
 
+#ifndef MVLM_FLOW_RES_BUDGET
+#define MVLM_FLOW_RES_BUDGET 32  // registers of the residual prefetch buffer in the dataflow kernel's variants
+#endif
+
 namespace mvlm {
 namespace epi {
 
@@ -160,8 +164,8 @@ template <int F, bool kFlow>
 __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpilogue& e, const int tile_h,
                                               const ChannelParams& ep, const TileCoord& tc, const ImageSlots& is,
                                               uint64_t* t_full, const uint32_t parity, const uint32_t tmem_acc,
-                                              float* stage, const int warp, const int lane, ArgmaxState& am,
-                                              const bool prof, long long& w0, EpiTrace& tr) {
+                                              float* stage, const int ew, const int lane_grp, const int lane,
+                                              ArgmaxState& am, const bool prof, long long& w0, EpiTrace& tr) {
   constexpr bool M64 = (F & F_M64) != 0;
   constexpr int kM = M64 ? 64 : kMTile;
   constexpr int kChGrp = M64 ? 16 : 32;      // channels per TMEM lane group
@@ -172,16 +176,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   constexpr bool kFrag = M64 && (F & F_HEAD) == 0;  // M = 64 accumulators read with the 16x256b shape
   static_assert(kCols * kPitch <= kStageFloats, "transpose buffer");
   const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
-  // cout < M: the weight rows are replicated `rep` times along M, so that all four TMEM lane groups (and
-  // therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows instead.
-  const int rep = kM / w_rows;
-  const int ew = warp - 2;
-  const int lane_grp = warp & 3;   // TMEM lanes this warp may read: 32*(warp%4)..
-  const int n_cgrp = 4 / rep;      // distinct channel groups along M
-  const int cgrp = lane_grp % n_cgrp;
-  const int replica = lane_grp / n_cgrp;
+  // cout < M: the weight rows are replicated `rep` = kM / w_rows (1, 2 or 4) times along M, so that all four TMEM
+  // lane groups (and therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows
+  // instead.  Shifts, not divisions: in the dataflow kernel this runs once per tile.
+  const int rep_log2 = (4 * w_rows <= kM) ? 2 : ((2 * w_rows <= kM) ? 1 : 0);
+  const int rep = 1 << rep_log2;
+  // ew = index of this epilogue warp (0..7), lane_grp = its hardware warp id % 4: the TMEM lanes it may read are
+  // 32 * lane_grp ..
+  const int n_cgrp = 4 >> rep_log2;  // distinct channel groups along M
+  const int cgrp = lane_grp & (n_cgrp - 1);
+  const int replica = lane_grp >> (2 - rep_log2);
   const int n_units = max(1, tile_h / kUnitRows);
-  const int upw = max(1, n_units / (2 * rep));              // units per warp
+  const int upw = max(1, n_units >> (1 + rep_log2));        // units per warp
   const int u_begin = ((ew >> 2) * rep + replica) * upw;    // first unit handled by this warp
   const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
   // channel-major role (TMEM load, bias, transpose store): lane = channel; M = 64 -> lanes 0..15 only.
@@ -208,7 +214,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   constexpr bool kHasRes = (F & (F_RES1 | F_RES2 | F_UP)) != 0;
   constexpr int kMaxUpw = M64 ? 4 : 8;  // units per warp at N = 256
   constexpr int kResRegs = 4 * (2 * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + (M64 ? 2 : 1) * ((F & F_UP) ? 1 : 0));
-  constexpr int kPref = !kHasRes ? 1 : (kResRegs * kMaxUpw <= 64 ? kMaxUpw : kMaxUpw / 2);  // units per batch
+  // Dataflow kernel: the first batch is issued AFTER the accumulator wait (below).  Issued before it, as in the
+  // per-layer kernel, the buffer is live across the wait loop and ptxas keeps it on the stack in the dataflow kernel's
+  // many-variant epilogue: every prefetched line was stored to local memory as it arrived, one exposed L2 round trip
+  // per load (measured: 19k cycles before the first unit of a 16-load tile).  Residuals come from L2 there, and one
+  // exposed round trip per tile (~1.5k cycles under load) is the price.
+  constexpr int kResBudget = kFlow ? MVLM_FLOW_RES_BUDGET : 64;
+  constexpr int kPref = !kHasRes ? 1 : (kResRegs * kMaxUpw <= kResBudget ? kMaxUpw : (kResRegs * kMaxUpw <= 2 * kResBudget ? kMaxUpw / 2 : (kMaxUpw >= 4 ? kMaxUpw / 4 : 1)));  // units per batch
   uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1][M64 ? 2 : 1];
 
   const int m0 = tc.mt * kM;
@@ -222,9 +234,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   const bool vx = ch_ok && xa < s.w;
   // element index of my pixel in pass 0 of the first unit of image `img`: (img, y_first + my_i, xa); 32-bit: pixel
   // count x channel stride < 2^31 (checked in conv_plan)
-  auto pix_of = [&](int img) { return (static_cast<uint32_t>(img) * s.h + y_first + my_i) * s.w + xa; };
+  auto pix_of = [&](int img) __attribute__((always_inline)) { return (static_cast<uint32_t>(img) * s.h + y_first + my_i) * s.w + xa; };
   // element index of the half-resolution pixel (img, y_first/2, xa/2): F_POOL outputs, F_UP input
-  auto ppix_of = [&](int img) {
+  auto ppix_of = [&](int img) __attribute__((always_inline)) {
     return (static_cast<uint32_t>(img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
   };
   if ((F & F_ARGMAX) && tc.img != am.cur_img) {
@@ -241,18 +253,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   // rows at / below my first pixel that exist in the image (0 when my pixel column / channels do not):
   // unit r, pass ip is valid iff kUnitRows * r + kPassStep * ip < n_rows_ok
   const int n_rows_ok = vx ? s.h - y_first - my_i : 0;
-  const uint8_t* const b_res1 = (F & F_RES1) ? reinterpret_cast<const uint8_t*>(e.res1 + e.res1_co + c0 + static_cast<size_t>(pix_of(is.res1)) * e.res1_cs) : nullptr;
-  const uint8_t* const b_res2 = (F & F_RES2) ? reinterpret_cast<const uint8_t*>(e.res2 + e.res2_co + c0 + static_cast<size_t>(pix_of(is.res2)) * e.res2_cs) : nullptr;
-  const uint8_t* const b_up = (F & F_UP) ? reinterpret_cast<const uint8_t*>(e.res_up + e.up_co + c0 + static_cast<size_t>(ppix_of(is.up)) * e.up_cs) : nullptr;
-  auto prefetch_batch = [&](int u0) {  // units u0 .. u0 + kPref - 1 (u0 compile-time after unrolling)
+  // (kFlow: lanes whose pixel column / channels / rows do not exist point at the tensor's first element, see
+  // prefetch_batch)
+  const bool res_ok = !kFlow || n_rows_ok > 0;
+  const uint8_t* const b_res1 = (F & F_RES1) ? reinterpret_cast<const uint8_t*>(res_ok ? e.res1 + e.res1_co + c0 + static_cast<size_t>(pix_of(is.res1)) * e.res1_cs : e.res1) : nullptr;
+  const uint8_t* const b_res2 = (F & F_RES2) ? reinterpret_cast<const uint8_t*>(res_ok ? e.res2 + e.res2_co + c0 + static_cast<size_t>(pix_of(is.res2)) * e.res2_cs : e.res2) : nullptr;
+  const uint8_t* const b_up = (F & F_UP) ? reinterpret_cast<const uint8_t*>(res_ok ? e.res_up + e.up_co + c0 + static_cast<size_t>(ppix_of(is.up)) * e.up_cs : e.res_up) : nullptr;
+  auto prefetch_batch = [&](int u0) __attribute__((always_inline)) {  // units u0 .. u0 + kPref - 1 (u0 compile-time after unrolling)
 #pragma unroll
     for (int q = 0; q < kPref; ++q) {
       const int u = u0 + q;
-      if (u < upw) {
+      if (kFlow || u < upw) {
 #pragma unroll
         for (int ip = 0; ip < 2; ++ip) {
           const int row = kUnitRows * u + kPassStep * ip;
-          if (row < n_rows_ok) {
+          if constexpr (kFlow) {
+            // unconditional loads (rows that do not exist re-read the tile's first row and are never used): with
+            // conditionally defined buffer entries ptxas keeps the whole buffer in local memory in the non-inlined
+            // variants of the dataflow kernel (load, store to the stack, reload: one L2 round trip per load)
+            const int rr = (u < upw && row < n_rows_ok) ? row : 0;
+            if (F & F_RES1) r1[q][ip] = load_res<kFlow>(b_res1 + static_cast<size_t>(rr * rs_res1));
+            if (F & F_RES2) r2[q][ip] = load_res<kFlow>(b_res2 + static_cast<size_t>(rr * rs_res2));
+            if ((F & F_UP) && (M64 || ip == 0))
+              ru[q][M64 ? ip : 0] = load_res<kFlow>(b_up + static_cast<size_t>((rr >> 1) * rs_up));
+          } else if (row < n_rows_ok) {
             if (F & F_RES1) r1[q][ip] = load_res<kFlow>(b_res1 + static_cast<size_t>(row * rs_res1));
             if (F & F_RES2) r2[q][ip] = load_res<kFlow>(b_res2 + static_cast<size_t>(row * rs_res2));
             // nearest x2: rows 2k, 2k+1 and columns xa, xa^1 all read low-res pixel (k, xa/2);
@@ -264,11 +288,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
       }
     }
   };
-  if (kHasRes && grp_active && rows_active) prefetch_batch(0);
+  if (!kFlow && kHasRes && grp_active && rows_active) prefetch_batch(0);
   // per-channel parameters of my 8 channels (pixel-major role) and my channel (channel-major role)
   float pre_s[8], pre_t[8], post_s[8], post_t[8];
-  if (F & F_PRE) { lds8(ep.pre_s + (ch_ok ? c0 : 0), pre_s); lds8(ep.pre_t + (ch_ok ? c0 : 0), pre_t); }
-  if (F & F_POST) { lds8(ep.post_s + (ch_ok ? c0 : 0), post_s); lds8(ep.post_t + (ch_ok ? c0 : 0), post_t); }
+  const int c0_ok = ch_ok ? c0 : 0;
+  if (F & F_PRE) { lds8(ep.pre_s + c0_ok, pre_s); lds8(ep.pre_t + c0_ok, pre_t); }
+  if (F & F_POST) { lds8(ep.post_s + c0_ok, post_s); lds8(ep.post_t + c0_ok, post_t); }
   const int c_lane_ok = c_lane < s.cout_pad ? c_lane : 0;
   const float bias_c = ep.bias[c_lane_ok];
   const float mid_s_c = ep.mid_s[c_lane_ok], mid_t_c = ep.mid_t[c_lane_ok];
@@ -283,7 +308,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
       if (F & F_MID) { fms[h] = ep.mid_s[ch]; fmt[h] = ep.mid_t[ch]; }
     }
   }
-  timed_wait(t_full, parity, prof, w0);
+  if constexpr (kFlow) {
+    // no call inside this wait, see ptx::mbar_wait_trap
+    if (!prof) {
+      ptx::mbar_wait_trap(t_full, parity);
+    } else {
+      const long long t0 = clock64();
+      ptx::mbar_wait_trap(t_full, parity);
+      w0 += clock64() - t0;
+    }
+  } else {
+    timed_wait(t_full, parity, prof, w0);
+  }
   ptx::tc_fence_after();
   MVLM_EPI_TRACE(5);
   if (grp_active && rows_active) {
@@ -293,7 +329,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
     // which spreads them over all 32 threads (2 channels x 16 pixels each): half the registers and, above all,
     // full 32-lane transpose stores -- the shared-memory pipe is what bounds these layers
     uint32_t vr[kFrag ? 16 : kCols];
-    auto tmem_load = [&](int u) {
+    auto tmem_load = [&](int u) __attribute__((always_inline)) {
       if constexpr (kFrag) ptx::tmem_ld_16x256b_x4(taddr + u * kCols, vr);
       else if constexpr (M64) ptx::tmem_ld32(taddr + u * kCols, vr);
       else ptx::tmem_ld16(taddr + u * kCols, vr);
@@ -302,7 +338,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
 #pragma unroll
     for (int r = 0; r < kMaxUpw; ++r) {
       if (r < upw) {
-        if (kHasRes && kPref < kMaxUpw && r == kPref) prefetch_batch(kPref);  // second batch
+        if (kHasRes && (kPref < kMaxUpw || kFlow) && (kFlow || r > 0) && r % kPref == 0) prefetch_batch(r);  // next batch
         const int y = y_first + kUnitRows * r;  // first image row of the unit
         ptx::tmem_ld_wait();
         if (r < 2) MVLM_EPI_TRACE(8 + 4 * r);
@@ -457,15 +493,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
 
 // flush of the running arg-max at the end of a CTA's tile range (arg-max convs have a single M tile)
 template <int F>
-__device__ __forceinline__ void epilogue_argmax_flush(const ConvShape& s, const ConvEpilogue& e, const int warp,
+__device__ __forceinline__ void epilogue_argmax_flush(const ConvShape& s, const ConvEpilogue& e, const int lane_grp,
                                                       const int lane, const ArgmaxState& am) {
   if ((F & F_ARGMAX) && am.cur_img >= 0 && am.best_hi != 0u) {
     constexpr bool M64 = (F & F_M64) != 0;
     constexpr int kM = M64 ? 64 : kMTile;
     constexpr int kChGrp = M64 ? 16 : 32;
     const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;
-    const int n_cgrp = 4 / (kM / w_rows);
-    const int c_lane = ((warp & 3) % n_cgrp) * kChGrp + lane;
+    const int n_cgrp = (4 * w_rows <= kM) ? 1 : ((2 * w_rows <= kM) ? 2 : 4);
+    const int c_lane = (lane_grp & (n_cgrp - 1)) * kChGrp + lane;
     if ((!M64 || lane < 16) && c_lane < e.cout_real)
       atomicMax(e.argmax_keys + static_cast<size_t>(am.cur_img) * e.cout_real + c_lane,
                 (static_cast<unsigned long long>(am.best_hi) << 32) | am.best_lo);

@@ -16,7 +16,12 @@ using namespace epi;
 
 // fixed operand rings (the per-layer kernel sizes them per layer; here tiles of different layers follow each
 // other through the same slots): 2 halo slots of (8+2) x (32+2) px x 128 B, 7 weight slots of 128 rows x 128 B
-constexpr int kFlowThreads = kThreads + 32;  // warp 11: completion signaller
+// warps 0..7 epilogue (two warpgroups), 8 dependency tracker + halo TMA, 9 MMA issuer, 10 weight TMA, 11 completion
+// signaller (one warpgroup): setmaxnreg moves registers from the third warpgroup to the first two
+constexpr int kFlowThreads = 384;
+constexpr int kWarpTracker = 8, kWarpMma = 9, kWarpWeights = 10, kWarpSignal = 11;
+constexpr int kEpiRegs = 224, kAuxRegs = 56;  // 2 x 128 x 224 + 128 x 56 = 64512 of the SM's 65536 registers
+constexpr int kFlowTraceSkip = 256;          // debug timeline: items of CTA 0 skipped before tracing starts
 constexpr int kHSlots = 2;
 constexpr int kWSlots = 7;
 constexpr int kHSlotBytes = 44032;
@@ -119,10 +124,12 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   }
 }
 
-// Element-wise items on the 256 epilogue threads: one 8 px x 32 row tile of the OUTPUT, all channels, as
+// Element-wise items on the 256 epilogue threads: one 8 px x kFlowEltRows tile of the OUTPUT, all channels, as
 // (pixel, 8 channels) 16-byte vectors; the arithmetic is that of pool2_act_kernel / bn_relu_kernel (eltwise.cu).
-__device__ __forceinline__ void elt_tile(const LayerSm& L, const Item& it, const int tid) {
-  const bool pool = L.kind == FLOW_POOL;
+// (not inlined: inside the epilogue warps' loop its load buffers upset the register allocation of the conv variants,
+// which then spill their residual prefetch buffers)
+template <bool pool>
+__device__ __noinline__ void elt_tile(const LayerSm& L, const Item& it, const int tid) {
   const int c8 = L.s.cin >> 3;
   const int hi = L.s.h, wi = L.s.w;
   const int ho = pool ? hi >> 1 : hi, wo = pool ? wi >> 1 : wi;
@@ -131,10 +138,11 @@ __device__ __forceinline__ void elt_tile(const LayerSm& L, const Item& it, const
   uint4* out_act = reinterpret_cast<uint4*>(L.e.out_post);
   const int img_in = it.img % L.ring_in;
   const int img_raw = it.img % L.ring_raw, img_act = it.img % L.ring_post;
-  const int n_vec = kTileW * kMaxTileH * c8;
-  constexpr int kU = 4;  // vectors per thread in flight: the loop is latency-bound (L2 round trips) otherwise
+  const int n_vec = kTileW * kFlowEltRows * c8;
+  // output vectors per thread in flight (16 / 8 loads): the loop is latency-bound (L2 round trips) otherwise
+  constexpr int kU = pool ? 4 : 8;
   for (int v0 = tid; v0 < n_vec; v0 += kU * kEpiWarps * 32) {
-    uint4 q[kU][4];
+    uint4 q[kU][pool ? 4 : 1];
     size_t o_idx[kU];
     bool ok[kU];
     int cvs[kU];
@@ -144,7 +152,7 @@ __device__ __forceinline__ void elt_tile(const LayerSm& L, const Item& it, const
       const int cv = v % c8;
       const int px = v / c8;
       const int x = it.tx * kTileW + (px & 7);
-      const int y = it.ty * kMaxTileH + (px >> 3);
+      const int y = it.ty * kFlowEltRows + (px >> 3);
       ok[u] = v < n_vec && x < wo && y < ho;
       cvs[u] = cv;
       o_idx[u] = (static_cast<size_t>(y) * wo + x) * c8 + cv;
@@ -188,24 +196,30 @@ __device__ __forceinline__ void elt_tile(const LayerSm& L, const Item& it, const
   }
 }
 
-// One epilogue variant per (non-inlined) function: inlined into the kernel's switch, the ~30 variants share one
-// register allocation and the widest ones spill; as separate functions each gets its own.
+// One epilogue variant, inlined into the epilogue warps' switch.  (As separate non-inlined functions the variants
+// kept their residual prefetch buffers on the stack -- every prefetched line was stored to local memory as soon as it
+// arrived, one L2 round trip per load -- and inlined under the kernel-wide 168-register cap the widest variants
+// spill; the epilogue warpgroups therefore raise their register allocation with setmaxnreg, see the kernel.)
 template <int F>
-__device__ __noinline__ void flow_epilogue(const LayerSm* L, const int mt, const int tx, const int ty, const int img,
-                                           uint64_t* t_full, const uint32_t parity, const uint32_t tmem_acc,
-                                           float* stage, const int warp, const int lane, long long* wait_cycles) {
+__device__ __forceinline__ void flow_epilogue(const LayerSm* L, const int mt, const int tx, const int ty, const int img,
+                                              uint64_t* t_full, const uint32_t parity, const uint32_t tmem_acc,
+                                              float* stage, const int ew, const int lane, long long* wait_cycles,
+                                              long long* trace_row, const long long trace_t0) {
   const TileCoord tc = {mt, tx, ty, img};
-  const ImageSlots is = {img % L->ring_pre, img % L->ring_raw, img % L->ring_post,
-                         img % L->ring_res1, img % L->ring_res2, img % L->ring_up};
+  // image -> slot of each tensor's buffer; the division only runs for ring buffers shorter than the image index
+  auto slot = [img](int ring) __attribute__((always_inline)) { return img < ring ? img : img % ring; };
+  const ImageSlots is = {slot(L->ring_pre), slot(L->ring_raw), slot(L->ring_post),
+                         slot(L->ring_res1), slot(L->ring_res2), slot(L->ring_up)};
   ArgmaxState am;
   EpiTrace tr;
+  tr.trace = trace_row; tr.trace_i = 0; tr.t0 = trace_t0; tr.on = trace_row != nullptr;
   long long w0 = 0;
-  epilogue_tile<F, true>(L->s, L->e, L->tile_h, L->cp, tc, is, t_full, parity, tmem_acc, stage, warp, lane, am,
+  epilogue_tile<F, true>(L->s, L->e, L->tile_h, L->cp, tc, is, t_full, parity, tmem_acc, stage, ew, ew & 3, lane, am,
                          wait_cycles != nullptr, w0, tr);
   if (wait_cycles) *wait_cycles += w0;
 }
 
-// (352 threads are allocated as 12 warps, so 168 registers per thread is the most this block shape can have)
+// (launched with 168 registers per thread, the most 12 warps can have; re-balanced at run time)
 __global__ void __launch_bounds__(kFlowThreads, 1)
 conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ layers_sm, const int n_layers,
                  const int4* __restrict__ items,
@@ -231,7 +245,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
     const int n_words = n_layers * static_cast<int>(sizeof(LayerSm) / 4);
     for (int i = threadIdx.x; i < n_words; i += kFlowThreads) dst[i] = __ldg(src + i);
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTracker && lane == 0) {
     for (int i = 0; i < kHSlots; ++i) {
       ptx::mbar_init(&bar->h_full[i], 1);
       ptx::mbar_init(&bar->h_empty[i], 1);
@@ -248,7 +262,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
     for (int i = 0; i < kEpiWarps; ++i) bar->epi_count[i] = 0;
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     ptx::tmem_alloc(&bar->tmem_base, 512);
     ptx::tmem_relinquish();
   }
@@ -268,7 +282,11 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
   const long long t_kernel0 = clock64();
   long long w0 = 0, w1 = 0;
 
-  if (warp == 0) {
+  // register re-allocation (all threads of a warpgroup execute it): the epilogue variants want up to ~200 registers,
+  // the single-thread roles a few dozen
+  if (warp >= kEpiWarps) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
+  if (warp == kWarpTracker) {
     // ===================== dependency tracker + TMA producer: activations =====================
     if (ptx::elect_one()) {
       int sh = 0;
@@ -321,7 +339,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
       }
       if (prof) { pc[0] = w0; pc[1] = w1; }
     }
-  } else if (warp == 10) {
+  } else if (warp == kWarpWeights) {
     // ===================== TMA producer: weights =====================
     if (ptx::elect_one()) {
       int sw = 0;
@@ -336,7 +354,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         const FlowLayer& GL = layers[it.layer];
         const int kM = (L.f & F_M64) ? 64 : kMTile;
         const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;
-        const int rep = kM / w_rows;
+        const int rep = (4 * w_rows <= kM) ? 4 : ((2 * w_rows <= kM) ? 2 : 1);
         const int n_chunks = (s.cin + 63) >> 6;
         for (int c = 0; c < n_chunks; ++c) {
           const bool is_tail = L.tail != 0 && c == n_chunks - 1;
@@ -354,7 +372,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       int sh = 0, sw = 0;
@@ -415,7 +433,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
       }
       if (prof) { pc[2] = w0; pc[3] = w1; pc[4] = clock64() - t_kernel0; }
     }
-  } else if (warp == 11) {
+  } else if (warp == kWarpSignal) {
     // ===================== completion signaller =====================
     // An epilogue warp only notes (CTA scope) that it has issued the stores of its part of an item.  This thread
     // waits until all eight have, makes those stores visible at GPU scope with ONE fence (cumulative over what it
@@ -447,9 +465,11 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         }
       }
     }
+  }
   } else {
     // ===================== epilogue / element-wise items =====================
-    float* stage = stage_all + (warp - 2) * kStageFloats;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    float* stage = stage_all + warp * kStageFloats;
     int acc = 0;
     uint32_t pacc = 0;
     int k = 0;
@@ -458,6 +478,7 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
       const Item it = decode_item(nxt);
       if (i + step < n_items) nxt = __ldg(items + i + step);
       ++k;
+      const long long t_item0 = prof ? clock64() : 0;
       // the tracker (warp 0) has seen this item's dependencies satisfied; normally it is tiles ahead
       if (ld_acquire_cta_shared(&bar->deps_ok) < k) {
         const long long t0 = clock64();
@@ -465,13 +486,20 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         w1 += clock64() - t0;
       }
       const LayerSm& L = lsm[it.layer];
+      // timeline of CTA 0, warp 2 (items kFlowTraceSkip .. +kTraceTiles): [0] item fetched, [1] dependencies seen,
+      // [2] layer, [3] item ordinal, [5] accumulator ready, [8..15] first two units (conv_umma.cu), [6] item done
+      long long* trow = nullptr;
+      if (prof && blockIdx.x == 0 && warp == 0 && lane == 0 && k > kFlowTraceSkip && k <= kFlowTraceSkip + kTraceTiles) {
+        trow = prof_buf + kNumSMs * 8 + (k - 1 - kFlowTraceSkip) * 16;
+        trow[0] = t_item0 - t_kernel0; trow[1] = clock64() - t_kernel0; trow[2] = it.layer; trow[3] = k;
+      }
       if (L.kind == FLOW_CONV) {
         const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(acc * 256);
         switch (L.f) {
 #define MVLM_FLOW_CASE(FLAGS)                                                                                      \
   case (FLAGS):                                                                                                    \
     flow_epilogue<(FLAGS)>(&L, it.mt, it.tx, it.ty, it.img, &bar->t_full[acc], pacc, tmem_acc, stage, warp, lane, \
-                           prof ? &w0 : nullptr);                                                                   \
+                           prof ? &w0 : nullptr, trow, t_kernel0);                                                  \
     break;
 #define MVLM_FLOW_CASE_M64(FLAGS) MVLM_FLOW_CASE((FLAGS) | F_M64)
           MVLM_FLOW_VARIANTS_BOTH(MVLM_FLOW_CASE)
@@ -491,19 +519,21 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         if (lane == 0) ptx::mbar_arrive(&bar->t_empty[acc]);
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       } else {
-        elt_tile(L, it, (warp - 2) * 32 + lane);
+        if (L.kind == FLOW_POOL) elt_tile<true>(L, it, warp * 32 + lane);
+        else elt_tile<false>(L, it, warp * 32 + lane);
         __syncwarp();
       }
       // this warp's part of the item is stored (the signaller publishes the item once all eight say so)
       __syncwarp();
-      if (lane == 0) st_release_cta_shared(&bar->epi_count[warp - 2], k);
+      if (lane == 0) st_release_cta_shared(&bar->epi_count[warp], k);
+      if (trow) trow[6] = clock64() - t_kernel0;
     }
-    if (prof && warp == 2 && lane == 0) { pc[5] = w0; pc[6] = w1; pc[7] = clock64() - t_kernel0; }
+    if (prof && warp == 0 && lane == 0) { pc[5] = w0; pc[6] = w1; pc[7] = clock64() - t_kernel0; }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -542,7 +572,6 @@ int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, in
                  "flow: layer %d has a bad tile grid", l);
     if (L.kind == FLOW_CONV) {
       MVLM_REQUIRE(supported_mask(L.f), "flow: layer %d has an unsupported epilogue mask 0x%x", l, L.f);
-      MVLM_REQUIRE(L.p.tile_h == kMaxTileH, "flow: layer %d is lower than one tile (%d rows)", l, L.p.tile_h);
       MVLM_REQUIRE(!e.out_f32 && !e.argmax_keys, "flow: head layers run through conv_launch");
     } else {
       MVLM_REQUIRE(s.in && s.cin % 8 == 0 && (e.out_raw || e.out_post), "flow: bad element-wise layer %d", l);

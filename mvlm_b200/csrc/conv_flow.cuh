@@ -23,8 +23,10 @@
 
 namespace mvlm {
 
-constexpr int kFlowMaxLayers = 16;  // layers per segment (their parameters are staged in shared memory)
+constexpr int kFlowMaxLayers = 20;  // layers per segment (their parameters are staged in shared memory)
 constexpr int kFlowMaxDeps = 10;
+constexpr int kFlowEltRows = 8;  // element-wise items cover 8 px x 8 rows of their output (short items: a long one
+                                 // delays every group that waits for its group)
 
 enum FlowKind : int { FLOW_CONV = 0, FLOW_POOL = 1, FLOW_BNRELU = 2 };
 

@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const ImageSlots is = {tc.img, tc.img, tc.img, tc.img, tc.img, tc.img};
       tr.trace_i = trace_i;
       epilogue_tile<F, false>(s, e, p.tile_h, cp, tc, is, &bar->t_full[acc], pacc,
-                              tmem_base + static_cast<uint32_t>(acc * 256), stage, warp, lane, am, prof, w0, tr);
+                              tmem_base + static_cast<uint32_t>(acc * 256), stage, warp - 2, warp & 3, lane, am, prof, w0,
+                              tr);
       // all tcgen05.ld of this accumulator stage have completed (wait::ld above)
       ptx::tc_fence_before();
       __syncwarp();
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       ++trace_i;
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
-    epilogue_argmax_flush<F>(s, e, warp, lane, am);
+    epilogue_argmax_flush<F>(s, e, warp & 3, lane, am);
     if (prof && warp == 2 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = w0; p.prof[blockIdx.x * 8 + 6] = clock64() - t_kernel0; }
   }
 

@@ -118,17 +118,32 @@ void* HourglassNet::ws_alloc(size_t bytes) {
   return p;
 }
 
+// Output resolution (rows) of an op, the quantity the dataflow window is defined on; -1: the op kind never joins a
+// segment (stem staging, memset, peaks, the arg-max head).
+static int op_out_rows(const NetOp& op) {
+  switch (op.kind) {
+    case NetOp::CONV: return op.is_head ? -1 : op.h;
+    case NetOp::POOL: return op.h / 2;
+    case NetOp::BNRELU: return op.h;
+    default: return -1;
+  }
+}
+
+// Consecutive ops whose output resolution lies in [flow_lo_, flow_hi_] form dataflow segments of at most
+// kFlowMaxLayers layers (a segment boundary is a launch boundary, i.e. a full dependency, so any cut is legal).
 void HourglassNet::push_op(const NetOp& op) {
+  const int rows = op_out_rows(op);
+  const bool in_window = flow_on_ && rows >= flow_lo_ && rows <= flow_hi_;
+  if (!in_window) {
+    cur_seg_ = -1;
+  } else if (cur_seg_ < 0 || cur_seg_layers_ >= kFlowMaxLayers) {
+    cur_seg_ = n_segs_++;
+    cur_seg_layers_ = 0;
+  }
+  if (in_window) ++cur_seg_layers_;
   ops_.push_back(op);
   op_seg_.push_back(cur_seg_);
 }
-
-void HourglassNet::seg_begin(int res) {
-  if (cur_seg_ >= 0 || !flow_on_ || res < flow_min_h_ || res < 32) return;
-  cur_seg_ = n_segs_++;
-}
-
-void HourglassNet::seg_end() { cur_seg_ = -1; }
 
 HourglassNet::T HourglassNet::alloc(int h, int w, int c) {
   T t;
@@ -221,6 +236,7 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
   NetOp op;
   op.kind = NetOp::CONV;
   op.tag = tag;
+  op.h = in.h; op.w = in.w;
   if (!dry_) {
     ConvShape s;
     s.in = in.p; s.n = V_; s.h = in.h; s.w = in.w; s.cin = cin; s.in_cs = in.c;
@@ -322,19 +338,14 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
   for (int lvl = 0; lvl < 5; ++lvl) {
     const std::string lb = p + ".rb" + std::to_string(low_blocks[lvl]);
     T pooled = alloc(cur.h / 2, cur.w / 2, F), a = alloc(cur.h / 2, cur.w / 2, F);
-    // the pool closes the dataflow segment of the level above (it reads that level's output); the level's own
-    // down-path block opens the next one
     rc = emit_pool(cur, pooled, (lb + ".bn1").c_str(), a);
     if (rc) return rc;
-    seg_end();
-    seg_begin(pooled.h);
     const int nxt = lvl < 4 ? skip_blocks[lvl] : 11;
     const std::string post = p + ".rb" + std::to_string(nxt) + ".bn1";
     rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_lows[lvl], &lows[lvl]);
     if (rc) return rc;
     cur = lows[lvl];
   }
-  seg_end();
   T low2, a2, low3;
   rc = rb(p + ".rb11", cur, a_lows[4], none, F, F, (p + ".rb12.bn1").c_str(), &a2, &low2);
   if (rc) return rc;
@@ -347,7 +358,6 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
     const std::string b1 = p + ".rb" + std::to_string(ups[lvl][0]);
     const std::string b2 = p + ".rb" + std::to_string(ups[lvl][1]);
     T s, a;
-    seg_begin(lows[3 - lvl].h);  // skip block + the two up-path blocks of one level
     rc = rb(sb, lows[3 - lvl], a_lows[3 - lvl], none, F, F, (b1 + ".bn1").c_str(), &a, &s, nullptr, &cur);
     if (rc) return rc;
     T l1, a1, l2;
@@ -355,11 +365,8 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
     if (rc) return rc;
     rc = rb(b2, l1, a1, none, F, F, nullptr, nullptr, &l2);
     if (rc) return rc;
-    seg_end();
     cur = l2;
   }
-  // rb1 opens the segment of the full-resolution trunk that follows the hourglass (closed by the caller)
-  seg_begin(x.h);
   T add5;
   rc = rb(p + ".rb1", x, a_x, none, F, F, nullptr, nullptr, &add5, nullptr, &cur);
   if (rc) return rc;
@@ -382,10 +389,11 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   if (Lp_ == 16) Lp_ = 32;
   ws_ = static_cast<uint8_t*>(workspace); ws_size_ = workspace_bytes; ws_off_ = 0;
   ops_.clear(); flops_ = 0.0;
-  op_seg_.clear(); segs_.clear(); seg_info_.clear(); cur_seg_ = -1; n_segs_ = 0;
+  op_seg_.clear(); segs_.clear(); seg_info_.clear(); cur_seg_ = -1; n_segs_ = 0; cur_seg_layers_ = 0;
   // experiment knobs of the dataflow plan (defaults in hourglass.cuh)
   if (const char* v = getenv("MVLM_FLOW")) flow_on_ = atoi(v) != 0;
-  if (const char* v = getenv("MVLM_FLOW_MIN_H")) flow_min_h_ = std::max(32, atoi(v));
+  if (const char* v = getenv("MVLM_FLOW_LO")) flow_lo_ = std::max(1, atoi(v));
+  if (const char* v = getenv("MVLM_FLOW_HI")) flow_hi_ = atoi(v);
   if (const char* v = getenv("MVLM_FLOW_TILES")) flow_tiles_ = std::max(1, atoi(v));
   if (const char* v = getenv("MVLM_FLOW_K")) flow_interleave_ = std::max(1, atoi(v));
   int rc;
@@ -401,10 +409,10 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
     op.out_raw = img16.p; op.h = h; op.w = w; op.c = cin;
     push_op(op);
     flops_ += 2.0 * 64 * cin * 9 * h * w;
-    seg_begin(h2);  // trunk segment: conv1 .. conv4 block and the first hourglass's first pool
     NetOp cv;
     cv.kind = NetOp::CONV;
     cv.tag = "conv1";
+    cv.h = h; cv.w = w;
     if (!dry_) {
       const float* w1 = nullptr;
       if ((rc = sd_get("conv1.weight", 64ll * cin * 9, &w1))) return rc;
@@ -490,7 +498,6 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
     if ((rc = emit_conv("conv10", ll2, F, "conv10", L_, Lp_, Lp_, 3, e, true))) return rc;
   }
   probes["x10"] = {x10.p, x10.h, x10.w, x10.c};
-  seg_end();
   // ---- conv11 on nearest-x2(conv10) (:428-429) as four 2x2 phase convs with fused arg-max
   keys_ = static_cast<unsigned long long*>(ws_alloc(sizeof(unsigned long long) * V_ * L_));
   {
@@ -508,6 +515,7 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
       op.kind = NetOp::CONV;
       op.is_head = true;
       op.tag = "conv11.phase";
+      op.h = h2; op.w = w2;
       if (!dry_) {
         const float* w11 = nullptr;
         if ((rc = sd_get("conv11.weight", 9ll * L_ * L_, &w11))) return rc;
@@ -588,7 +596,7 @@ int HourglassNet::build_segments() {
         if (op.out_act) { L.cp.post_s = op.scale; L.cp.post_t = op.shift; }
         L.p.tile_h = epi::kMaxTileH;
         d.tiles_x = ceil_div(pool ? op.w / 2 : op.w, epi::kTileW);
-        d.tiles_y = ceil_div(pool ? op.h / 2 : op.h, epi::kMaxTileH);
+        d.tiles_y = ceil_div(pool ? op.h / 2 : op.h, kFlowEltRows);
         d.n_nt = 1;
       } else {
         MVLM_REQUIRE(false, "hourglass: op kind %d cannot run inside a dataflow segment", static_cast<int>(op.kind));
@@ -596,7 +604,9 @@ int HourglassNet::build_segments() {
       layers.push_back(d);
     }
     MVLM_REQUIRE(!layers.empty() && min_tiles < (1 << 30), "hourglass: empty dataflow segment %d", sgm);
-    const int batch = std::min(V_, ceil_div(flow_tiles_, min_tiles));
+    // views per batch: enough for flow_tiles_ tiles per group, but at least flow_interleave_ batches (the low
+    // levels have one tile per view: three batches of a third of the views keep their dependent chains overlapped)
+    const int batch = std::max(1, std::min(ceil_div(flow_tiles_, min_tiles), ceil_div(V_, flow_interleave_)));
     seg_info_[sgm].batch = batch;
     seg_info_[sgm].n_layers = static_cast<int>(layers.size());
     const int rc = flow_build_segment(layers, V_, batch, flow_interleave_, &owned_, &segs_[sgm]);
@@ -700,6 +710,8 @@ int HourglassNet::profile_ops(const unsigned char* img_u8, const float* img_f32,
             for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] += static_cast<double>(host[c * 8 + k]);
           }
           for (int k = 0; k < 8; ++k) roles_out[i * 8 + k] /= ctas > 0 ? ctas : 1;
+          if (trace_out && static_cast<int>(i) == trace_op)
+            for (int k = 0; k < kConvTraceTiles * 16; ++k) trace_out[k] = host[kNumSMs * 8 + k];
         }
         continue;
       }

@@ -92,15 +92,19 @@ class HourglassNet {
   int hourglass(const std::string& p, T x, T a_x, T* out);
   int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
 
-  // ---- dataflow segments (conv_flow.cuh): consecutive ops executed by ONE persistent launch over small view
-  // batches, so that their intermediate tensors stay in L2.  Ops emitted between seg_begin() / seg_end() belong
-  // to the segment; op_seg_[i] = segment of op i or -1 (per-layer launch).
+  // ---- dataflow segments (conv_flow.cuh): runs of consecutive ops executed by ONE persistent launch over view
+  // batches with tile-level dependencies instead of one launch per layer.  op_seg_[i] = segment of op i or -1
+  // (per-layer launch); push_op assigns them from the ops' output resolution.
   void push_op(const NetOp& op);
-  void seg_begin(int res);
-  void seg_end();
   int build_segments();
-  bool flow_on_ = true;
-  int flow_min_h_ = 64;      // hourglass levels at least this high run as dataflow segments
+  // Off unless MVLM_FLOW=1: measured on the headline workload (profiles/r2_flow_experiments.txt) the segments are
+  // bit-identical to the per-layer launches but not faster -- 18.0 ms against 18.0 ms with the hourglass levels of
+  // <= 32 rows in segments (2 x 55 latency-bound launches become 2 x 3), 20.0 ms with the large layers in them (their
+  // epilogues cannot prefetch residuals across the accumulator wait without spilling) -- so the default plan keeps one
+  // launch per layer.  Ops whose output is flow_lo_ .. flow_hi_ rows high run in segments when it is on.
+  bool flow_on_ = false;
+  int flow_lo_ = 1, flow_hi_ = 32;
+  int cur_seg_layers_ = 0;
   int flow_tiles_ = 64;      // views per batch = smallest count giving every conv group this many tiles
   int flow_interleave_ = 3;  // batches advanced in lock step
   int cur_seg_ = -1, n_segs_ = 0;

@@ -32,13 +32,14 @@ def _build(env, *args):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("n_landmarks,mode,size,views,min_h,tiles,k", [
-    (73, "RGB+depth", 128, 7, 32, 64, 3),    # trunk + two hourglass levels as segments, ragged last batch
-    (84, "geometry+depth", 128, 3, 64, 16, 2),
-    (73, "RGB+depth", 256, 5, 64, 64, 3),    # the headline geometry (segment layout of the 100-view plan)
-    (73, "RGB", 256, 4, 32, 128, 1),         # no interleave: every group waits for the one right before it
+@pytest.mark.parametrize("n_landmarks,mode,size,views,lo,hi,tiles,k", [
+    (73, "RGB+depth", 128, 7, 1, 32, 64, 3),      # the default window: hourglass levels of <= 32 rows (tiles of 32 .. 4 rows)
+    (73, "RGB+depth", 128, 7, 32, 128, 64, 3),    # the large layers as segments, ragged last batch
+    (84, "geometry+depth", 128, 3, 1, 1024, 16, 2),  # everything the kernel supports in segments
+    (73, "RGB+depth", 256, 5, 1, 32, 64, 3),      # the headline geometry (segment layout of the 100-view plan)
+    (73, "RGB", 256, 4, 64, 256, 128, 1),         # no interleave: every group waits for the one right before it
 ])
-def test_flow_equals_per_layer_plan(lib, n_landmarks, mode, size, views, min_h, tiles, k):
+def test_flow_equals_per_layer_plan(lib, n_landmarks, mode, size, views, lo, hi, tiles, k):
     sd = seeded_state_dict(n_landmarks, mode, seed=1234)
     cin = IMAGE_CHANNELS[mode]
     g = torch.Generator().manual_seed(11)
@@ -47,7 +48,7 @@ def test_flow_equals_per_layer_plan(lib, n_landmarks, mode, size, views, min_h, 
     img = img.cuda()
     args = (sd, n_landmarks, cin, views, size, size)
     ref = _build({"MVLM_FLOW": "0"}, *args)
-    flow = _build({"MVLM_FLOW": "1", "MVLM_FLOW_MIN_H": str(min_h), "MVLM_FLOW_TILES": str(tiles),
+    flow = _build({"MVLM_FLOW": "1", "MVLM_FLOW_LO": str(lo), "MVLM_FLOW_HI": str(hi), "MVLM_FLOW_TILES": str(tiles),
                    "MVLM_FLOW_K": str(k)}, *args)
     assert flow.num_segments > 0 and ref.num_segments == 0
     pk_ref, hm_ref = ref.forward(img, want_heatmaps=True)

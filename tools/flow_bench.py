@@ -1,6 +1,6 @@
 """CNN stage time of the dataflow plan vs the per-layer plan at the headline workload (GPU box).
 
-usage: python tools/flow_bench.py [V] [S] [--cfg=min_h,tiles,k ...]   (several --cfg allowed)
+usage: python tools/flow_bench.py [V] [S] [--cfg=lo,hi,tiles,k ...]   (several --cfg allowed)
 """
 import os
 import sys
@@ -16,7 +16,7 @@ build.build()
 pos = [a for a in sys.argv[1:] if not a.startswith("--")]
 V = int(pos[0]) if len(pos) > 0 else 100
 S = int(pos[1]) if len(pos) > 1 else 256
-cfgs = [a.split("=")[1] for a in sys.argv[1:] if a.startswith("--cfg=")] or ["64,64,3"]
+cfgs = [a.split("=")[1] for a in sys.argv[1:] if a.startswith("--cfg=")] or ["1,32,64,3"]
 sd = seeded_state_dict(73, "RGB+depth", 1234)
 img = torch.randint(0, 256, (V, S, S, 4), dtype=torch.uint8, device="cuda")
 
@@ -41,12 +41,12 @@ print(f"per-layer plan: {t_ref:.3f} ms  ({ref.num_launches} ops, workspace {ref.
 del ref
 torch.cuda.empty_cache()
 for cfg in cfgs:
-    min_h, tiles, k = cfg.split(",")
-    os.environ.update({"MVLM_FLOW": "1", "MVLM_FLOW_MIN_H": min_h, "MVLM_FLOW_TILES": tiles, "MVLM_FLOW_K": k})
+    lo, hi, tiles, k = cfg.split(",")
+    os.environ.update({"MVLM_FLOW": "1", "MVLM_FLOW_LO": lo, "MVLM_FLOW_HI": hi, "MVLM_FLOW_TILES": tiles, "MVLM_FLOW_K": k})
     net = ops.Hourglass(sd, 73, 4, V, S, S)
     t, pk = timed(net)
     same = torch.equal(pk.view(torch.int32), pk_ref.view(torch.int32))
-    print(f"dataflow plan min_h={min_h} tiles={tiles} k={k}: {t:.3f} ms  ({net.num_segments} segments, workspace "
+    print(f"dataflow plan rows {lo}..{hi} tiles={tiles} k={k}: {t:.3f} ms  ({net.num_segments} segments, workspace "
           f"{net.workspace.numel() / 1e9:.2f} GB)  peaks identical: {same}", flush=True)
     del net
     torch.cuda.empty_cache()

@@ -27,7 +27,17 @@ for a in sys.argv:
 trace = (C.c_longlong * (64 * 16))()
 _lib.check(lib.mvlm_debug_hourglass_profile(net._h, img.data_ptr(), None, peaks.data_ptr(), 5, ms, roles, trace_op, trace,
                                             torch.cuda.current_stream().cuda_stream), "profile")
-if trace_op >= 0:
+if trace_op >= 0 and "--flow" in sys.argv:
+    print(f"timeline of CTA 0 / epilogue warp 2, segment at op {trace_op}: item | layer | fetched, deps-seen, acc-ready, done | "
+          "item-span | unit0: ld sts out end | unit1: ld sts out end")
+    for t in range(64):
+        r = [trace[t * 16 + k] for k in range(16)]
+        if r[3] == 0:
+            continue
+        print(f"  item {r[3]:5d} layer {r[2]:2d} | {r[0]:9d} {r[1] - r[0]:6d} {r[5] - r[0] if r[5] else -1:6d} {r[6] - r[0]:6d} | "
+              f"unit0: ld {r[8] - r[5]:5d} sts {r[9] - r[8]:5d} out {r[10] - r[9]:5d} end {r[11] - r[10]:5d} | unit1: ld {r[12] - r[11]:5d} "
+              f"sts {r[13] - r[12]:5d} out {r[14] - r[13]:5d} end {r[15] - r[14]:5d}")
+elif trace_op >= 0:
     lib.mvlm_debug_hourglass_describe(net._h, trace_op, C.create_string_buffer(256), 256)
     print(f"timeline of CTA 0, op {trace_op} (cycles since kernel start): tile | P halo-issued, P weights-issued | "
           "M acc-acquired, M halo-landed, M issued | E acc-ready, E released")
