@@ -232,8 +232,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
   const int xa = tc.tx * kTileW + pj;
   const bool vx = ch_ok && xa < s.w;
-  // element index of my pixel in pass 0 of the first unit of image `img`: (img, y_first + my_i, xa); 32-bit: pixel
-  // count x channel stride < 2^31 (checked in conv_plan)
+  // PIXEL index of my pixel in pass 0 of the first unit of image `img`: (img, y_first + my_i, xa); 32-bit (checked in
+  // conv_plan), widened before it is multiplied with a channel stride
   auto pix_of = [&](int img) __attribute__((always_inline)) { return (static_cast<uint32_t>(img) * s.h + y_first + my_i) * s.w + xa; };
   // element index of the half-resolution pixel (img, y_first/2, xa/2): F_POOL outputs, F_UP input
   auto ppix_of = [&](int img) __attribute__((always_inline)) {

@@ -409,11 +409,8 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   MVLM_REQUIRE(!e.mid_scale || (e.mid_shift && !e.out_f32 && !e.argmax_keys), "conv_plan: mid affine needs mid_shift and bf16 outputs");
   MVLM_REQUIRE(!((e.argmax_keys || e.out_f32) && (e.res1 || e.res2 || e.out_pre || e.out_raw || e.out_post)),
                "conv_plan: fp32 / arg-max outputs cannot be combined with bf16 outputs or residual inputs");
-  {
-    const long long npix = 1ll * s.n * s.h * s.w;
-    const int max_cs = std::max(std::max(std::max(e.pre_cs, e.raw_cs), std::max(std::max(e.post_cs, e.res1_cs), e.res2_cs)), e.up_cs);
-    MVLM_REQUIRE(npix * std::max(max_cs, 1) < (1ll << 31), "conv_plan: tensor too large for 32-bit element offsets");
-  }
+  // pixel indices are 32-bit (they are widened before the multiplication with a channel stride)
+  MVLM_REQUIRE(1ll * s.n * s.h * s.w < (1ll << 32), "conv_plan: %d x %d x %d pixels exceed 32-bit pixel indices", s.n, s.h, s.w);
   MVLM_REQUIRE(s.kh >= 1 && s.kh <= 3 && s.kw >= 1 && s.kw <= 3, "conv_plan: kernel %dx%d unsupported", s.kh, s.kw);
   MVLM_REQUIRE((reinterpret_cast<uintptr_t>(s.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(s.wpacked) & 15) == 0,
                "conv_plan: pointers must be 16-byte aligned");

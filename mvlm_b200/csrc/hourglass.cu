@@ -111,11 +111,117 @@ HourglassNet::~HourglassNet() {
   for (void* p : owned_) cudaFree(p);
 }
 
+// Workspace allocation with buffer reuse.  The plan is emitted twice: a LAYOUT pass (no CUDA calls) hands out fake,
+// never-reused addresses and records for every buffer the first and the last op that touches it; assign_offsets()
+// then packs the buffers so that two share memory only when their lifetimes are disjoint (launches are stream-
+// ordered, and programmatic dependent launch only overlaps a kernel's prologue, which touches no activation); the
+// real pass hands out the packed addresses in the same allocation order.  20.3 GB -> a few GB at 100 views of 256^2.
+static uint8_t* const kFakeBase = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(1) << 44);
+
 void* HourglassNet::ws_alloc(size_t bytes) {
   const size_t aligned = (bytes + 1023) & ~static_cast<size_t>(1023);
-  void* p = (dry_ || ws_ == nullptr) ? nullptr : ws_ + ws_off_;
-  ws_off_ += aligned;
-  return p;
+  if (layout_pass_) {
+    Buf b;
+    b.bytes = aligned;
+    b.fake_off = fake_off_;
+    bufs_.push_back(b);
+    fake_off_ += aligned;
+    return kFakeBase + b.fake_off;
+  }
+  if (dry_ || ws_ == nullptr || next_buf_ >= bufs_.size()) return nullptr;
+  return ws_ + bufs_[next_buf_++].offset;
+}
+
+// the op about to be pushed reads or writes the buffer `p` points into
+void HourglassNet::note_use(const void* p) {
+  if (!layout_pass_ || p == nullptr) return;
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  if (q < kFakeBase || q >= kFakeBase + fake_off_) return;
+  const size_t off = static_cast<size_t>(q - kFakeBase);
+  // buffers are in address order: last one starting at or before `off`
+  size_t lo = 0, hi = bufs_.size();
+  while (hi - lo > 1) {
+    const size_t mid = (lo + hi) / 2;
+    if (bufs_[mid].fake_off <= off) lo = mid; else hi = mid;
+  }
+  Buf& b = bufs_[lo];
+  const int op = static_cast<int>(ops_.size());
+  if (b.first < 0) b.first = op;
+  b.last = std::max(b.last, op);
+}
+
+void HourglassNet::note_conv(const void* in, const ConvEpilogue& e) {
+  note_use(in); note_use(e.out_pre); note_use(e.res1); note_use(e.res2); note_use(e.res_up); note_use(e.out_raw);
+  note_use(e.out_post); note_use(e.argmax_keys);
+}
+
+void HourglassNet::assign_offsets() {
+  const int n_ops = static_cast<int>(ops_.size());
+  // a buffer touched inside a dataflow segment is live for the whole segment (its ops run interleaved)
+  std::vector<int> seg_first(n_segs_, n_ops), seg_last(n_segs_, -1);
+  for (int i = 0; i < n_ops; ++i)
+    if (op_seg_[i] >= 0) {
+      seg_first[op_seg_[i]] = std::min(seg_first[op_seg_[i]], i);
+      seg_last[op_seg_[i]] = std::max(seg_last[op_seg_[i]], i);
+    }
+  for (Buf& b : bufs_) {
+    if (b.first < 0) { b.first = 0; b.last = n_ops; }  // never referenced by an op: keep it for the whole plan
+    if (b.first < n_ops && op_seg_[b.first] >= 0) b.first = seg_first[op_seg_[b.first]];
+    if (b.last < n_ops && op_seg_[b.last] >= 0) b.last = seg_last[op_seg_[b.last]];
+    if (b.pinned || !reuse_) { b.first = 0; b.last = n_ops; }
+  }
+  // first-fit over a sorted free list, buffers taken in order of their first use
+  std::vector<size_t> order(bufs_.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return bufs_[a].first < bufs_[b].first; });
+  struct Block { size_t off, bytes; };
+  std::vector<Block> free_list;
+  std::vector<size_t> live;
+  size_t top = 0;
+  auto release = [&](size_t id) {
+    Block nb = {bufs_[id].offset, bufs_[id].bytes};
+    size_t k = 0;
+    while (k < free_list.size() && free_list[k].off < nb.off) ++k;
+    free_list.insert(free_list.begin() + k, nb);
+    for (size_t j = 0; j + 1 < free_list.size();) {  // coalesce neighbours
+      if (free_list[j].off + free_list[j].bytes == free_list[j + 1].off) {
+        free_list[j].bytes += free_list[j + 1].bytes;
+        free_list.erase(free_list.begin() + j + 1);
+      } else {
+        ++j;
+      }
+    }
+    if (!free_list.empty() && free_list.back().off + free_list.back().bytes == top) {  // give the tail back
+      top = free_list.back().off;
+      free_list.pop_back();
+    }
+  };
+  for (size_t id : order) {
+    Buf& b = bufs_[id];
+    for (size_t j = 0; j < live.size();) {
+      if (bufs_[live[j]].last < b.first) {
+        release(live[j]);
+        live.erase(live.begin() + j);
+      } else {
+        ++j;
+      }
+    }
+    size_t best = free_list.size();
+    for (size_t j = 0; j < free_list.size(); ++j)
+      if (free_list[j].bytes >= b.bytes && (best == free_list.size() || free_list[j].bytes < free_list[best].bytes)) best = j;
+    if (best < free_list.size()) {
+      b.offset = free_list[best].off;
+      free_list[best].off += b.bytes;
+      free_list[best].bytes -= b.bytes;
+      if (free_list[best].bytes == 0) free_list.erase(free_list.begin() + best);
+    } else {
+      b.offset = top;
+      top += b.bytes;
+    }
+    ws_needed_ = std::max(ws_needed_, b.offset + b.bytes);
+    ws_needed_ = std::max(ws_needed_, top);
+    live.push_back(id);
+  }
 }
 
 // Output resolution (rows) of an op, the quantity the dataflow window is defined on; -1: the op kind never joins a
@@ -149,16 +255,6 @@ HourglassNet::T HourglassNet::alloc(int h, int w, int c) {
   T t;
   t.h = h; t.w = w; t.c = c;
   t.p = static_cast<__nv_bfloat16*>(ws_alloc(static_cast<size_t>(V_) * h * w * c * sizeof(__nv_bfloat16)));
-  return t;
-}
-
-HourglassNet::T HourglassNet::scratch(int h, int w, int c, int slot) {
-  char key[64];
-  snprintf(key, sizeof(key), "%d_%d_%d_%d", h, w, c, slot);
-  auto it = scratch_.find(key);
-  if (it != scratch_.end()) return it->second;
-  T t = alloc(h, w, c);
-  scratch_[key] = t;
   return t;
 }
 
@@ -233,6 +329,7 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
   // algorithmic FLOPs use the true (unpadded) channel counts of the reference layer
   const int cin_real = (wname == "conv7") ? L_ : cin;
   flops_ += 2.0 * cout * cin_real * k * k * in.h * in.w;
+  note_conv(in.p, e);
   NetOp op;
   op.kind = NetOp::CONV;
   op.tag = tag;
@@ -277,9 +374,10 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
   }
   if (pool_raw) *pool_raw = alloc(h / 2, w / 2, cout);
   const int c1 = cout / 2, c2 = cout / 4;
-  // tightly packed intermediates (a 32-channel a2 in a 64-channel-stride buffer doubles its DRAM traffic)
-  T a1 = scratch(h, w, c1, 1);
-  T a2 = scratch(h, w, c2, 2);
+  // tightly packed intermediates (a 32-channel a2 in a 64-channel-stride buffer doubles its DRAM traffic); they die
+  // with the block, and the packing reuses their memory
+  T a1 = alloc(h, w, c1);
+  T a2 = alloc(h, w, c2);
   const int widths[3] = {c1, c2, c2};
   const int offs[3] = {0, c1, c1 + c2};
   const int cins[3] = {cin, c1, c2};
@@ -312,6 +410,7 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
 }
 
 int HourglassNet::emit_pool(T in, T out_raw, const char* bn_name, T out_act) {
+  note_use(in.p); note_use(out_raw.p); note_use(out_act.p);
   NetOp op;
   op.kind = NetOp::POOL;
   op.in0 = in.p; op.out_raw = out_raw.p; op.out_act = out_act.p;
@@ -381,21 +480,53 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   MVLM_REQUIRE(n_views > 0 && h >= 64 && w >= 64 && h % 64 == 0 && w % 64 == 0,
                "hourglass: image size %dx%d must be a positive multiple of 64", h, w);
   MVLM_REQUIRE(dry || (sd && workspace), "hourglass: null state_dict/workspace");
-  sd_ = sd; dry_ = dry;
+  sd_ = sd;
   V_ = n_views; H_ = h; W_ = w; L_ = n_landmarks; cin_ = cin;
   Lp_ = pad_to(L_, 16);
   if (Lp_ == 112) Lp_ = 128;
   if (Lp_ == 48) Lp_ = 64;
   if (Lp_ == 16) Lp_ = 32;
-  ws_ = static_cast<uint8_t*>(workspace); ws_size_ = workspace_bytes; ws_off_ = 0;
-  ops_.clear(); flops_ = 0.0;
-  op_seg_.clear(); segs_.clear(); seg_info_.clear(); cur_seg_ = -1; n_segs_ = 0; cur_seg_layers_ = 0;
+  ws_ = static_cast<uint8_t*>(workspace); ws_size_ = workspace_bytes;
   // experiment knobs of the dataflow plan (defaults in hourglass.cuh)
   if (const char* v = getenv("MVLM_FLOW")) flow_on_ = atoi(v) != 0;
   if (const char* v = getenv("MVLM_FLOW_LO")) flow_lo_ = std::max(1, atoi(v));
   if (const char* v = getenv("MVLM_FLOW_HI")) flow_hi_ = atoi(v);
   if (const char* v = getenv("MVLM_FLOW_TILES")) flow_tiles_ = std::max(1, atoi(v));
   if (const char* v = getenv("MVLM_FLOW_K")) flow_interleave_ = std::max(1, atoi(v));
+  // MVLM_HG_KEEP_PROBES=1: the probe tensors (layer-wise parity tests) keep their memory for the whole plan;
+  // MVLM_HG_NO_REUSE=1: every buffer does (the round-1 layout, for A/B runs)
+  keep_probes_ = getenv("MVLM_HG_KEEP_PROBES") != nullptr && atoi(getenv("MVLM_HG_KEEP_PROBES")) != 0;
+  reuse_ = !(getenv("MVLM_HG_NO_REUSE") != nullptr && atoi(getenv("MVLM_HG_NO_REUSE")) != 0);
+  // layout pass: lifetimes and packed offsets
+  bufs_.clear(); fake_off_ = 0; ws_needed_ = 0; next_buf_ = 0;
+  dry_ = true; layout_pass_ = true;
+  int rc = emit();
+  layout_pass_ = false;
+  if (rc) return rc;
+  assign_offsets();
+  if (dry) return MVLM_OK;
+  MVLM_REQUIRE(ws_needed_ <= ws_size_, "hourglass: workspace too small (%zu needed, %zu given)", ws_needed_, ws_size_);
+  dry_ = false;
+  if ((rc = emit())) return rc;
+  if ((rc = build_segments())) return rc;
+  MVLM_CHECK_CUDA(cudaDeviceSynchronize());
+  return MVLM_OK;
+}
+
+void HourglassNet::probe(const char* name, const T& t) {
+  probes[name] = {t.p, t.h, t.w, t.c};
+  if (layout_pass_ && keep_probes_ && t.p) {
+    const size_t off = static_cast<size_t>(reinterpret_cast<const uint8_t*>(t.p) - kFakeBase);
+    for (Buf& b : bufs_)
+      if (b.fake_off == off) b.pinned = true;
+  }
+}
+
+// emits the plan: ops_, op_seg_, probes, flops_ (layout pass: fake addresses, no CUDA calls)
+int HourglassNet::emit() {
+  const int h = H_, w = W_, cin = cin_;
+  ops_.clear(); flops_ = 0.0; probes.clear();
+  op_seg_.clear(); segs_.clear(); seg_info_.clear(); cur_seg_ = -1; n_segs_ = 0; cur_seg_layers_ = 0;
   int rc;
   const int F = 256, h2 = h / 2, w2 = w / 2;
 
@@ -404,11 +535,13 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   T a_c2 = alloc(h, w, 64), ar_c2 = alloc(h, w, 64);
   T img16 = alloc(h, w, 16);
   {
+    note_use(img16.p);
     NetOp op;
     op.kind = NetOp::STEM;
     op.out_raw = img16.p; op.h = h; op.w = w; op.c = cin;
     push_op(op);
     flops_ += 2.0 * 64 * cin * 9 * h * w;
+    note_use(img16.p); note_use(a_c2.p); note_use(ar_c2.p);
     NetOp cv;
     cv.kind = NetOp::CONV;
     cv.tag = "conv1";
@@ -439,11 +572,12 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   // conv2 block: its output is only consumed through the max-pool (:411) -> pooled outputs straight from the epilogues
   T x1;
   if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, "conv3.bn1", &a3, &y2, &x1))) return rc;
-  probes["x1"] = {x1.p, x1.h, x1.w, x1.c};
+  probe("x1", x1);
   if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3))) return rc;
-  probes["y3"] = {y3.p, y3.h, y3.w, y3.c};
+  probe("y3", y3);
   ar4 = alloc(h2, w2, 128);
   {
+    note_use(y3.p); note_use(ar4.p);
     NetOp op;
     op.kind = NetOp::BNRELU;
     op.in0 = y3.p; op.out_act = ar4.p; op.h = h2; op.w = w2; op.c = 128;
@@ -451,11 +585,11 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
     push_op(op);
   }
   if ((rc = rb("conv4", y3, a4, ar4, 128, F, "hg1.rb1.bn1", &a_h1, &r3))) return rc;
-  probes["r3"] = {r3.p, r3.h, r3.w, r3.c};
+  probe("r3", r3);
   // ---- hourglass 1 (:414), conv5+bn2+relu (:416), conv6 (:417), conv7 + sum (:420-422)
   T hg1;
   if ((rc = hourglass("hg1", r3, a_h1, &hg1))) return rc;
-  probes["hg1"] = {hg1.p, hg1.h, hg1.w, hg1.c};
+  probe("hg1", hg1);
   T ll1 = alloc(h2, w2, F);
   {
     ConvEpilogue e;
@@ -480,7 +614,7 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
     e.out_post = a_h2.p; e.post_cs = F; e.post_co = 0;
     if ((rc = emit_conv("conv7", x6, Lp_, "conv7", F, F, 128, 3, e, true))) return rc;
   }
-  probes["sum_temp"] = {sum.p, sum.h, sum.w, sum.c};
+  probe("sum_temp", sum);
   // ---- hourglass 2 (:424), conv9+bn3+relu (:426), conv10 (:427)
   T hg2;
   if ((rc = hourglass("hg2", sum, a_h2, &hg2))) return rc;
@@ -497,10 +631,11 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
     e.out_raw = x10.p; e.raw_cs = Lp_; e.raw_co = 0;
     if ((rc = emit_conv("conv10", ll2, F, "conv10", L_, Lp_, Lp_, 3, e, true))) return rc;
   }
-  probes["x10"] = {x10.p, x10.h, x10.w, x10.c};
+  probe("x10", x10);
   // ---- conv11 on nearest-x2(conv10) (:428-429) as four 2x2 phase convs with fused arg-max
   keys_ = static_cast<unsigned long long*>(ws_alloc(sizeof(unsigned long long) * V_ * L_));
   {
+    note_use(keys_);
     NetOp op;
     op.kind = NetOp::MEMSET;
     op.ptr = keys_; op.bytes = sizeof(unsigned long long) * V_ * L_;
@@ -511,6 +646,7 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   if ((rc = bias("conv11.bias", L_, Lp_, &b11))) return rc;
   for (int a = 0; a < 2; ++a) {
     for (int b = 0; b < 2; ++b) {
+      note_use(x10.p); note_use(keys_);
       NetOp op;
       op.kind = NetOp::CONV;
       op.is_head = true;
@@ -539,14 +675,10 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
     }
   }
   {
+    note_use(keys_);
     NetOp op;
     op.kind = NetOp::PEAKS;
     push_op(op);
-  }
-  if (!dry_) {
-    MVLM_REQUIRE(ws_off_ <= ws_size_, "hourglass: workspace too small (%zu needed, %zu given)", ws_off_, ws_size_);
-    if ((rc = build_segments())) return rc;
-    MVLM_CHECK_CUDA(cudaDeviceSynchronize());
   }
   return MVLM_OK;
 }

@@ -60,7 +60,7 @@ class HourglassNet {
   // one-line description of op i ("conv rb.conv 128x128 256->128 k3 pre res1 raw", "pool 64x64x256", ...)
   std::string describe_op(int i) const;
 
-  size_t workspace_needed() const { return ws_off_; }
+  size_t workspace_needed() const { return ws_needed_; }
   int n_views() const { return V_; }
   int n_landmarks() const { return L_; }
   int height() const { return H_; }
@@ -76,8 +76,21 @@ class HourglassNet {
  private:
   struct T { __nv_bfloat16* p = nullptr; int h = 0, w = 0, c = 0; };
   T alloc(int h, int w, int c);
-  T scratch(int h, int w, int c, int slot);
   void* ws_alloc(size_t bytes);
+  // workspace packing, see ws_alloc in hourglass.cu
+  struct Buf {
+    size_t bytes = 0, fake_off = 0, offset = 0;
+    int first = -1, last = -1;  // first / last op touching the buffer
+    bool pinned = false;
+  };
+  int emit();
+  void note_use(const void* p);
+  void note_conv(const void* in, const ConvEpilogue& e);
+  void assign_offsets();
+  void probe(const char* name, const T& t);
+  std::vector<Buf> bufs_;
+  size_t fake_off_ = 0, ws_needed_ = 0, next_buf_ = 0;
+  bool layout_pass_ = false, keep_probes_ = false, reuse_ = true;
   int bn(const std::string& name, int c, const float** scale, const float** shift);
   int packed(const std::string& name, int cout, int cin, int k, int cout_pad, int cin_pad, const __nv_bfloat16** out);
   int bias(const std::string& name, int cout, int cout_pad, const float** out);
@@ -121,10 +134,9 @@ class HourglassNet {
   bool dry_ = true;
   int V_ = 0, H_ = 0, W_ = 0, L_ = 0, Lp_ = 0, cin_ = 0;
   uint8_t* ws_ = nullptr;
-  size_t ws_size_ = 0, ws_off_ = 0;
+  size_t ws_size_ = 0;
   std::vector<void*> owned_;
   std::map<std::string, std::pair<float*, float*>> bn_cache_;
-  std::map<std::string, T> scratch_;
   std::vector<NetOp> ops_;
   unsigned long long* keys_ = nullptr;
   double flops_ = 0.0;

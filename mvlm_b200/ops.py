@@ -4,6 +4,7 @@ Tensors are torch CUDA tensors used purely as device buffers.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import os
@@ -102,14 +103,37 @@ def raster_multiview(verts, uvs, tris, tex, rot, h: int, w: int, channel_mode: s
     return {"u8": out_u8, "f32": f32, "tri": tri, "z": z}
 
 
+@contextlib.contextmanager
+def _plan_env(**kv):
+    """Plan-build switches of the library are environment variables read by mvlm_hourglass_workspace_bytes / _create."""
+    old = {k: os.environ.get(k) for k in kv}
+    os.environ.update(kv)
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 class Hourglass:
     """Owns the device copy of a state_dict, the workspace and the planned network for a fixed
     (n_views, H, W).  `forward` runs the whole CNN (+ fused arg-max) on the current stream."""
 
-    def __init__(self, state_dict: dict, n_landmarks: int, cin: int, n_views: int, h: int, w: int, device="cuda"):
+    def __init__(self, state_dict: dict, n_landmarks: int, cin: int, n_views: int, h: int, w: int, device="cuda",
+                 keep_probes: bool = False):
+        """keep_probes: the intermediate tensors `probe()` returns keep their memory for the whole plan (layer-wise
+        parity tests); otherwise the workspace packing reuses it (4.4 GB instead of 8 GB at 100 views of 256^2)."""
         lib = _lib.load()
         self.n_landmarks, self.cin, self.n_views, self.h, self.w = n_landmarks, cin, n_views, h, w
         self.device = torch.device(device)
+        self.keep_probes = bool(keep_probes)
+        with _plan_env(MVLM_HG_KEEP_PROBES="1" if keep_probes else "0"):
+            self._create(lib, state_dict, n_landmarks, cin, n_views, h, w)
+
+    def _create(self, lib, state_dict, n_landmarks, cin, n_views, h, w):
         self._sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()
                     if v.is_floating_point()}
         nbytes = lib.mvlm_hourglass_workspace_bytes(n_landmarks, cin, n_views, h, w)
@@ -155,6 +179,8 @@ class Hourglass:
 
     def probe(self, name: str) -> torch.Tensor:
         """Copy of an intermediate NHWC bf16 tensor (layer-wise parity tests)."""
+        if not self.keep_probes:
+            raise _lib.MvlmError("Hourglass.probe needs keep_probes=True (the workspace packing reuses the tensor's memory)")
         lib = _lib.load()
         p, h, w, c = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
         check(lib.mvlm_hourglass_probe(self._h, name.encode(), C.byref(p), C.byref(h), C.byref(w), C.byref(c)), "probe")

@@ -63,26 +63,33 @@ class PaulsenModel(Predictor2D):
     def network(self, n_views: int, h: int, w: int) -> ops.Hourglass:
         key = (n_views, h, w)
         if key not in self._nets:
-            # at most two plans alive (20.6 GB of workspace at 100 views of 256^2): the current stack shape and, when a
-            # stack is sliced along the view axis, the shorter last slice
+            # at most two plans alive (4.4 GB of workspace each at 100 views of 256^2): the current stack shape and, when
+            # a stack is sliced along the view axis, the shorter last slice
             while len(self._nets) >= 2:
                 self._nets.pop(next(iter(self._nets)))
             if self._nets and self.device.type == "cuda":
                 free, _ = torch.cuda.mem_get_info(self.device)
-                if free < 3200 * n_views * h * w * 1.2:
+                if free < self.workspace_bytes(n_views, h, w) * 1.2:
                     self._nets.clear()
             self._nets[key] = ops.Hourglass(self._state_dict, self.get_lm_count(), IMAGE_CHANNELS[self.image_mode],
                                             n_views, h, w, device=self.device)
         return self._nets[key]
 
+    def workspace_bytes(self, n_views: int, h: int, w: int) -> int:
+        from .. import _lib
+
+        return int(_lib.load().mvlm_hourglass_workspace_bytes(self.get_lm_count(), IMAGE_CHANNELS[self.image_mode], n_views, h, w))
+
     def max_views_per_launch(self, v: int, h: int, w: int) -> int:
-        """Largest slice of the view axis one plan may take: 32-bit element offsets and, on a GPU, half of the free
-        memory for the workspace.  Prefers a divisor of v so that every slice reuses the same plan."""
-        limit = (2 ** 31 - 1) // (h * w * 256)
+        """Largest slice of the view axis one plan may take: 32-bit pixel indices and, on a GPU, half of the free
+        memory for the (packed) workspace.  Prefers a divisor of v so that every slice reuses the same plan.
+        200 views of 512^2 (config C4) are one plan of 35 GB."""
+        limit = (2 ** 32 - 1) // (h * w)
         if self.device.type == "cuda":
             free, _ = torch.cuda.mem_get_info(self.device)
             cached = sum(n.workspace.numel() for n in self._nets.values())
-            limit = min(limit, max(1, int((free + cached) * 0.5) // (h * w * 3200)))
+            per_view = max(1, self.workspace_bytes(min(v, 64), h, w) // min(v, 64))
+            limit = min(limit, max(1, int((free + cached) * 0.5) // per_view))
         if v <= limit:
             return v
         best = max(d for d in range(1, limit + 1) if v % d == 0)

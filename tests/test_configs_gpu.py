@@ -97,7 +97,8 @@ def test_c5_consensus_microbench_parity(lib):
 
 
 def test_view_axis_slicing_equals_one_launch(lib, monkeypatch):
-    """Stacks beyond one plan's limits (32-bit element offsets / workspace) run as slices of the view axis: same peaks."""
+    """Stacks beyond one plan's limits (32-bit pixel indices / half of the free memory) run as slices of the view axis:
+    same peaks.  With the packed workspace 100 views of 512^2 (17.6 GB) are ONE plan on a B200."""
     import mvlm
     from mvlm_b200.prediction.paulsenpredictor import PaulsenModel
 
@@ -108,7 +109,8 @@ def test_view_axis_slicing_equals_one_launch(lib, monkeypatch):
     dmesh = dm.renderer_3d.upload(mesh)
     u8 = dm.renderer_3d.render_device(dmesh, tr)["u8"]
     whole = dm.predictor_2d.predict_landmarks_device(u8).clone()
-    assert dm.predictor_2d.max_views_per_launch(100, 512, 512) == 25      # 2^31 / (512*512*256) = 31 -> divisor 25
+    assert dm.predictor_2d.max_views_per_launch(100, 512, 512) == 100     # was 25 with the unpacked 20.6 GB / 100-view layout
+    assert dm.predictor_2d.max_views_per_launch(40000, 512, 512) <= (2 ** 32 - 1) // (512 * 512)
     monkeypatch.setattr(PaulsenModel, "max_views_per_launch", lambda self, v, h, w: min(v, 4))
     dm.predictor_2d._nets.clear()                                          # forget the 12-view plan: slices of 4 now
     sliced = dm.predictor_2d.predict_landmarks_device(u8)

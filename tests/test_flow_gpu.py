@@ -23,7 +23,7 @@ def _build(env, *args):
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
-        return ops.Hourglass(*args)
+        return ops.Hourglass(*args, keep_probes=True)
     finally:
         for k, v in old.items():
             if v is None:
@@ -65,3 +65,26 @@ def test_flow_equals_per_layer_plan(lib, n_landmarks, mode, size, views, lo, hi,
     pk_g2, _ = flow.forward(img, graph=True)
     torch.cuda.synchronize()
     assert torch.equal(pk_g2.view(torch.int32), pk_ref.view(torch.int32))
+
+
+def test_workspace_packing_is_bit_identical_and_small(lib):
+    """Buffer reuse (hourglass.cu, ws_alloc / assign_offsets) changes addresses only: peaks and heat maps of the packed
+    plan equal those of the plan where every buffer has its own memory; the headline plan fits 6 GB."""
+    from mvlm_b200 import ops
+
+    assert lib.mvlm_hourglass_workspace_bytes(73, 4, 100, 256, 256) <= 6e9
+    sd = seeded_state_dict(73, "RGB+depth", seed=1234)
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (6, 128, 128, 4), generator=g, dtype=torch.uint8).cuda()
+    args = (sd, 73, 4, 6, 128, 128)
+    flat = _build({"MVLM_HG_NO_REUSE": "1"}, *args)
+    packed = ops.Hourglass(*args)
+    assert packed.workspace.numel() < 0.35 * flat.workspace.numel()
+    pk0, hm0 = flat.forward(img, want_heatmaps=True)
+    for _ in range(2):
+        pk1, hm1 = packed.forward(img, want_heatmaps=True)
+        torch.cuda.synchronize()
+        assert torch.equal(pk0.view(torch.int32), pk1.view(torch.int32))
+        assert torch.equal(hm0.view(torch.int32), hm1.view(torch.int32))
+    with pytest.raises(Exception):
+        packed.probe("r3")

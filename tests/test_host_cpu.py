@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.mvlm_last_error() is not None
     # size queries are pure host functions (no compute)
     assert lib.mvlm_raster_workspace_bytes(100, 256, 256) == 100 * 256 * 256 * 8
-    assert lib.mvlm_hourglass_workspace_bytes(73, 4, 100, 256, 256) > 10 * 2 ** 30
+    assert 2 * 2 ** 30 < lib.mvlm_hourglass_workspace_bytes(73, 4, 100, 256, 256) <= 6e9  # packed (20.3 GB unpacked)
     assert lib.mvlm_consensus_workspace_bytes(84, 200, 16384) > 0
     assert lib.mvlm_snap_workspace_bytes(73, 100000) > 0
     assert lib.mvlm_hourglass_workspace_bytes(73, 4, 1, 100, 100) == 0  # not a multiple of 64 -> error

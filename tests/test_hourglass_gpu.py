@@ -41,7 +41,7 @@ def test_hourglass_matches_oracle(lib, n_landmarks, mode, size, views):
     img_u8 = torch.randint(0, 256, (views, size, size, 4), generator=g, dtype=torch.uint8)
     img_u8[..., cin:] = 0
     img = (img_u8[..., :cin].float() / 255.0)
-    net = ops.Hourglass(sd, n_landmarks, cin, views, size, size)
+    net = ops.Hourglass(sd, n_landmarks, cin, views, size, size, keep_probes=True)
     peaks, hm = net.forward(img_u8.cuda(), want_heatmaps=True, want_peaks=True)
     torch.cuda.synchronize()
     hm = hm.cpu()

@@ -29,7 +29,7 @@ print("  cudnn32 vs fp64: max %.3e mean %.3e" % ((ref.double() - ref64).abs().ma
 sd = seeded_state_dict(73, "RGB+depth", 1234)
 gen = torch.Generator().manual_seed(5)
 img_u8 = torch.randint(0, 256, (2, 64, 64, 4), generator=gen, dtype=torch.uint8)
-net = ops.Hourglass(sd, 73, 4, 2, 64, 64)
+net = ops.Hourglass(sd, 73, 4, 2, 64, 64, keep_probes=True)
 peaks, hm = net.forward(img_u8.cuda(), want_heatmaps=True)
 xin = (img_u8.float() / 255).permute(0, 3, 1, 2).contiguous()
 r32, i32 = HourglassOracle(sd).forward(xin, return_intermediates=True)
