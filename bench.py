@@ -74,6 +74,10 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="ncu mode: exact --warmup, no e2e / cpu legs")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child run that measures the CNN's DRAM bytes")
+    ap.add_argument("--no-view-split", action="store_true", help="skip the config-4 leg (one scan's views split over the ranks)")
+    ap.add_argument("--vs-views", type=int, default=200)
+    ap.add_argument("--vs-size", type=int, default=512)
+    ap.add_argument("--vs-grid", type=int, default=1001, help="1001 -> 1 002 001 vertices / 2 000 000 triangles")
     return ap.parse_args()
 
 
@@ -284,6 +288,111 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ config 4
+def run_view_split(args, world, rank, local, dev):
+    """BASELINE.json config 4 under the driver: ONE scan (2M triangles, 200 views of 512^2) whose views are split over
+    the ranks -- each rank rasterises and runs the CNN on its block, the fused arg-max writes the keys into the rank's
+    slot of the gather buffer, one in-place NCCL all-gather, peaks / rays / consensus / snap on every rank
+    (mvlm_b200/sharding.py::predict_mesh_view_split).  Strong scaling: the work per scan is fixed.  Reports ms/scan
+    (CUDA events, max over ranks), the collective, the scan upload, the same scan on rank 0 alone in this run
+    (N = 1 point of the curve) and whether a 32-view scan gives bit-identical landmarks both ways."""
+    import torch
+    import torch.distributed as dist
+
+    from mvlm_b200 import ops, sharding, synth
+    from mvlm_b200.io_obj import Mesh
+    from mvlm_b200.pipeline import create_pipeline
+    from mvlm_b200.weights import seeded_state_dict
+
+    v_all, size = args.vs_views, args.vs_size
+    verts, uvs, tris = synth.face_mesh(grid=args.vs_grid, seed=1234)
+    mesh = Mesh(verts=verts, tris=tris, uvs=uvs, texture=synth.face_texture(1024, seed=1234))
+    tr = synth.random_view_transforms(v_all, seed=77)
+    sd = seeded_state_dict(N_LANDMARKS, IMAGE_MODE, 1234)
+    dm = create_pipeline("dtu3d", n_views=v_all, weights=sd, seed=5, n_hypotheses=args.hyp, verbose=False,
+                         image_size=(size, size), transforms=tr, device=f"cuda:{local}")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps, warm):
+        for _ in range(warm):
+            out = fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    res = {"workload": f"one scan, {len(verts)} verts / {len(tris)} tris, {v_all} views {size}^2, views split over {world} rank(s)",
+           "scaling": "strong", "n_ranks": world}
+    if world > 1:
+        ms_split, lm_split = timed(lambda: sharding.predict_mesh_view_split(dm, mesh, tr), 5, 3)
+        res["ms_per_scan"] = ms_split
+        # the collective alone: in-place all-gather of the keys + the kernel that turns the gathered keys into peaks
+        kb = dm.__dict__["_vs_keys"]
+        ms_gather, _ = timed(lambda: (sharding.allgather_keys(kb), ops.peaks_from_gathered_keys(kb, v_all, size)), 20, 5)
+        res["allgather_us"] = 1e3 * ms_gather
+        res["allgather_bytes_per_rank"] = int(kb[0].numel() * 8)
+        ms_up, _ = timed(lambda: sharding.upload_mesh_sharded(dm.renderer_3d, mesh), 5, 3)
+        res["upload_ms"] = ms_up
+        res["upload_bytes"] = int(sharding._mesh_bytes(mesh))
+        # this rank's share of raster + CNN (what the split cannot remove)
+        start, count = sharding.split_views(v_all, rank, world)
+        dmesh = dm.renderer_3d.upload(mesh)
+
+        def share():
+            loc = dm.renderer_3d.render_device(dmesh, tr[start:start + count])
+            dm.predictor_2d.predict_keys_device(loc["u8"], kb[rank, :count])
+
+        ms_share, _ = timed(share, 5, 2)
+        res["rank_raster_cnn_ms"] = ms_share
+        res["overhead_ms"] = ms_split - ms_share
+    # the same scan on one GPU (rank 0 alone; the other ranks wait): the N = 1 point of the strong-scaling curve
+    sync_all()
+    single_ms = None
+    lm_single = None
+    if rank == 0:
+        for _ in range(2):
+            lm_single = dm.predict_mesh(mesh)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            lm_single = dm.predict_mesh(mesh)
+        e1.record()
+        torch.cuda.synchronize()
+        single_ms = e0.elapsed_time(e1) / 3
+    sync_all()
+    res["single_rank_ms"] = single_ms
+    if world == 1:
+        res["ms_per_scan"] = single_ms
+    elif rank == 0:
+        res["strong_scaling_efficiency"] = single_ms / (world * res["ms_per_scan"])
+    # 32 views both ways: bit-identical landmarks
+    if world > 1:
+        tr32 = tr[:32]
+        dm32 = create_pipeline("dtu3d", n_views=32, weights=sd, seed=5, n_hypotheses=args.hyp, verbose=False,
+                               image_size=(size, size), transforms=tr32, device=f"cuda:{local}")
+        a = sharding.predict_mesh_view_split(dm32, mesh, tr32)
+        b = dm32.predict_mesh(mesh)
+        flag = torch.tensor([int(np.array_equal(a, b))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        res["equals_single_rank_32_views"] = bool(flag.item())
+    del dm
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -448,6 +557,12 @@ def run_ours(args):
             files_nvjpeg_value = world * n_files / float(tf.item())
             dm.texture_decoder = "pil"
 
+    view_split = None
+    if not args.profile and not args.no_view_split:
+        try:
+            view_split = run_view_split(args, world, rank, local, dev)
+        except Exception as ex:  # noqa: BLE001  (the headline numbers above stand on their own)
+            view_split = {"error": f"{type(ex).__name__}: {ex}"}
     if rank == 0:
         pk, pk_kind = peaks_file()
         flops_scan = net.flops_per_view * args.views
@@ -472,6 +587,7 @@ def run_ours(args):
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                          "peak_source": f"{pk_kind} bf16_tflops_sustained", "flops_per_scan": flops_scan},
             "clocks": clocks,
+            "view_split": view_split,
         }
         if world == 1 and not args.profile and not args.no_traffic:
             # dram__bytes_read.sum + dram__bytes_write.sum over every CNN launch of one scan, measured now by an ncu

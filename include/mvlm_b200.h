@@ -147,6 +147,17 @@ int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const flo
  * (img, out) pointer tuple on first use and replayed afterwards (buffers must stay valid and unchanged). */
 int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                                  float* out_heatmaps, float* out_peaks, void* stream);
+/* View-split hand-off (SURVEY.md 8b "mvlm_allgather_peaks", 8e): when one scan's views are split over ranks, each rank
+ * runs the network on its block of views with the fused arg-max of the last convolution writing its keys
+ * (u64 = ordered value << 32 | ~index, n_views x n_landmarks) STRAIGHT into this rank's slot of the all-gather buffer
+ * keys[world][slot_views][n_landmarks]; the host layer issues ONE in-place NCCL all-gather on that buffer
+ * (torch.distributed's communicator: mvlm_b200/sharding.py::allgather_keys) and ONE kernel turns the gathered keys of
+ * ALL views into peaks (L, V, 3), mapping view v to (rank, row) by the contiguous split of sharding.split_views.
+ * No padding copy, no per-rank scatter. */
+int mvlm_hourglass_forward_keys(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, uint64_t* out_keys,
+                                void* stream);
+int mvlm_peaks_from_gathered_keys(const uint64_t* keys, int n_views, int n_landmarks, int w, int world, int slot_views,
+                                  float* out_peaks /* (L, V, 3) */, void* stream);
 int mvlm_hourglass_num_launches(const mvlm_hourglass* net);
 /* number of dataflow segments of the plan (csrc/conv_flow.cuh): runs of layers executed by one persistent launch
  * over small view batches so that their intermediate tensors stay in L2; 0 = every layer is its own launch */

@@ -178,6 +178,19 @@ int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, con
   return net->net.forward_graph(img_u8, img_f32, out_heatmaps, out_peaks, static_cast<cudaStream_t>(stream));
 }
 
+int mvlm_hourglass_forward_keys(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, uint64_t* out_keys,
+                                void* stream) {
+  MVLM_REQUIRE(net, "mvlm_hourglass_forward_keys: null handle");
+  return net->net.forward_keys(img_u8, img_f32, reinterpret_cast<unsigned long long*>(out_keys),
+                               static_cast<cudaStream_t>(stream));
+}
+
+int mvlm_peaks_from_gathered_keys(const uint64_t* keys, int n_views, int n_landmarks, int w, int world, int slot_views,
+                                  float* out_peaks, void* stream) {
+  return peaks_from_gathered_keys(reinterpret_cast<const unsigned long long*>(keys), n_views, n_landmarks, w, world,
+                                  slot_views, out_peaks, static_cast<cudaStream_t>(stream));
+}
+
 int mvlm_debug_hourglass_profile(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, float* out_peaks,
                                  int reps, float* ms_out, double* roles_out, int trace_op, long long* trace_out,
                                  void* stream) {

@@ -749,6 +749,9 @@ int HourglassNet::build_segments() {
 
 int HourglassNet::run_op(NetOp& op, const unsigned char* img_u8, const float* img_f32, float* out_heatmaps,
                          float* out_peaks, cudaStream_t stream) {
+  // out_keys_ (forward_keys): the fused arg-max writes the caller's key buffer, e.g. this rank's slot of an
+  // all-gather buffer, instead of the plan's own; no peak kernel runs here then
+  unsigned long long* const keys = out_keys_ ? out_keys_ : keys_;
   switch (op.kind) {
     case NetOp::STEM:
       return image_to_hilo16(img_u8, img_f32, op.c, static_cast<size_t>(V_) * op.h * op.w, op.out_raw, stream);
@@ -756,6 +759,7 @@ int HourglassNet::run_op(NetOp& op, const unsigned char* img_u8, const float* im
       if (op.is_head) {
         ConvParams p = op.conv;
         p.e.out_f32 = out_heatmaps;
+        p.e.argmax_keys = keys;
         return conv_launch(p, stream);
       }
       return conv_launch(op.conv, stream);
@@ -764,13 +768,23 @@ int HourglassNet::run_op(NetOp& op, const unsigned char* img_u8, const float* im
     case NetOp::BNRELU:
       return bn_relu(op.in0, static_cast<size_t>(V_) * op.h * op.w, op.c, op.scale, op.shift, op.out_act, stream);
     case NetOp::MEMSET:
-      MVLM_CHECK_CUDA(cudaMemsetAsync(op.ptr, 0, op.bytes, stream));
+      MVLM_CHECK_CUDA(cudaMemsetAsync(keys, 0, op.bytes, stream));
       return MVLM_OK;
     case NetOp::PEAKS:
-      if (out_peaks) return peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
+      if (out_peaks && !out_keys_) return peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
       return MVLM_OK;
   }
   return MVLM_OK;
+}
+
+int HourglassNet::forward_keys(const unsigned char* img_u8, const float* img_f32, unsigned long long* out_keys,
+                               cudaStream_t stream) {
+  MVLM_REQUIRE(out_keys, "hourglass: null key buffer");
+  out_keys_ = out_keys;
+  // graph key: the key buffer takes the place of the peak buffer (a distinct pointer tuple)
+  const int rc = forward_graph(img_u8, img_f32, nullptr, reinterpret_cast<float*>(out_keys), stream);
+  out_keys_ = nullptr;
+  return rc;
 }
 
 int HourglassNet::forward(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,

@@ -52,6 +52,11 @@ class HourglassNet {
   int forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
                     cudaStream_t stream);
 
+  // The network up to the fused arg-max: writes the (n_views x n_landmarks) u64 keys (ordered value << 32 | ~index)
+  // into `out_keys` and runs no peak kernel (view-split path: out_keys is this rank's slot of the all-gather buffer).
+  // Replays a CUDA graph like forward_graph.
+  int forward_keys(const unsigned char* img_u8, const float* img_f32, unsigned long long* out_keys, cudaStream_t stream);
+
   // Debug aid: runs the plan `reps` times with a CUDA event pair around every op; ms_out[n_ops()] = mean ms per op.
   // roles_out (optional, n_ops() x 8 doubles): mean per-CTA role stall cycles of every conv op (conv_umma.cu).
   // trace_out (optional, kConvTraceTiles x 8 int64): per-tile timeline of CTA 0 of conv op `trace_op`.
@@ -139,6 +144,7 @@ class HourglassNet {
   std::map<std::string, std::pair<float*, float*>> bn_cache_;
   std::vector<NetOp> ops_;
   unsigned long long* keys_ = nullptr;
+  unsigned long long* out_keys_ = nullptr;  // set for the duration of forward_keys
   double flops_ = 0.0;
   struct GraphKey { const void* a; const void* b; const void* c; const void* d; };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs_;

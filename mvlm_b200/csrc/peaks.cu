@@ -135,7 +135,39 @@ __global__ void peaks_from_keys_kernel(const unsigned long long* __restrict__ ke
   o[2] = val;
 }
 
+// keys gathered from `world` ranks, slot r = (slot_views x L) keys of rank r's contiguous view block (the first
+// V % world ranks hold one view more, sharding.split_views); unused slot rows are never read
+__global__ void peaks_from_gathered_keys_kernel(const unsigned long long* __restrict__ keys, int V, int L, int W, int world,
+                                                int slot_views, float* __restrict__ peaks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // v * L + l
+  if (i >= V * L) return;
+  const int v = i / L, l = i % L;
+  const int base = V / world, rem = V % world;
+  // rank r starts at r * base + min(r, rem)
+  int r = (v < rem * (base + 1)) ? v / (base + 1) : rem + (v - rem * (base + 1)) / max(base, 1);
+  const int start = r * base + min(r, rem);
+  const unsigned long long k = keys[(static_cast<size_t>(r) * slot_views + (v - start)) * L + l];
+  const unsigned int idx = 0xFFFFFFFFu - static_cast<unsigned int>(k & 0xFFFFFFFFu);
+  const float val = unorder_f32(static_cast<unsigned int>(k >> 32));
+  const int row = idx / W, col = idx % W;
+  float* o = peaks + (static_cast<size_t>(l) * V + v) * 3;
+  o[0] = static_cast<float>(row - 1);
+  o[1] = static_cast<float>(col) - 0.5f;
+  o[2] = val;
+}
+
 }  // namespace
+
+int peaks_from_gathered_keys(const unsigned long long* keys, int v, int l, int w, int world, int slot_views, float* peaks,
+                             cudaStream_t s) {
+  MVLM_REQUIRE(keys && peaks, "peaks_from_gathered_keys: null pointer");
+  MVLM_REQUIRE(v > 0 && l > 0 && w > 0 && world > 0 && world <= v && slot_views >= ceil_div(v, world),
+               "peaks_from_gathered_keys: bad layout (%d views, %d ranks, %d views per slot)", v, world, slot_views);
+  peaks_from_gathered_keys_kernel<<<ceil_div(v * l, 256), 256, 0, s>>>(keys, v, l, w, world, slot_views, peaks);
+  count_launch();
+  MVLM_CHECK_CUDA(cudaGetLastError());
+  return MVLM_OK;
+}
 
 int peaks_from_heatmaps(const float* hm, int v, int l, int h, int w, int method, float* peaks, cudaStream_t s) {
   MVLM_REQUIRE(hm && peaks, "peaks: null pointer");

@@ -29,6 +29,9 @@ int raster_launch(const RasterArgs& a, cudaStream_t stream);
 int peaks_from_heatmaps(const float* hm, int v, int l, int h, int w, int method, float* peaks, cudaStream_t s);
 // fused path: keys[v*l] written by the conv11 epilogue -> peaks (simple method only)
 int peaks_from_keys(const unsigned long long* keys, int v, int l, int h, int w, float* peaks, cudaStream_t s);
+// view-split path: keys of all ranks gathered into `world` slots of slot_views x l keys each -> peaks (l, v, 3)
+int peaks_from_gathered_keys(const unsigned long long* keys, int v, int l, int w, int world, int slot_views, float* peaks,
+                             cudaStream_t s);
 
 // ---- rays.cu --------------------------------------------------------------
 int rays_from_peaks(const float* peaks, const double* rot, int l, int v, int image_size, double* starts,

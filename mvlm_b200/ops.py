@@ -103,6 +103,11 @@ def raster_multiview(verts, uvs, tris, tex, rot, h: int, w: int, channel_mode: s
     return {"u8": out_u8, "f32": f32, "tri": tri, "z": z}
 
 
+def _on_device(device):
+    device = torch.device(device)
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
 @contextlib.contextmanager
 def _plan_env(**kv):
     """Plan-build switches of the library are environment variables read by mvlm_hourglass_workspace_bytes / _create."""
@@ -130,7 +135,9 @@ class Hourglass:
         self.n_landmarks, self.cin, self.n_views, self.h, self.w = n_landmarks, cin, n_views, h, w
         self.device = torch.device(device)
         self.keep_probes = bool(keep_probes)
-        with _plan_env(MVLM_HG_KEEP_PROBES="1" if keep_probes else "0"):
+        # the plan's cudaMalloc / weight repacking launches and every later forward run on self.device, whatever the
+        # caller's current device is
+        with _on_device(self.device), _plan_env(MVLM_HG_KEEP_PROBES="1" if keep_probes else "0"):
             self._create(lib, state_dict, n_landmarks, cin, n_views, h, w)
 
     def _create(self, lib, state_dict, n_landmarks, cin, n_views, h, w):
@@ -153,6 +160,10 @@ class Hourglass:
         self.num_segments = lib.mvlm_hourglass_num_segments(handle)
 
     def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False):
+        with _on_device(self.device):
+            return self._forward(img, want_heatmaps, want_peaks, graph)
+
+    def _forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False):
         """img: (V,H,W,4) uint8 (rasteriser output) or (V,H,W,cin) float32; returns (peaks (L,V,3) f32, heatmaps|None).
         graph=True replays a CUDA graph of the launch sequence; the returned peaks tensor is then a persistent
         buffer owned by this object (overwritten by the next call)."""
@@ -177,6 +188,18 @@ class Hourglass:
               "mvlm_hourglass_forward")
         return peaks, hm
 
+    def forward_keys(self, img, out_keys: torch.Tensor) -> None:
+        """The network with its fused arg-max writing the u64 keys of this block of views into `out_keys`
+        ((n_views, n_landmarks) int64, e.g. this rank's slot of an all-gather buffer); no peak kernel, CUDA-graph replay."""
+        lib = _lib.load()
+        assert img.shape[0] == self.n_views and img.shape[1] == self.h and img.shape[2] == self.w
+        assert out_keys.dtype == torch.int64 and out_keys.is_contiguous() and out_keys.numel() == self.n_views * self.n_landmarks
+        u8 = img if img.dtype == torch.uint8 else None
+        f32 = img.contiguous() if img.dtype == torch.float32 else None
+        with _on_device(self.device):
+            check(lib.mvlm_hourglass_forward_keys(self._h, ptr(u8), ptr(f32), ptr(out_keys), cur_stream()),
+                  "mvlm_hourglass_forward_keys")
+
     def probe(self, name: str) -> torch.Tensor:
         """Copy of an intermediate NHWC bf16 tensor (layer-wise parity tests)."""
         if not self.keep_probes:
@@ -195,6 +218,17 @@ class Hourglass:
                 self._h = None
         except Exception:  # noqa: BLE001
             pass
+
+
+def peaks_from_gathered_keys(keys: torch.Tensor, n_views: int, w: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """keys (world, slot_views, L) int64 gathered from all ranks -> peaks (L, n_views, 3) float32."""
+    lib = _lib.load()
+    world, slot_views, l = keys.shape
+    if out is None:
+        out = torch.empty((l, n_views, 3), dtype=torch.float32, device=keys.device)
+    check(lib.mvlm_peaks_from_gathered_keys(ptr(keys), n_views, l, w, world, slot_views, ptr(out), cur_stream()),
+          "mvlm_peaks_from_gathered_keys")
+    return out
 
 
 def heatmap_peaks(heatmaps: torch.Tensor, selection_method: str = "simple") -> torch.Tensor:

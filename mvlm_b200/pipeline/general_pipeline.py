@@ -21,6 +21,36 @@ from ..prediction.paulsenpredictor import PaulsenModel
 from ..utils import Estimator3D, ObjRenderer3D
 
 
+class _DeviceLock:
+    """Re-entrant lock that also makes the pipeline's device the current CUDA device while it is held: every kernel
+    of the library is launched on the current stream of the CURRENT device, so create_pipeline(device="cuda:1") must
+    not depend on what the calling thread's current device happens to be."""
+
+    def __init__(self, device: torch.device):
+        import threading
+
+        self._lock = threading.RLock()
+        self._device = device
+        self._guards = []
+
+    def __enter__(self):
+        self._lock.acquire()
+        guard = torch.cuda.device(self._device) if self._device.type == "cuda" else None
+        if guard is not None:
+            guard.__enter__()
+        self._guards.append(guard)
+        return self
+
+    def __exit__(self, *exc):
+        guard = self._guards.pop()
+        try:
+            if guard is not None:
+                guard.__exit__(*exc)
+        finally:
+            self._lock.release()
+        return False
+
+
 class TimeMixin:
     def __init__(self):
         self.start_time = time.time()
@@ -67,9 +97,7 @@ class Pipeline(abc.ABC, TimeMixin):
         # One pipeline object = one set of device buffers (renderer images, CNN workspace, CUDA graphs): calls from
         # several threads (the reference's FastAPI server shares one pipeline across its thread pool without a lock,
         # 3DMD_server.py:24-31) are serialised here.
-        import threading
-
-        self._lock = threading.RLock()
+        self._lock = _DeviceLock(self.device)
         self.predictor_2d = None  # assigned by the subclasses
         self.last_error = None    # "Landmarks [Error]" of the last scan (general_pipeline.py:109)
 

@@ -50,14 +50,27 @@ class PaulsenModel(Predictor2D):
             return ckpt["state_dict"] if "state_dict" in ckpt else ckpt
         if weights is None:
             for d in (Path(__file__).parent / "models", Path(os.environ.get("MVLM_B200_WEIGHTS_DIR", "/nonexistent"))):
-                for cand in sorted(d.glob(f"{name.replace('-', '_')}*.pth")) + sorted(d.glob(f"{name}*.pth")):
-                    ckpt = torch.load(str(cand), map_location="cpu")
-                    return ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+                for cand in sorted(d.glob("*.pth")):
+                    if self._checkpoint_matches(cand.name):
+                        ckpt = torch.load(str(cand), map_location="cpu")
+                        return ckpt["state_dict"] if "state_dict" in ckpt else ckpt
         if weights == "random" or os.environ.get("MVLM_B200_RANDOM_INIT"):
             return seeded_state_dict(self.get_lm_count(), self.image_mode, seed)
         raise RuntimeError(
             f"no weights for {name}: pass weights=<state_dict|path>, put a checkpoint in prediction/models/ or "
             "$MVLM_B200_WEIGHTS_DIR, or set MVLM_B200_RANDOM_INIT=1 for a seeded random init (no network access)")
+
+    def _checkpoint_matches(self, file_name: str) -> bool:
+        """The reference's checkpoint files (paulsenpredictor.py:15-39) are named <model_type>_<mode>_<date...>.pth with
+        the mode in either case ("..._DTU3D_Depth_19092019..."); "RGB" must not match "RGB+depth_..." nor "geometry"
+        "geometry+depth_...": the mode has to be followed by a separator.  (A wrong file would still be rejected by the
+        tensor-size check of mvlm_hourglass_create.)"""
+        low = file_name.lower()
+        for sep in ("_", "-"):
+            prefix = f"{self.model_type}{sep}{self.image_mode}".lower()
+            if low.startswith(prefix) and len(low) > len(prefix) and low[len(prefix)] in "_-.":
+                return True
+        return False
 
     # ------------------------------------------------------------------ network cache
     def network(self, n_views: int, h: int, w: int) -> ops.Hourglass:
@@ -110,8 +123,8 @@ class PaulsenModel(Predictor2D):
         if img.dtype == torch.float32 and img.shape[3] > cin:
             img = img[..., :cin].contiguous()   # e.g. an RGB model fed the 4-channel stack
         v, h, w = img.shape[0], img.shape[1], img.shape[2]
-        # View batches: the conv kernel indexes its NHWC tensors with 32-bit element offsets (V*H*W*256 < 2^31) and the
-        # plan's workspace grows with V (3.2 KB per pixel); larger stacks run as equal slices of the view axis.
+        # View batches: the conv kernel indexes pixels with 32 bits (V*H*W < 2^32) and the plan's workspace grows with V
+        # (about 0.7 KB per pixel); larger stacks run as equal slices of the view axis.
         chunk = v if (v, h, w) in self._nets else self.max_views_per_launch(v, h, w)  # a cached plan fits by construction
         if chunk < v:
             return torch.cat([self.predict_landmarks_device(img[i:i + chunk]).clone() for i in range(0, v, chunk)], dim=1)
@@ -125,6 +138,19 @@ class PaulsenModel(Predictor2D):
             return ops.heatmap_peaks(hm, "moment")
         # the reference leaves the coordinates at zero for unknown methods (:118,:129)
         return torch.zeros((self.get_lm_count(), v, 3), dtype=torch.float32, device=self.device)
+
+    def can_write_keys(self, v: int, h: int, w: int) -> bool:
+        """True when `predict_keys_device` applies: the default arg-max selection and one plan for the whole block."""
+        return self.selection_method == "simple" and ((v, h, w) in self._nets or self.max_views_per_launch(v, h, w) >= v)
+
+    def predict_keys_device(self, img: torch.Tensor, out_keys: torch.Tensor) -> None:
+        """View-split hand-off: the network's fused arg-max writes the (V, L) u64 keys of this block of views straight
+        into `out_keys` (this rank's slot of the all-gather buffer, sharding.predict_mesh_view_split)."""
+        cin = IMAGE_CHANNELS[self.image_mode]
+        if img.dtype == torch.float32 and img.shape[3] > cin:
+            img = img[..., :cin].contiguous()
+        v, h, w = img.shape[0], img.shape[1], img.shape[2]
+        self.network(v, h, w).forward_keys(img, out_keys)
 
     def find_maxima_in_batch_of_heatmaps(self, heatmaps, heatmap_maxima=None):
         """(V,L,H,W) float32 (numpy or torch) -> (L,V,3); paulsenpredictor.py:160-165."""

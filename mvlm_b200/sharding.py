@@ -26,27 +26,49 @@ def split_views(n_views: int, rank: int, world: int) -> tuple[int, int]:
     return start, count
 
 
+def _view_rows(n_views: int, world: int, device) -> torch.Tensor:
+    """Row of global view v in a gather buffer of `world` slots of ceil(n_views / world) views (rank-major)."""
+    slot = split_views(n_views, 0, world)[1]
+    rows = []
+    for r in range(world):
+        s, c = split_views(n_views, r, world)
+        rows.extend(r * slot + i for i in range(c))
+    return torch.tensor(rows, dtype=torch.long, device=device)
+
+
+_ROWS_CACHE: dict = {}
+
+
 def allgather_peaks(local_peaks: torch.Tensor, n_views: int, group=None) -> torch.Tensor:
     """local_peaks (L, V_local, 3) float32 of this rank's view block -> (L, V, 3) on every rank.
 
-    One collective of at most L*ceil(V/world)*12 bytes per rank (25 KB at L=84, V=200, world=8):
-    latency-bound; NCCL over NVLink on GPUs, gloo on CPU (tests).  Blocks are padded to the largest
-    block so that a single fixed-size all_gather is used."""
+    Fallback of the view-split path (non-default peak selection, sliced plans; the default path gathers the arg-max
+    KEYS in place, see allgather_keys).  One in-place collective of L*ceil(V/world)*12 bytes per rank (25 KB at L=84,
+    V=200, world=8): latency-bound; NCCL over NVLink on GPUs, gloo on CPU (tests).  The block is written view-major into
+    this rank's slot of the receive buffer, the gather runs in place, and ONE indexed read (cached row table) puts the
+    views in order: no zero-filled send buffer, no per-rank copy loop."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     l = local_peaks.shape[0]
-    max_count = split_views(n_views, 0, world)[1]
+    slot = split_views(n_views, 0, world)[1]
     start, count = split_views(n_views, rank, world)
     assert local_peaks.shape[1] == count, (local_peaks.shape, count)
-    send = torch.zeros((l, max_count, 3), dtype=local_peaks.dtype, device=local_peaks.device)
-    send[:, :count] = local_peaks
-    recv = torch.empty((world, l, max_count, 3), dtype=local_peaks.dtype, device=local_peaks.device)
-    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
-    out = torch.empty((l, n_views, 3), dtype=local_peaks.dtype, device=local_peaks.device)
-    for r in range(world):
-        s, c = split_views(n_views, r, world)
-        out[:, s:s + c] = recv[r, :, :c]
-    return out
+    recv = torch.empty((world, slot, l, 3), dtype=local_peaks.dtype, device=local_peaks.device)
+    if count < slot:
+        recv[rank, count:].zero_()  # the unused row of a short block travels too: keep it defined
+    recv[rank, :count].copy_(local_peaks.permute(1, 0, 2))
+    dist.all_gather_into_tensor(recv.view(-1), recv[rank].reshape(-1), group=group)
+    key = (n_views, world, str(local_peaks.device))
+    if key not in _ROWS_CACHE:
+        _ROWS_CACHE[key] = _view_rows(n_views, world, local_peaks.device)
+    return recv.view(world * slot, l, 3).index_select(0, _ROWS_CACHE[key]).permute(1, 0, 2).contiguous()
+
+
+def allgather_keys(keys_all: torch.Tensor, group=None) -> None:
+    """In-place all-gather of the arg-max keys: keys_all (world, slot_views, L) int64, slot [rank] already written by
+    this rank's network (Hourglass.forward_keys).  One NCCL collective, no staging copy."""
+    rank = dist.get_rank(group)
+    dist.all_gather_into_tensor(keys_all.view(-1), keys_all[rank].reshape(-1), group=group)
 
 
 # Scans at least this large take the sharded upload in predict_mesh_view_split.  Measured (profiles/r1_view_split_c4.txt):
@@ -92,6 +114,8 @@ def upload_mesh_sharded(renderer, mesh, group=None):
     if isinstance(tex, torch.Tensor):  # decoded on the device already
         if mesh.texture_ready is not None:
             torch.cuda.current_stream().wait_event(mesh.texture_ready)
+        if tex.is_cuda:
+            tex.record_stream(torch.cuda.current_stream())  # decoded on a loader stream: keep its memory until we are done
         tex_d = tex
     else:
         tex_d = None if tex is None else allgather_bytes(tex, device, stage, "tex", group)
@@ -121,11 +145,28 @@ def predict_mesh_view_split(pipeline, mesh, transforms: np.ndarray, group=None) 
     transforms = np.asarray(transforms)
     n_views = transforms.shape[0]
     start, count = split_views(n_views, rank, world)
+    slot = split_views(n_views, 0, world)[1]
+    size = r.image_size
+    n_lm = p.get_lm_count()
     # every rank needs the whole mesh: large scans are uploaded 1/world per rank and all-gathered over NVLink
     dmesh = upload_mesh_sharded(r, mesh, group) if world > 1 and _mesh_bytes(mesh) >= SHARDED_UPLOAD_MIN_BYTES else r.upload(mesh)
-    local = r.render_device(dmesh, transforms[start:start + count])
-    peaks_local = p.predict_landmarks_device(local["u8"])
-    peaks = allgather_peaks(peaks_local, n_views, group)
+    dev = dmesh.verts.device
+    # more ranks than views: the ranks without a view skip raster and CNN and still join the collectives
+    local = r.render_device(dmesh, transforms[start:start + count]) if count > 0 else None
+    if p.can_write_keys(max(count, 1), size[0], size[1]):
+        # default path: the last convolution's fused arg-max writes this rank's keys straight into its slot of the
+        # (persistent) gather buffer, ONE in-place collective, ONE kernel from the gathered keys to the peaks of all views
+        kb = pipeline.__dict__.get("_vs_keys")
+        if kb is None or kb.shape != (world, slot, n_lm) or kb.device != dev:
+            kb = pipeline.__dict__["_vs_keys"] = torch.zeros((world, slot, n_lm), dtype=torch.int64, device=dev)
+        if count > 0:
+            p.predict_keys_device(local["u8"], kb[rank, :count])
+        allgather_keys(kb, group)
+        peaks = ops.peaks_from_gathered_keys(kb, n_views, size[1])
+    else:
+        peaks_local = p.predict_landmarks_device(local["u8"]) if count > 0 else \
+            torch.empty((n_lm, 0, 3), dtype=torch.float32, device=dev)
+        peaks = allgather_peaks(peaks_local, n_views, group)
     if e.seed is None:
         raise ValueError("view-split prediction needs a seeded hypothesis table (Estimator3D.seed)")
     # rotation matrices of ALL views and the hypothesis table are cached on the device across scans

@@ -73,6 +73,31 @@ def test_c4_view_split_equals_single_rank(lib):
     assert np.array_equal(single, split)
 
 
+def test_view_split_key_handoff_equals_plain_peaks(lib):
+    """The view-split hand-off on one GPU: three ranks' blocks of views (3 + 2 + 2 of 7) written by forward_keys into the
+    slots of the gather buffer, one kernel from the gathered keys -> peaks of all views, bit-identical to the peaks of one
+    plan over all 7 views (a view's CNN result does not depend on which other views share its launch)."""
+    from mvlm_b200 import ops
+    from mvlm_b200.sharding import split_views
+
+    sd = seeded_state_dict(73, "RGB+depth", seed=7)
+    g = torch.Generator().manual_seed(2)
+    v, size, world = 7, 64, 3
+    img = torch.randint(0, 256, (v, size, size, 4), generator=g, dtype=torch.uint8).cuda()
+    whole, _ = ops.Hourglass(sd, 73, 4, v, size, size).forward(img)
+    slot = split_views(v, 0, world)[1]
+    kb = torch.full((world, slot, 73), -1, dtype=torch.int64, device="cuda")  # garbage in the rows no rank owns
+    nets = {}
+    for r in range(world):
+        s0, c = split_views(v, r, world)
+        net = nets.setdefault(c, ops.Hourglass(sd, 73, 4, c, size, size))
+        for _ in range(2):  # second call replays the CUDA graph captured for this key buffer
+            net.forward_keys(img[s0:s0 + c].contiguous(), kb[r, :c])
+    peaks = ops.peaks_from_gathered_keys(kb, v, size)
+    torch.cuda.synchronize()
+    assert torch.equal(peaks.view(torch.int32), whole.view(torch.int32))
+
+
 def test_c5_consensus_microbench_parity(lib):
     from mvlm_b200 import ops
 

@@ -170,3 +170,24 @@ def test_estimator_reference_draws_replay_global_rng():
     e.mode = "bogus"
     with pytest.raises(ValueError, match="Unknown mode for line matching"):
         e.reference_draws(peaks)
+
+
+def test_checkpoint_name_matching():
+    """Weight auto-discovery picks the reference's file of exactly this model / mode (paulsenpredictor.py:15-39)."""
+    from mvlm_b200.prediction.paulsenpredictor import PaulsenModel
+
+    names = ["MVLMModel_DTU3D_RGB_07092019_only_state_dict-c0255a70.pth", "MVLMModel_DTU3D_Depth_19092019_only_state_dict-95b89b63.pth",
+             "MVLMModel_DTU3D_geometry_only_state_dict-41851074.pth", "MVLMModel_DTU3D_geometry+depth_20102019_15epoch_only_state_dict-73b20e31.pth",
+             "MVLMModel_DTU3D_RGB+depth_20092019_only_state_dict-e3c12463a9.pth", "MVLMModel_BU_3DFE_RGB+depth_05102019_5epoch-90e29350.pth"]
+
+    class M(PaulsenModel):
+        def __init__(self, model_type, mode):
+            self.model_type, self.image_mode = model_type, mode
+
+        def get_lm_count(self):
+            return 73
+
+    for mode, want in (("RGB", 0), ("depth", 1), ("geometry", 2), ("geometry+depth", 3), ("RGB+depth", 4)):
+        hits = [i for i, n in enumerate(names) if M("MVLMModel_DTU3D", mode)._checkpoint_matches(n)]
+        assert hits == [want], (mode, hits)
+    assert [i for i, n in enumerate(names) if M("MVLMModel_BU_3DFE", "RGB+depth")._checkpoint_matches(n)] == [5]

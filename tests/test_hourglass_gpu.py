@@ -87,3 +87,20 @@ def test_hourglass_flops_match_survey(lib):
     """Algorithmic FLOPs/view of the plan == SURVEY.md 8(d) (reference census minus the dead conv8)."""
     assert abs(lib.mvlm_hourglass_flops_per_view(73, 4, 256, 256) / 1e9 - 146.106) < 1e-3
     assert abs(lib.mvlm_hourglass_flops_per_view(84, 2, 256, 256) / 1e9 - 150.484) < 1e-3
+
+
+def test_state_dict_of_another_model_is_rejected(lib):
+    """load_state_dict raises on any shape mismatch (paulsenpredictor.py:108); so does mvlm_hourglass_create: an
+    84-landmark BU-3DFE checkpoint in the 73-landmark model, a 4-channel conv1 in an RGB model, a missing key."""
+    from mvlm_b200 import _lib, ops
+
+    sd84 = seeded_state_dict(84, "RGB+depth", seed=1)
+    with pytest.raises(_lib.MvlmError, match="size mismatch"):
+        ops.Hourglass(sd84, 73, 4, 1, 64, 64)
+    sd = seeded_state_dict(73, "RGB+depth", seed=1)
+    with pytest.raises(_lib.MvlmError, match="size mismatch for conv1.weight"):
+        ops.Hourglass(sd, 73, 3, 1, 64, 64)
+    broken = {k: v for k, v in sd.items() if k != "hg2.rb7.conv2.weight"}
+    with pytest.raises(_lib.MvlmError, match="missing state_dict key hg2.rb7.conv2.weight"):
+        ops.Hourglass(broken, 73, 4, 1, 64, 64)
+    ops.Hourglass(sd, 73, 4, 1, 64, 64)  # the right one still builds

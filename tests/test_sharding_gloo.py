@@ -37,6 +37,39 @@ def _worker(rank, world, port, n_views, q):
     dist.destroy_process_group()
 
 
+def _rows_worker(rank, world, port, n_views, q):
+    """the in-place key gather + row table: what peaks_from_gathered_keys does on the device, checked on CPU"""
+    from mvlm_b200.sharding import _view_rows, allgather_keys
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_lm = 5
+    slot = split_views(n_views, 0, world)[1]
+    full = torch.arange(n_views * n_lm, dtype=torch.int64).view(n_views, n_lm) + 7
+    kb = torch.zeros((world, slot, n_lm), dtype=torch.int64)
+    s, c = split_views(n_views, rank, world)
+    if c:
+        kb[rank, :c] = full[s:s + c]
+    allgather_keys(kb)
+    got = kb.view(world * slot, n_lm).index_select(0, _view_rows(n_views, world, "cpu"))
+    q.put((rank, bool(torch.equal(got, full))))
+    dist.destroy_process_group()
+
+
+def test_allgather_keys_in_place_world3_and_more_ranks_than_views():
+    ctx = mp.get_context("spawn")
+    for world, n_views in ((3, 8), (3, 2), (2, 7)):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_rows_worker, args=(r, world, port, n_views, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        assert sorted(res) == [(r, True) for r in range(world)], (world, n_views, res)
+
+
 def test_allgather_peaks_world2_uneven():
     ctx = mp.get_context("spawn")
     for n_views in (8, 7):
