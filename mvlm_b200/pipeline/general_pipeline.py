@@ -10,6 +10,7 @@ from __future__ import annotations
 __all__ = ["Pipeline"]
 
 import abc
+import dataclasses
 import time
 from pathlib import Path
 
@@ -18,7 +19,7 @@ import torch
 
 from ..io_obj import Mesh, load_obj
 from ..prediction.paulsenpredictor import PaulsenModel
-from ..utils import Estimator3D, ObjRenderer3D
+from ..utils import Estimator3D, ObjRenderer3D, prealign
 
 
 class _DeviceLock:
@@ -76,7 +77,7 @@ class Pipeline(abc.ABC, TimeMixin):
                  screenshot_folder: Path | None = None, *, image_size: tuple = (256, 256),
                  channel_mode: str = "RGB+depth", n_hypotheses: int = 1, seed: int | None = None,
                  transforms: np.ndarray | None = None, device: str = "cuda", verbose: bool = True,
-                 texture_decoder: str = "pil"):
+                 texture_decoder: str = "pil", pre_align: dict | None = None):
         TimeMixin.__init__(self)
         self.render_image_stack = render_image_stack
         self.render_image_folder = render_image_folder
@@ -87,11 +88,15 @@ class Pipeline(abc.ABC, TimeMixin):
         self.device = torch.device(device)
         # "pil": host decode (shared with the parity oracle); "nvjpeg": decode on the GPU into device memory
         self.texture_decoder = texture_decoder
+        # legacy "pre-align" block (configs/*.json:59-84): {"align_center_of_mass", "rot_x", "rot_y", "rot_z", "scale"};
+        # None / identity = off, see utils/prealign.py
+        self.pre_align = None if prealign.is_identity(pre_align) else dict(pre_align)
 
         self.renderer_3d = ObjRenderer3D(image_size=image_size, offscreen=offscreen, n_views=n_views,
                                          channel_mode=channel_mode, device=device)
         self.renderer_3d.transforms = transforms
         self.renderer_3d.verbose = verbose
+        self.renderer_3d.pre_align = self.pre_align
         self.estimator_3d = Estimator3D(n_hypotheses=n_hypotheses, seed=seed, device=device)
         self.estimator_3d.verbose = verbose
         # One pipeline object = one set of device buffers (renderer images, CNN workspace, CUDA graphs): calls from
@@ -207,6 +212,12 @@ class Pipeline(abc.ABC, TimeMixin):
         if transforms is None:
             transforms = r.generate_3d_transformations()
         transforms = np.asarray(transforms)
+        back = None
+        if self.pre_align is not None:
+            # the whole path runs on the pre-aligned scan; the snapped landmarks are mapped back in _finish
+            a, b = prealign.affine(mesh.verts, self.pre_align)
+            mesh = dataclasses.replace(mesh, verts=prealign.apply(mesh.verts, a, b))
+            back = (a, b)
         dmesh = r.upload(mesh)
         out = r.render_device(dmesh, transforms)
         peaks = p.predict_landmarks_device(out["u8"])
@@ -232,20 +243,22 @@ class Pipeline(abc.ABC, TimeMixin):
         host.copy_(result, non_blocking=True)
         done = torch.cuda.Event()
         done.record()
-        return host, done, (dmesh, result, peaks, starts, ends, lm)
+        return host, done, (dmesh, result, peaks, starts, ends, lm, back)
 
-    def _finish(self, host: torch.Tensor, done) -> np.ndarray:
+    def _finish(self, host: torch.Tensor, done, keep=None) -> np.ndarray:
         done.synchronize()
         result = host.numpy().copy()
         self.last_error = float(result[-1])
         self._print("Landmarks [Error]: ", f"{self.last_error:08.6f}", " mm")
-        return result[:-1].reshape(-1, 3)
+        lm = result[:-1].reshape(-1, 3)
+        back = keep[-1] if keep else None
+        return lm if back is None else prealign.invert(lm, *back)
 
     def predict_mesh(self, mesh: Mesh, transforms: np.ndarray | None = None) -> np.ndarray:
         """Fused device path for an already loaded scan (host arrays in, (L,3) float64 out)."""
         with self._lock:
-            host, done, _keep = self._enqueue_mesh(mesh, transforms)
-            return self._finish(host, done)
+            host, done, keep = self._enqueue_mesh(mesh, transforms)
+            return self._finish(host, done, keep)
 
     def predict_meshes(self, meshes, depth: int = 2) -> list:
         """Batch form of predict_mesh: same results, but up to `depth` scans are in flight -- the copies and launches of
@@ -261,9 +274,9 @@ class Pipeline(abc.ABC, TimeMixin):
                     inflight.append(self._enqueue_mesh(mesh))
                 while len([x for x in inflight if x is not None]) > depth or (inflight and inflight[0] is None):
                     head = inflight.pop(0)
-                    results.append(None if head is None else self._finish(head[0], head[1]))
+                    results.append(None if head is None else self._finish(*head))
             for head in inflight:
-                results.append(None if head is None else self._finish(head[0], head[1]))
+                results.append(None if head is None else self._finish(*head))
             return results
 
     def _predict_seams(self, file_name: Path, full_s: float):
@@ -286,6 +299,8 @@ class Pipeline(abc.ABC, TimeMixin):
         self._print("Landmarks [1] - From View Lines: ", self.toc_p())
         self.tic()
         landmarks = self.estimator_3d.project_landmarks_to_surface(pd, landmarks)
+        if self.pre_align is not None:  # pd is the pre-aligned scan: back to the scan's own space (estimator3d.py:286)
+            landmarks = prealign.invert(landmarks, *self.renderer_3d.last_pre_align)
         self._print("Landmarks [2] - Project to Surface: ", self.toc_p())
         self.last_error = error
         self._print("Landmarks [Error]: ", f"{error:08.6f}", " mm")

@@ -1,4 +1,5 @@
-__all__ = ["ObjRenderer3D", "ObjVTKRenderer3D", "Estimator3D"]
+__all__ = ["ObjRenderer3D", "ObjVTKRenderer3D", "Estimator3D", "prealign"]
 
+from . import prealign
 from .estimator3d import Estimator3D
 from .render3d import ObjRenderer3D, ObjVTKRenderer3D

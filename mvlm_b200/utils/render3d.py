@@ -151,6 +151,8 @@ class ObjRenderer3D:
                  channel_mode: str = "RGB+depth", device: str = "cuda"):
         self.n_views = n_views
         self.image_size = image_size
+        self.pre_align = None       # set by the pipeline (seam path only; the fused path transforms before upload)
+        self.last_pre_align = None
         self.offscreen = offscreen  # kept for signature compatibility; there is no window
         self.min_x_angle, self.max_x_angle = min_x_angle, max_x_angle
         self.min_y_angle, self.max_y_angle = min_y_angle, max_y_angle
@@ -225,6 +227,13 @@ class ObjRenderer3D:
     def render_3d_multi_rgb_geometry_depth(self, transform_stack, file_name):
         tt = time.time()
         mesh = file_name if isinstance(file_name, Mesh) else load_obj(file_name)
+        if self.pre_align is not None:  # legacy "pre-align" block, see utils/prealign.py; the seam path's back-transform
+            import dataclasses           # is Pipeline._predict_seams'
+
+            from . import prealign
+
+            self.last_pre_align = prealign.affine(mesh.verts, self.pre_align)
+            mesh = dataclasses.replace(mesh, verts=prealign.apply(mesh.verts, *self.last_pre_align))
         dmesh = self.upload(mesh)
         if self.verbose:
             print("Render [1] - Setup time: ", f"{time.time() - tt:08.6f} s")

@@ -179,3 +179,32 @@ def landmarks_from_lines(landmark_stack, lines_s, lines_e, raw_draws, mode="quan
             landmarks[lm] = p
             errs[lm] = e
     return landmarks, float(np.sum(errs) / n_landmarks), errs
+
+
+# ---------------------------------------------------------------------------------------
+# pre-align   configs/*.json:59-84, commented apply_pre_transformation  src/mvlm/utils/estimator3d.py:186-224
+#             + transform_landmarks_to_original_space :226-248
+#   t = vtkTransform(); t.Scale(s, s, s); t.RotateY(ry); t.RotateX(rx); t.RotateZ(rz); t.Translate(-cm)
+#   vtkTransform is in PreMultiply mode by default: every call sets  M <- M @ op  (4x4, column vectors), so the
+#   calls compose left to right and a point goes through the LAST call first.
+# ---------------------------------------------------------------------------------------
+def pre_align_matrix(verts: np.ndarray, cfg: dict) -> np.ndarray:
+    """4x4 float64 homogeneous matrix of the legacy pre-alignment, built call by call like vtkTransform."""
+    def rot(axis, deg):
+        a = np.deg2rad(deg)
+        c, s = np.cos(a), np.sin(a)
+        m = np.eye(4)
+        i, j = {"x": (1, 2), "y": (2, 0), "z": (0, 1)}[axis]
+        m[i, i], m[i, j], m[j, i], m[j, j] = c, -s, s, c
+        return m
+
+    m = np.eye(4)                                      # t.Identity()
+    sc = float(cfg.get("scale", 1))
+    m = m @ np.diag([sc, sc, sc, 1.0])                 # t.Scale(s, s, s)
+    m = m @ rot("y", float(cfg.get("rot_y", 0)))       # t.RotateY(ry)
+    m = m @ rot("x", float(cfg.get("rot_x", 0)))       # t.RotateX(rx)
+    m = m @ rot("z", float(cfg.get("rot_z", 0)))       # t.RotateZ(rz)
+    tr = np.eye(4)
+    if cfg.get("align_center_of_mass", False):         # vtkCenterOfMass, UseScalarsAsWeights(False): mean of the points
+        tr[:3, 3] = -np.asarray(verts, np.float64).mean(axis=0)
+    return m @ tr                                      # t.Translate(translation)

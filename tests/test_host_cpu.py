@@ -191,3 +191,30 @@ def test_checkpoint_name_matching():
         hits = [i for i, n in enumerate(names) if M("MVLMModel_DTU3D", mode)._checkpoint_matches(n)]
         assert hits == [want], (mode, hits)
     assert [i for i, n in enumerate(names) if M("MVLMModel_BU_3DFE", "RGB+depth")._checkpoint_matches(n)] == [5]
+
+
+def test_pre_align_transform_matches_vtk_call_order():
+    """mvlm_b200/utils/prealign.py == the 4x4 composition of the legacy vtkTransform calls (oracle/stages.py), its
+    inverse returns the points, and the order is the one of estimator3d.py:198-209 (translate first, scale last)."""
+    from mvlm_b200.utils import prealign
+    from oracle import stages
+
+    rng = np.random.RandomState(5)
+    verts = (rng.rand(500, 3) * 100 + [10, -20, 30]).astype(np.float32)
+    cfg = {"align_center_of_mass": True, "rot_x": 12.0, "rot_y": -35.0, "rot_z": 7.5, "scale": 1.25}
+    a, b = prealign.affine(verts, cfg)
+    m = stages.pre_align_matrix(verts, cfg)
+    assert np.abs(m[:3, :3] - a).max() <= 1e-14 and np.abs(m[:3, 3] - b).max() <= 1e-11
+    moved = prealign.apply(verts, a, b)
+    assert moved.dtype == np.float32
+    want = (np.c_[verts.astype(np.float64), np.ones(len(verts))] @ m.T)[:, :3]
+    assert np.abs(moved - want).max() <= 1e-4                       # float32 storage of ~100 mm coordinates
+    assert np.abs(moved.astype(np.float64).mean(0)).max() <= 1e-4    # centre of mass at the origin
+    assert np.abs(prealign.invert(want, a, b) - verts).max() <= 1e-9
+    # a point on the z axis: Rz leaves it, Rx(90) takes it to -y, then scale 2
+    a2, b2 = prealign.affine(verts, {"rot_x": 90.0, "rot_z": 45.0, "scale": 2.0})
+    assert np.allclose(a2 @ [0, 0, 1.0] + b2, [0, -2.0, 0], atol=1e-12)
+    assert prealign.is_identity(None) and prealign.is_identity({"rot_x": 0, "scale": 1, "align_center_of_mass": False})
+    assert not prealign.is_identity({"align_center_of_mass": True})
+    with pytest.raises(ValueError):
+        prealign.affine(verts, {"rot_w": 1})

@@ -31,7 +31,8 @@ def _nchw(t):
 
 
 @pytest.mark.parametrize("n_landmarks,mode,size,views", [(73, "RGB+depth", 64, 2), (84, "geometry+depth", 64, 1),
-                                                        (73, "RGB", 128, 1)])
+                                                        (73, "RGB", 128, 1),
+                                                        (84, "RGB+depth", 128, 1)])  # the bu3dfe pipeline's default model
 def test_hourglass_matches_oracle(lib, n_landmarks, mode, size, views):
     from mvlm_b200 import ops
 

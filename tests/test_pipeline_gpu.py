@@ -224,3 +224,33 @@ def test_predict_folder_writes_reference_txt_files(lib, scan, tmp_path):
         assert back.shape == (84, 3) and np.array_equal(back, lm)      # %.18e round-trips float64 exactly
     with pytest.raises(ValueError, match="does not contain any .obj"):
         dm.predict_folder(tmp_path / "out")
+
+
+def test_pre_align_runs_the_path_on_the_aligned_scan_and_maps_back(lib, scan):
+    """pre_align (configs/*.json:59-84, estimator3d.py:186-248,257,286): landmarks of a pipeline with pre_align on scan X
+    == landmarks of the plain pipeline on the pre-aligned copy of X mapped back with the inverse transform; the identity
+    configuration changes nothing; the file path (fused and seam-by-seam) agrees with the array path."""
+    import dataclasses
+
+    import mvlm
+    from mvlm_b200.utils import prealign
+
+    path, mesh = scan, load_obj(scan)
+    tr = synth.random_view_transforms(8, seed=11)
+    kw = dict(n_views=8, weights=seeded_state_dict(73, "RGB+depth", 3), seed=4, n_hypotheses=4, verbose=False,
+              image_size=(128, 128), transforms=tr)
+    cfg = {"align_center_of_mass": True, "rot_x": 10.0, "rot_y": -15.0, "rot_z": 5.0, "scale": 0.9}
+    plain = mvlm.pipeline.create_pipeline("dtu3d", **kw)
+    aligned = mvlm.pipeline.create_pipeline("dtu3d", pre_align=cfg, **kw)
+    a, b = prealign.affine(mesh.verts, cfg)
+    moved = dataclasses.replace(mesh, verts=prealign.apply(mesh.verts, a, b))
+    want = prealign.invert(plain.predict_mesh(moved), a, b)
+    got = aligned.predict_mesh(mesh)
+    assert np.array_equal(got, want)
+    assert not np.allclose(got, plain.predict_mesh(mesh))            # the alignment does change what the CNN sees
+    ident = mvlm.pipeline.create_pipeline("dtu3d", pre_align={"rot_x": 0, "scale": 1}, **kw)
+    assert ident.pre_align is None and np.array_equal(ident.predict_mesh(mesh), plain.predict_mesh(mesh))
+    from_file = aligned.predict_one_file(path)
+    assert np.abs(from_file - got).max() <= 1e-9
+    seam = aligned._predict_seams(path, 0.0)                           # the reference's stage-by-stage flow
+    assert np.abs(seam - got).max() <= 1e-6
