@@ -147,6 +147,11 @@ int mvlm_hourglass_forward(mvlm_hourglass* net, const uint8_t* img_u8, const flo
  * (img, out) pointer tuple on first use and replayed afterwards (buffers must stay valid and unchanged). */
 int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32,
                                  float* out_heatmaps, float* out_peaks, void* stream);
+/* Peak selection of the out_peaks of forward / forward_graph (PaulsenModel.selection_method, paulsenpredictor.py:55,
+ * 112-158): 0 = "simple" (the fused arg-max), 1 = "moment" (centre of mass of the 31x31 window around it, :129-156).
+ * "moment" stays on the fused path: the window's heat-map values are re-evaluated from the last layer's input by a
+ * small kernel, so the (V,L,H,W) fp32 heat maps are not written to memory for it either. */
+int mvlm_hourglass_set_selection_method(mvlm_hourglass* net, int method);
 /* View-split hand-off (SURVEY.md 8b "mvlm_allgather_peaks", 8e): when one scan's views are split over ranks, each rank
  * runs the network on its block of views with the fused arg-max of the last convolution writing its keys
  * (u64 = ordered value << 32 | ~index, n_views x n_landmarks) STRAIGHT into this rank's slot of the all-gather buffer

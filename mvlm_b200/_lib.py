@@ -74,6 +74,7 @@ def _declare(lib: C.CDLL) -> None:
                                    i32, i32, vp, C.c_size_t, C.POINTER(vp)], i32),
         "mvlm_hourglass_forward": ([vp, vp, vp, vp, vp, vp], i32),
         "mvlm_hourglass_forward_graph": ([vp, vp, vp, vp, vp, vp], i32),
+        "mvlm_hourglass_set_selection_method": ([vp, i32], i32),
         "mvlm_hourglass_forward_keys": ([vp, vp, vp, vp, vp], i32),
         "mvlm_peaks_from_gathered_keys": ([vp, i32, i32, i32, i32, i32, vp, vp], i32),
         "mvlm_hourglass_num_launches": ([vp], i32),

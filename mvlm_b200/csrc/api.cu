@@ -178,6 +178,11 @@ int mvlm_hourglass_forward_graph(mvlm_hourglass* net, const uint8_t* img_u8, con
   return net->net.forward_graph(img_u8, img_f32, out_heatmaps, out_peaks, static_cast<cudaStream_t>(stream));
 }
 
+int mvlm_hourglass_set_selection_method(mvlm_hourglass* net, int method) {
+  MVLM_REQUIRE(net, "mvlm_hourglass_set_selection_method: null handle");
+  return net->net.set_selection_method(method);
+}
+
 int mvlm_hourglass_forward_keys(mvlm_hourglass* net, const uint8_t* img_u8, const float* img_f32, uint64_t* out_keys,
                                 void* stream) {
   MVLM_REQUIRE(net, "mvlm_hourglass_forward_keys: null handle");

@@ -644,6 +644,8 @@ int HourglassNet::emit() {
   flops_ += 2.0 * L_ * L_ * 9 * h * w;  // algorithmic FLOPs of the reference's conv11
   const float* b11 = nullptr;
   if ((rc = bias("conv11.bias", L_, Lp_, &b11))) return rc;
+  b11_ = b11;
+  x10_ = x10.p;
   for (int a = 0; a < 2; ++a) {
     for (int b = 0; b < 2; ++b) {
       note_use(x10.p); note_use(keys_);
@@ -660,6 +662,7 @@ int HourglassNet::emit() {
         owned_.push_back(wp);
         pack_phase_weight_kernel<<<64, 256>>>(w11, L_, L_, a, b, Lp_, Lp_, wp);
         MVLM_CHECK_CUDA(cudaGetLastError());
+        phase_w_[2 * a + b] = wp;
         ConvShape s;
         s.in = x10.p; s.n = V_; s.h = h2; s.w = w2; s.cin = Lp_; s.in_cs = Lp_;
         s.wpacked = wp; s.cout_pad = Lp_; s.n_tile = Lp_; s.kh = 2; s.kw = 2;
@@ -676,6 +679,7 @@ int HourglassNet::emit() {
   }
   {
     note_use(keys_);
+    note_use(x10.p);  // the "moment" selection re-evaluates windows of the last layer from its input
     NetOp op;
     op.kind = NetOp::PEAKS;
     push_op(op);
@@ -771,8 +775,22 @@ int HourglassNet::run_op(NetOp& op, const unsigned char* img_u8, const float* im
       MVLM_CHECK_CUDA(cudaMemsetAsync(keys, 0, op.bytes, stream));
       return MVLM_OK;
     case NetOp::PEAKS:
-      if (out_peaks && !out_keys_) return peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
+      if (out_peaks && !out_keys_) {
+        if (peak_method_ == 1)
+          return peaks_moment_from_keys(keys_, x10_, Lp_, Lp_, phase_w_, b11_, V_, L_, H_, W_, out_peaks, stream);
+        return peaks_from_keys(keys_, V_, L_, H_, W_, out_peaks, stream);
+      }
       return MVLM_OK;
+  }
+  return MVLM_OK;
+}
+
+int HourglassNet::set_selection_method(int method) {
+  MVLM_REQUIRE(method == 0 || method == 1, "hourglass: unknown selection method %d", method);
+  if (method != peak_method_) {
+    for (auto& g : graphs_) cudaGraphExecDestroy(g.second);  // the captured launch sequences end in the other peak kernel
+    graphs_.clear();
+    peak_method_ = method;
   }
   return MVLM_OK;
 }

@@ -52,6 +52,8 @@ class HourglassNet {
   int forward_graph(const unsigned char* img_u8, const float* img_f32, float* out_heatmaps, float* out_peaks,
                     cudaStream_t stream);
 
+  // 0 = "simple" (arg-max), 1 = "moment" (paulsenpredictor.py:129-156) for the peaks forward() / forward_graph() write
+  int set_selection_method(int method);
   // The network up to the fused arg-max: writes the (n_views x n_landmarks) u64 keys (ordered value << 32 | ~index)
   // into `out_keys` and runs no peak kernel (view-split path: out_keys is this rank's slot of the all-gather buffer).
   // Replays a CUDA graph like forward_graph.
@@ -145,6 +147,10 @@ class HourglassNet {
   std::vector<NetOp> ops_;
   unsigned long long* keys_ = nullptr;
   unsigned long long* out_keys_ = nullptr;  // set for the duration of forward_keys
+  int peak_method_ = 0;
+  const __nv_bfloat16* phase_w_[4] = {nullptr, nullptr, nullptr, nullptr};  // conv11 phase kernels, bias, input
+  const float* b11_ = nullptr;
+  const __nv_bfloat16* x10_ = nullptr;
   double flops_ = 0.0;
   struct GraphKey { const void* a; const void* b; const void* c; const void* d; };
   std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs_;

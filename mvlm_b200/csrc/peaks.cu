@@ -135,6 +135,94 @@ __global__ void peaks_from_keys_kernel(const unsigned long long* __restrict__ ke
   o[2] = val;
 }
 
+// "moment" selection on the fused path (paulsenpredictor.py:129-156): the 31x31 window of heat-map values around the
+// fused arg-max is RE-EVALUATED here from the last layer's input instead of being read from materialised heat maps
+// (1.9 GB of fp32 written and read back at 100 views otherwise): conv11 on the nearest-x2 up-sampled conv10 output, as
+// the same four 2x2 phase kernels the tensor-core path uses (bf16 operands, fp32 accumulation, + bias), 961 pixels x
+// 4 taps x Lp channels per (view, landmark).  One block per (view, landmark); sums in fp64 like peaks_kernel.
+struct PhaseWeights {
+  const __nv_bfloat16* w[4];  // phase (a, b) -> [cout_pad][kx(2)][ky(2)][cin_pad], index 2 * a + b
+};
+
+__global__ void __launch_bounds__(256) moment_from_keys_kernel(const unsigned long long* __restrict__ keys,
+                                                               const __nv_bfloat16* __restrict__ x, int cs, int cin,
+                                                               PhaseWeights pw, const float* __restrict__ bias, int V,
+                                                               int L, int H, int W, float* __restrict__ peaks) {
+  extern __shared__ float wl[];  // [4 phases][kx][ky][cin] of output channel l
+  const int vl = blockIdx.x;
+  const int v = vl / L, l = vl % L;
+  const unsigned long long k = keys[vl];
+  const unsigned int idx = 0xFFFFFFFFu - static_cast<unsigned int>(k & 0xFFFFFFFFu);
+  const float val = unorder_f32(static_cast<unsigned int>(k >> 32));
+  const int row = idx / W, col = idx % W;
+  double frow = row, fcol = col;
+  const int sz = 15;
+  __shared__ double acc[3];
+  // reference window test uses the map height for both axes (square maps), :141
+  if (row > sz && H - row > sz && col > sz && H - col > sz) {
+    for (int i = threadIdx.x; i < 16 * cin; i += blockDim.x) {
+      const int ph = i / (4 * cin), r = i % (4 * cin);
+      wl[i] = __bfloat162float(pw.w[ph][static_cast<size_t>(l) * 4 * cin + r]);
+    }
+    if (threadIdx.x < 3) acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int h2 = H >> 1, w2 = W >> 1;
+    const float b = bias[l];
+    double s_tot = 0.0, s_row = 0.0, s_col = 0.0;
+    for (int i = threadIdx.x; i < 31 * 31; i += blockDim.x) {
+      const int dr = i / 31, dc = i % 31;
+      const int y = row - sz + dr, xx = col - sz + dc;
+      const int pa = y & 1, pb = xx & 1;
+      const float* wp = wl + (2 * pa + pb) * 4 * cin;
+      float a = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 2; ++kx) {
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky) {
+          const int yy = (y >> 1) + ky + pa - 1, xl = (xx >> 1) + kx + pb - 1;
+          if (yy < 0 || yy >= h2 || xl < 0 || xl >= w2) continue;  // zero padding of the convolution
+          const uint4* px = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(v) * h2 + yy) * w2 + xl) * cs);
+          const float* wt = wp + (kx * 2 + ky) * cin;
+          for (int c8 = 0; c8 < (cin >> 3); ++c8) {
+            const uint4 q = __ldg(px + c8);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 t = __bfloat1622float2(h[j]);
+              a = fmaf(t.x, wt[8 * c8 + 2 * j], a);
+              a = fmaf(t.y, wt[8 * c8 + 2 * j + 1], a);
+            }
+          }
+        }
+      }
+      const double e = static_cast<double>(a + b);
+      s_tot += e;
+      s_row += e * dr;
+      s_col += e * dc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s_tot += __shfl_xor_sync(0xffffffffu, s_tot, o);
+      s_row += __shfl_xor_sync(0xffffffffu, s_row, o);
+      s_col += __shfl_xor_sync(0xffffffffu, s_col, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&acc[0], s_tot);
+      atomicAdd(&acc[1], s_row);
+      atomicAdd(&acc[2], s_col);
+    }
+    __syncthreads();
+    frow = row + (acc[1] / acc[0] - sz);
+    fcol = col + (acc[2] / acc[0] - sz);
+  }
+  if (threadIdx.x == 0) {
+    float* o = peaks + (static_cast<size_t>(l) * V + v) * 3;
+    o[0] = static_cast<float>(frow - 1.0);
+    o[1] = static_cast<float>(fcol - 0.5);
+    o[2] = val;
+  }
+}
+
 // keys gathered from `world` ranks, slot r = (slot_views x L) keys of rank r's contiguous view block (the first
 // V % world ranks hold one view more, sharding.split_views); unused slot rows are never read
 __global__ void peaks_from_gathered_keys_kernel(const unsigned long long* __restrict__ keys, int V, int L, int W, int world,
@@ -164,6 +252,19 @@ int peaks_from_gathered_keys(const unsigned long long* keys, int v, int l, int w
   MVLM_REQUIRE(v > 0 && l > 0 && w > 0 && world > 0 && world <= v && slot_views >= ceil_div(v, world),
                "peaks_from_gathered_keys: bad layout (%d views, %d ranks, %d views per slot)", v, world, slot_views);
   peaks_from_gathered_keys_kernel<<<ceil_div(v * l, 256), 256, 0, s>>>(keys, v, l, w, world, slot_views, peaks);
+  count_launch();
+  MVLM_CHECK_CUDA(cudaGetLastError());
+  return MVLM_OK;
+}
+
+int peaks_moment_from_keys(const unsigned long long* keys, const __nv_bfloat16* x, int x_cs, int cin,
+                           const __nv_bfloat16* const* phase_w, const float* bias, int v, int l, int h, int w, float* peaks,
+                           cudaStream_t s) {
+  MVLM_REQUIRE(keys && x && phase_w && bias && peaks, "peaks_moment_from_keys: null pointer");
+  MVLM_REQUIRE(cin % 8 == 0 && x_cs % 8 == 0 && h % 2 == 0 && w % 2 == 0, "peaks_moment_from_keys: bad shape");
+  PhaseWeights pw;
+  for (int i = 0; i < 4; ++i) pw.w[i] = phase_w[i];
+  moment_from_keys_kernel<<<v * l, 256, 16 * cin * sizeof(float), s>>>(keys, x, x_cs, cin, pw, bias, v, l, h, w, peaks);
   count_launch();
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;

@@ -29,6 +29,11 @@ int raster_launch(const RasterArgs& a, cudaStream_t stream);
 int peaks_from_heatmaps(const float* hm, int v, int l, int h, int w, int method, float* peaks, cudaStream_t s);
 // fused path: keys[v*l] written by the conv11 epilogue -> peaks (simple method only)
 int peaks_from_keys(const unsigned long long* keys, int v, int l, int h, int w, float* peaks, cudaStream_t s);
+// fused path, selection_method "moment": the 31x31 window around every fused arg-max is re-evaluated from the last
+// layer's input x (V, h/2, w/2, x_cs) bf16 with the four 2x2 phase kernels phase_w[2a+b] ([cout][2][2][cin]) + bias
+int peaks_moment_from_keys(const unsigned long long* keys, const __nv_bfloat16* x, int x_cs, int cin,
+                           const __nv_bfloat16* const* phase_w, const float* bias, int v, int l, int h, int w, float* peaks,
+                           cudaStream_t s);
 // view-split path: keys of all ranks gathered into `world` slots of slot_views x l keys each -> peaks (l, v, 3)
 int peaks_from_gathered_keys(const unsigned long long* keys, int v, int l, int w, int world, int slot_views, float* peaks,
                              cudaStream_t s);

@@ -159,8 +159,13 @@ class Hourglass:
         self.num_launches = lib.mvlm_hourglass_num_launches(handle)
         self.num_segments = lib.mvlm_hourglass_num_segments(handle)
 
-    def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False):
+    def forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False,
+                selection_method: str = "simple"):
+        """selection_method: "simple" (fused arg-max) or "moment" (31x31 centre of mass around it, windows re-evaluated
+        from the last layer's input: no heat maps in memory for either)."""
         with _on_device(self.device):
+            check(_lib.load().mvlm_hourglass_set_selection_method(self._h, {"simple": 0, "moment": 1}[selection_method]),
+                  "mvlm_hourglass_set_selection_method")
             return self._forward(img, want_heatmaps, want_peaks, graph)
 
     def _forward(self, img, want_heatmaps: bool = False, want_peaks: bool = True, graph: bool = False):

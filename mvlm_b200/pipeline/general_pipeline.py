@@ -128,7 +128,7 @@ class Pipeline(abc.ABC, TimeMixin):
                 return None
             fused = (isinstance(self.predictor_2d, PaulsenModel) and type(self.renderer_3d) is ObjRenderer3D
                      and type(self.estimator_3d) is Estimator3D and not self.render_image_stack
-                     and self.predictor_2d.selection_method == "simple")
+                     and self.predictor_2d.selection_method in ("simple", "moment"))
             if fused:
                 r = self.renderer_3d
                 if not file_name.is_file():

@@ -129,13 +129,12 @@ class PaulsenModel(Predictor2D):
         if chunk < v:
             return torch.cat([self.predict_landmarks_device(img[i:i + chunk]).clone() for i in range(0, v, chunk)], dim=1)
         net = self.network(v, h, w)
-        if self.selection_method == "simple":
-            # the rasteriser's persistent u8 image has a stable address: replay the captured CUDA graph
-            peaks, _ = net.forward(img, want_heatmaps=False, want_peaks=True, graph=img.dtype == torch.uint8)
+        if self.selection_method in ("simple", "moment"):
+            # the rasteriser's persistent u8 image has a stable address: replay the captured CUDA graph.  "moment" is
+            # fused too: its 31x31 windows are re-evaluated around the fused arg-max (csrc/peaks.cu), no heat maps
+            peaks, _ = net.forward(img, want_heatmaps=False, want_peaks=True, graph=img.dtype == torch.uint8,
+                                   selection_method=self.selection_method)
             return peaks
-        if self.selection_method == "moment":
-            _, hm = net.forward(img, want_heatmaps=True, want_peaks=False)
-            return ops.heatmap_peaks(hm, "moment")
         # the reference leaves the coordinates at zero for unknown methods (:118,:129)
         return torch.zeros((self.get_lm_count(), v, 3), dtype=torch.float32, device=self.device)
 

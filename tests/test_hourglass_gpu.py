@@ -105,3 +105,33 @@ def test_state_dict_of_another_model_is_rejected(lib):
     with pytest.raises(_lib.MvlmError, match="missing state_dict key hg2.rb7.conv2.weight"):
         ops.Hourglass(broken, 73, 4, 1, 64, 64)
     ops.Hourglass(sd, 73, 4, 1, 64, 64)  # the right one still builds
+
+
+@pytest.mark.parametrize("n_landmarks,mode,size,views", [(73, "RGB+depth", 128, 3), (84, "geometry+depth", 64, 2)])
+def test_fused_moment_selection_equals_moment_of_materialised_heat_maps(lib, n_landmarks, mode, size, views):
+    """selection_method="moment" (paulsenpredictor.py:129-156) on the fused path: the 31x31 windows re-evaluated around
+    the fused arg-max give the same sub-pixel peaks (<= 1e-4 px; same value, same validity rule at the borders) as the
+    standalone peak kernel on the heat maps the same plan materialises -- and those equal the numpy restatement."""
+    from mvlm_b200 import ops
+    from oracle import stages
+
+    sd = seeded_state_dict(n_landmarks, mode, seed=21)
+    cin = IMAGE_CHANNELS[mode]
+    g = torch.Generator().manual_seed(9)
+    img = torch.randint(0, 256, (views, size, size, 4), generator=g, dtype=torch.uint8)
+    img[..., cin:] = 0
+    img = img.cuda()
+    net = ops.Hourglass(sd, n_landmarks, cin, views, size, size)
+    simple, hm = net.forward(img, want_heatmaps=True)
+    want = ops.heatmap_peaks(hm, "moment")
+    fused = net.forward(img, selection_method="moment")[0].clone()
+    fused_graph = net.forward(img, selection_method="moment", graph=True)[0].clone()
+    back = net.forward(img, graph=True)[0].clone()            # switching back replays the arg-max plan again
+    torch.cuda.synchronize()
+    assert torch.equal(fused, fused_graph) and torch.equal(back, simple)
+    assert torch.equal(fused[..., 2], want[..., 2])
+    assert (fused[..., :2] - want[..., :2]).abs().max().item() <= 1e-4
+    ref = stages.heatmap_peaks(hm.cpu().numpy(), "moment")
+    assert np.abs(fused.cpu().numpy()[..., :2] - ref[..., :2]).max() <= 2e-4
+    moved = (fused[..., :2] != simple[..., :2]).any(-1).float().mean().item()
+    assert moved > 0.3   # the refinement does apply to most peaks (those 16 px away from the border)
