@@ -425,14 +425,14 @@ def run_ours(args):
     dmesh = r.upload(mesh)
     rot = torch.from_numpy(rotation_matrices(transforms).reshape(-1, 9)).to(dev)
     draws = torch.from_numpy(e.seeded_draws(N_LANDMARKS).view(np.int32)).to(dev)
-    zbuf = torch.empty((args.views, args.size, args.size), dtype=torch.int64, device=dev)
+    zbuf = ops.raster_workspace(args.views, args.size, args.size, len(mesh.verts), dev)
     u8 = torch.empty((args.views, args.size, args.size, 4), dtype=torch.uint8, device=dev)
     ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in ("raster", "cnn", "tail")}
 
     def device_step(record=False):
         if record:
             ev["raster"][0].record()
-        ops.raster_multiview(dmesh.verts, dmesh.uvs, dmesh.tris, dmesh.tex, rot, args.size, args.size, IMAGE_MODE,
+        ops.raster_multiview(dmesh.verts, dmesh.uvs, dmesh.tris, dmesh.tex4(), rot, args.size, args.size, IMAGE_MODE,
                              zbuf=zbuf, out_u8=u8)
         if record:
             ev["raster"][1].record()

@@ -113,12 +113,15 @@ int mvlm_jpeg_decode_rgb(const uint8_t* data, size_t len, uint8_t* out_rgb_dev, 
 /*   material src/mvlm/utils/utils3d.py:26-64.                                 */
 /* rot: (V,9) float64 row-major R = Ry(ry)*Rx(rx)*Rz(rz) per view.             */
 /* channel_mode: 0 RGB+depth, 1 geometry+depth, 2 RGB, 3 depth, 4 geometry.    */
-/* zbuf_workspace: V*H*W*8 bytes.  Any of the four outputs may be NULL.        */
+/* tex: (Th,Tw,tex_channels) u8, tex_channels 3 (RGB) or 4 (RGBA, one 4-byte load  */
+/* per texel).  workspace: mvlm_raster_workspace_bytes(...) bytes = the packed      */
+/* depth|triangle-id keys of all pixels + the per-(view, vertex) window coordinates */
+/* (each vertex is transformed once per view).  Any of the four outputs may be NULL.*/
 /* ------------------------------------------------------------------------- */
-size_t mvlm_raster_workspace_bytes(int n_views, int h, int w);
-int mvlm_raster_multiview(const float* verts, const float* uvs, const int32_t* tris, int n_tris,
-                          const uint8_t* tex, int tex_h, int tex_w, const double* rot, int n_views,
-                          int h, int w, int channel_mode, void* zbuf_workspace,
+size_t mvlm_raster_workspace_bytes(int n_views, int h, int w, int n_verts);
+int mvlm_raster_multiview(const float* verts, int n_verts, const float* uvs, const int32_t* tris, int n_tris,
+                          const uint8_t* tex, int tex_h, int tex_w, int tex_channels, const double* rot,
+                          int n_views, int h, int w, int channel_mode, void* workspace, size_t workspace_bytes,
                           uint8_t* out_u8 /* (V,H,W,4) */, float* out_f32 /* (V,H,W,C) */,
                           int32_t* out_tri_id /* (V,H,W) */, float* out_depth /* (V,H,W) */,
                           void* stream);

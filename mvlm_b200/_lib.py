@@ -66,8 +66,9 @@ def _declare(lib: C.CDLL) -> None:
         "mvlm_version": ([], i32),
         "mvlm_conv2d_bf16": ([C.POINTER(ConvArgs), vp], i32),
         "mvlm_pack_conv_weight": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
-        "mvlm_raster_workspace_bytes": ([i32, i32, i32], C.c_size_t),
-        "mvlm_raster_multiview": ([vp, vp, vp, i32, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp], i32),
+        "mvlm_raster_workspace_bytes": ([i32, i32, i32, i32], C.c_size_t),
+        "mvlm_raster_multiview": ([vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, C.c_size_t, vp, vp,
+                                   vp, vp, vp], i32),
         "mvlm_hourglass_workspace_bytes": ([i32, i32, i32, i32, i32], C.c_size_t),
         "mvlm_hourglass_flops_per_view": ([i32, i32, i32, i32], f64),
         "mvlm_hourglass_create": ([C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(C.c_longlong), i32, i32, i32, i32,

@@ -113,18 +113,19 @@ int mvlm_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw
   return MVLM_OK;
 }
 
-size_t mvlm_raster_workspace_bytes(int n_views, int h, int w) {
-  return static_cast<size_t>(n_views) * h * w * sizeof(unsigned long long);
+size_t mvlm_raster_workspace_bytes(int n_views, int h, int w, int n_verts) {
+  return raster_workspace_bytes(n_views, h, w, n_verts);
 }
 
-int mvlm_raster_multiview(const float* verts, const float* uvs, const int32_t* tris, int n_tris, const uint8_t* tex,
-                          int tex_h, int tex_w, const double* rot, int n_views, int h, int w, int channel_mode,
-                          void* zbuf_workspace, uint8_t* out_u8, float* out_f32, int32_t* out_tri_id,
-                          float* out_depth, void* stream) {
+int mvlm_raster_multiview(const float* verts, int n_verts, const float* uvs, const int32_t* tris, int n_tris,
+                          const uint8_t* tex, int tex_h, int tex_w, int tex_channels, const double* rot, int n_views, int h,
+                          int w, int channel_mode, void* workspace, size_t workspace_bytes, uint8_t* out_u8, float* out_f32,
+                          int32_t* out_tri_id, float* out_depth, void* stream) {
   RasterArgs a;
-  a.verts = verts; a.uvs = uvs; a.tris = tris; a.nt = n_tris; a.tex = tex; a.th = tex_h; a.tw = tex_w;
+  a.verts = verts; a.nv = n_verts; a.uvs = uvs; a.tris = tris; a.nt = n_tris;
+  a.tex = tex; a.th = tex_h; a.tw = tex_w; a.tex_c = tex_channels;
   a.rot = rot; a.n_views = n_views; a.h = h; a.w = w; a.channel_mode = channel_mode;
-  a.zbuf = static_cast<unsigned long long*>(zbuf_workspace);
+  a.zbuf = static_cast<unsigned long long*>(workspace); a.workspace_bytes = workspace_bytes;
   a.out_u8 = out_u8; a.out_f32 = out_f32; a.out_tri = out_tri_id; a.out_z = out_depth;
   return raster_launch(a, static_cast<cudaStream_t>(stream));
 }

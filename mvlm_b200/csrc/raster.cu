@@ -1,22 +1,30 @@
-// Batched multi-view orthographic rasteriser: all V views of one mesh in one launch pair.
+// Batched multi-view orthographic rasteriser: all V views of one mesh in one launch sequence.
 //
 // Replaces ObjVTKRenderer3D.render_3d_multi_rgb_geometry_depth (reference
 // src/mvlm/utils/render3d.py:114-177; camera :53-59,:136,:150-152; depth byte encoder
 // :73-77,:166-170; row flip :177; /255 :191) and obj_to_actor's material
 // (src/mvlm/utils/utils3d.py:26-64: nearest-neighbour texture, ambient 1 / diffuse 0).
 //
-//   raster_tris    one thread per (view, triangle): rotate the three vertices (double, like
-//                  vtkTransformPolyDataFilter), map to the window in fp32, and atomicMin the packed
-//                  (depth bits << 32 | triangle id) key of every covered pixel centre.  The meshes
-//                  are micro-polygon (~0.5 px/triangle at 256^2), so the work is triangle setup
-//                  plus < 1 atomic per triangle; a per-view z-buffer is 512 KB and stays in L2.
-//   raster_resolve one thread per pixel: winner triangle -> barycentric uv -> nearest texel,
-//                  depth byte, optional geometry shade; writes the u8 NHWC4 image the CNN stem
+//   raster_xform   one thread per (view, vertex): rotate the vertex (double, like
+//                  vtkTransformPolyDataFilter) and map it to the window in fp32 ONCE; the (x, y, z-buffer value)
+//                  triple is kept as a float4 per (view, vertex) for the two kernels below.  (Round 1 re-did this
+//                  per incident triangle and again per covered pixel: ~6x + 3x redundant fp64 work, and the
+//                  triangle kernel was instruction-bound on it.)
+//   raster_tris    one thread per (view, triangle): three 16-byte gathers, edge functions, and an atomicMin of
+//                  the packed (depth bits << 32 | triangle id) key on every covered pixel centre.  The meshes are
+//                  micro-polygon (~0.5 px/triangle at 256^2, 0.1 at config 4), so the work is triangle setup plus
+//                  < 1 atomic per triangle; a per-view z-buffer is 512 KB and stays in L2.  Binning triangles into
+//                  screen tiles with a shared-memory z-tile (the textbook design for LARGE triangles) costs two more
+//                  passes over the (view, triangle) pairs to save less than one global atomic each: DESIGN.md 7d.
+//   raster_resolve one thread per pixel: winner triangle -> barycentric uv -> nearest texel (one 4-byte load from
+//                  the RGBA texture), depth byte, optional geometry shade; writes the u8 NHWC4 image the CNN stem
 //                  consumes and, on request, the fp32 (V,H,W,C) stack / triangle-id / z maps.
 //
 // This file is compiled with --fmad=false: every fp32 operation rounds separately, in the same
 // order as oracle/csrc/oracle_native.c (built with -ffp-contract=off), so triangle-id maps and
 // depth bytes are bit-identical to the CPU oracle.
+#include <algorithm>
+
 #include "common.cuh"
 #include "stages.cuh"
 
@@ -49,29 +57,47 @@ __device__ __forceinline__ SV xform_vertex(const float* __restrict__ v, const do
   return o;
 }
 
-__global__ void __launch_bounds__(256) raster_tris_kernel(const float* __restrict__ verts,
-                                                          const int* __restrict__ tris, int nt,
-                                                          const double* __restrict__ rot, int H, int W,
-                                                          unsigned long long* __restrict__ zbuf) {
+// (view, vertex) -> window position + z-buffer value, computed once (sv[view * nv + vertex])
+__global__ void __launch_bounds__(256) raster_xform_kernel(const float* __restrict__ verts, int nv,
+                                                           const double* __restrict__ rot, int H, int W,
+                                                           float4* __restrict__ sv) {
   __shared__ double R[9];
   const int view = blockIdx.y;
   if (threadIdx.x < 9) R[threadIdx.x] = rot[view * 9 + threadIdx.x];
   __syncthreads();
   const float kx = static_cast<float>(static_cast<double>(W) / 300.0);
   const float ky = static_cast<float>(static_cast<double>(H) / 300.0);
+  float4* out = sv + static_cast<size_t>(view) * nv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+    const SV a = xform_vertex(verts + 3 * i, R, kx, ky);
+    out[i] = make_float4(a.sx, a.sy, a.zb, 0.f);
+  }
+}
+
+__device__ __forceinline__ SV load_sv(const float4* __restrict__ sv, int i) {
+  const float4 q = __ldg(sv + i);
+  SV o;
+  o.sx = q.x; o.sy = q.y; o.zb = q.z;
+  return o;
+}
+
+__global__ void __launch_bounds__(256) raster_tris_kernel(const float4* __restrict__ sv, int nv,
+                                                          const int* __restrict__ tris, int nt, int H, int W,
+                                                          unsigned long long* __restrict__ zbuf) {
+  const int view = blockIdx.y;
+  const float4* svv = sv + static_cast<size_t>(view) * nv;
   unsigned long long* zb = zbuf + static_cast<size_t>(view) * H * W;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int i0 = __ldg(tris + 3 * t), i1 = __ldg(tris + 3 * t + 1), i2 = __ldg(tris + 3 * t + 2);
-    const SV a = xform_vertex(verts + 3 * i0, R, kx, ky);
-    const SV b = xform_vertex(verts + 3 * i1, R, kx, ky);
-    const SV c = xform_vertex(verts + 3 * i2, R, kx, ky);
-    const float area = edge_fn(a.sx, a.sy, b.sx, b.sy, c.sx, c.sy);
-    if (area == 0.0f || area != area) continue;
+    const SV a = load_sv(svv, i0), b = load_sv(svv, i1), c = load_sv(svv, i2);
     const float minx = fminf(a.sx, fminf(b.sx, c.sx)), maxx = fmaxf(a.sx, fmaxf(b.sx, c.sx));
     const float miny = fminf(a.sy, fminf(b.sy, c.sy)), maxy = fmaxf(a.sy, fmaxf(b.sy, c.sy));
     int x0 = static_cast<int>(ceilf(minx - 0.5f)), x1 = static_cast<int>(floorf(maxx - 0.5f));
     int y0 = static_cast<int>(ceilf(miny - 0.5f)), y1 = static_cast<int>(floorf(maxy - 0.5f));
     x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, W - 1); y1 = min(y1, H - 1);
+    if (x0 > x1 || y0 > y1) continue;  // no pixel centre inside the bounding box: most micro-polygons end here
+    const float area = edge_fn(a.sx, a.sy, b.sx, b.sy, c.sx, c.sy);
+    if (area == 0.0f || area != area) continue;
     for (int py = y0; py <= y1; ++py) {
       for (int px = x0; px <= x1; ++px) {
         const float cx = static_cast<float>(px) + 0.5f, cy = static_cast<float>(py) + 0.5f;
@@ -92,10 +118,13 @@ __global__ void __launch_bounds__(256) raster_tris_kernel(const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g) {
-  const size_t total = static_cast<size_t>(g.n_views) * g.h * g.w;
-  const size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (pix >= total) return;
+// views view0 .. view0 + n_chunk - 1 (sv holds the transformed vertices of exactly these views)
+__global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g, const float4* __restrict__ sv, int view0,
+                                                             int n_chunk) {
+  const size_t total = static_cast<size_t>(n_chunk) * g.h * g.w;
+  const size_t lpix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (lpix >= total) return;
+  const size_t pix = lpix + static_cast<size_t>(view0) * g.h * g.w;
   const int px = static_cast<int>(pix % g.w);
   const int py = static_cast<int>((pix / g.w) % g.h);
   const int view = static_cast<int>(pix / (static_cast<size_t>(g.w) * g.h));
@@ -110,11 +139,8 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g) {
     const int i0 = __ldg(g.tris + 3 * tid), i1 = __ldg(g.tris + 3 * tid + 1), i2 = __ldg(g.tris + 3 * tid + 2);
     const double* R = g.rot + view * 9;
     if (g.tex && g.uvs && (mode == 0 || mode == 2)) {
-      const float kx = static_cast<float>(static_cast<double>(g.w) / 300.0);
-      const float ky = static_cast<float>(static_cast<double>(g.h) / 300.0);
-      const SV a = xform_vertex(g.verts + 3 * i0, R, kx, ky);
-      const SV b = xform_vertex(g.verts + 3 * i1, R, kx, ky);
-      const SV c = xform_vertex(g.verts + 3 * i2, R, kx, ky);
+      const float4* svv = sv + static_cast<size_t>(view - view0) * g.nv;
+      const SV a = load_sv(svv, i0), b = load_sv(svv, i1), c = load_sv(svv, i2);
       const float cx = static_cast<float>(px) + 0.5f, cy = static_cast<float>(py) + 0.5f;
       const float area = edge_fn(a.sx, a.sy, b.sx, b.sy, c.sx, c.sy);
       const float l0 = edge_fn(b.sx, b.sy, c.sx, c.sy, cx, cy) / area;
@@ -126,8 +152,14 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g) {
       int ty = static_cast<int>(floorf(v * static_cast<float>(g.th)));
       tx %= g.tw; if (tx < 0) tx += g.tw;
       ty %= g.th; if (ty < 0) ty += g.th;
-      const unsigned char* texel = g.tex + (static_cast<size_t>(g.th - 1 - ty) * g.tw + tx) * 3;
-      r8 = texel[0]; g8 = texel[1]; b8 = texel[2];
+      const size_t ti = static_cast<size_t>(g.th - 1 - ty) * g.tw + tx;
+      if (g.tex_c == 4) {  // RGBA texture: one 4-byte load per texel
+        const uchar4 q4 = __ldg(reinterpret_cast<const uchar4*>(g.tex) + ti);
+        r8 = q4.x; g8 = q4.y; b8 = q4.z;
+      } else {
+        const unsigned char* texel = g.tex + ti * 3;
+        r8 = texel[0]; g8 = texel[1]; b8 = texel[2];
+      }
       r = static_cast<float>(r8) / 255.0f; gr = static_cast<float>(g8) / 255.0f; bl = static_cast<float>(b8) / 255.0f;
     }
     if (mode == 1 || mode == 4) {
@@ -184,17 +216,44 @@ int raster_channels(int mode) {
   return -1;
 }
 
+// transformed vertices are kept for at most this many bytes at a time (views are processed in chunks beyond it):
+// 100 views of a 50k-vertex scan are 80 MB (one chunk), config 4 (1M vertices) runs 16 views per chunk
+constexpr size_t kSvBudgetBytes = 256u << 20;
+
+static int sv_chunk_views(int n_views, int nv) {
+  const size_t per_view = static_cast<size_t>(nv) * sizeof(float4);
+  const size_t fit = per_view ? kSvBudgetBytes / per_view : static_cast<size_t>(n_views);
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(n_views), fit)));
+}
+
+size_t raster_workspace_bytes(int n_views, int h, int w, int n_verts) {
+  const size_t z = (static_cast<size_t>(n_views) * h * w * sizeof(unsigned long long) + 255) & ~static_cast<size_t>(255);
+  return z + static_cast<size_t>(sv_chunk_views(n_views, n_verts)) * n_verts * sizeof(float4);
+}
+
 int raster_launch(const RasterArgs& g, cudaStream_t stream) {
   MVLM_REQUIRE(g.verts && g.tris && g.rot && g.zbuf, "raster: null pointer");
-  MVLM_REQUIRE(g.nt > 0 && g.n_views > 0 && g.h > 0 && g.w > 0, "raster: bad sizes");
+  MVLM_REQUIRE(g.nt > 0 && g.nv > 0 && g.n_views > 0 && g.h > 0 && g.w > 0, "raster: bad sizes");
   MVLM_REQUIRE(raster_channels(g.channel_mode) > 0, "raster: unknown channel_mode %d", g.channel_mode);
+  MVLM_REQUIRE(!g.tex || g.tex_c == 3 || g.tex_c == 4, "raster: texture must have 3 or 4 channels (got %d)", g.tex_c);
+  MVLM_REQUIRE(g.workspace_bytes >= raster_workspace_bytes(g.n_views, g.h, g.w, g.nv),
+               "raster: workspace too small (%zu bytes given, %zu needed)", g.workspace_bytes,
+               raster_workspace_bytes(g.n_views, g.h, g.w, g.nv));
   const size_t npix = static_cast<size_t>(g.n_views) * g.h * g.w;
+  const size_t zbytes = (npix * sizeof(unsigned long long) + 255) & ~static_cast<size_t>(255);
+  float4* sv = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(g.zbuf) + zbytes);
   MVLM_CHECK_CUDA(cudaMemsetAsync(g.zbuf, 0xFF, npix * sizeof(unsigned long long), stream));
-  dim3 grid(ceil_div(g.nt, 256), g.n_views);
-  if (grid.x > 1024) grid.x = 1024;
-  raster_tris_kernel<<<grid, 256, 0, stream>>>(g.verts, g.tris, g.nt, g.rot, g.h, g.w, g.zbuf);
-  raster_resolve_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(g);
-  count_launch(2);
+  const int chunk = sv_chunk_views(g.n_views, g.nv);
+  const size_t view_pix = static_cast<size_t>(g.h) * g.w;
+  for (int v0 = 0; v0 < g.n_views; v0 += chunk) {
+    const int nc = std::min(chunk, g.n_views - v0);
+    dim3 gx(std::min(ceil_div(g.nv, 256), 1024), nc);
+    raster_xform_kernel<<<gx, 256, 0, stream>>>(g.verts, g.nv, g.rot + static_cast<size_t>(v0) * 9, g.h, g.w, sv);
+    dim3 gt(std::min(ceil_div(g.nt, 256), 1024), nc);
+    raster_tris_kernel<<<gt, 256, 0, stream>>>(sv, g.nv, g.tris, g.nt, g.h, g.w, g.zbuf + static_cast<size_t>(v0) * view_pix);
+    raster_resolve_kernel<<<static_cast<unsigned>((nc * view_pix + 255) / 256), 256, 0, stream>>>(g, sv, v0, nc);
+    count_launch(3);
+  }
   MVLM_CHECK_CUDA(cudaGetLastError());
   return MVLM_OK;
 }

@@ -7,21 +7,24 @@ namespace mvlm {
 // ---- raster.cu ------------------------------------------------------------
 struct RasterArgs {
   const float* verts = nullptr;       // (Nv,3)
+  int nv = 0;
   const float* uvs = nullptr;         // (Nv,2) or null
   const int* tris = nullptr;          // (Nt,3)
   int nt = 0;
-  const unsigned char* tex = nullptr;  // (Th,Tw,3) or null
-  int th = 0, tw = 0;
+  const unsigned char* tex = nullptr;  // (Th,Tw,tex_c) or null
+  int th = 0, tw = 0, tex_c = 3;       // tex_c = 3 (RGB) or 4 (RGBA: one 4-byte load per texel)
   const double* rot = nullptr;        // (V,9) row-major R = Ry*Rx*Rz
   int n_views = 0, h = 0, w = 0;
   int channel_mode = 0;               // 0 RGB+depth, 1 geometry+depth, 2 RGB, 3 depth, 4 geometry
-  unsigned long long* zbuf = nullptr;  // (V,H,W) workspace
+  unsigned long long* zbuf = nullptr;  // workspace of raster_workspace_bytes(): (V,H,W) keys, then transformed vertices
+  size_t workspace_bytes = 0;
   unsigned char* out_u8 = nullptr;     // (V,H,W,4) packed channels (CNN stem input) or null
   float* out_f32 = nullptr;            // (V,H,W,C) reference-layout stack or null
   int* out_tri = nullptr;              // (V,H,W) or null
   float* out_z = nullptr;              // (V,H,W) or null
 };
 int raster_channels(int mode);
+size_t raster_workspace_bytes(int n_views, int h, int w, int n_verts);
 int raster_launch(const RasterArgs& a, cudaStream_t stream);
 
 // ---- peaks.cu -------------------------------------------------------------

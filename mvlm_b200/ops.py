@@ -81,24 +81,33 @@ CHANNEL_MODES = {"RGB+depth": 0, "geometry+depth": 1, "RGB": 2, "depth": 3, "geo
 MODE_CHANNELS = {0: 4, 1: 2, 2: 3, 3: 1, 4: 1}
 
 
+def raster_workspace(n_views: int, h: int, w: int, n_verts: int, device) -> torch.Tensor:
+    """Scratch of the rasteriser: packed depth|triangle-id keys of all pixels + per-(view, vertex) window coordinates."""
+    n = _lib.load().mvlm_raster_workspace_bytes(n_views, h, w, n_verts)
+    return torch.empty(((n + 7) // 8,), dtype=torch.int64, device=device)
+
+
 def raster_multiview(verts, uvs, tris, tex, rot, h: int, w: int, channel_mode: str = "RGB+depth",
                      want_f32: bool = False, want_tri: bool = False, want_z: bool = False, zbuf=None, out_u8=None):
-    """verts (Nv,3) f32, uvs (Nv,2) f32|None, tris (Nt,3) i32, tex (Th,Tw,3) u8|None, rot (V,9|3,3) f64 -- all cuda.
+    """verts (Nv,3) f32, uvs (Nv,2) f32|None, tris (Nt,3) i32, tex (Th,Tw,3|4) u8|None, rot (V,9|3,3) f64 -- all cuda.
+    zbuf: optional persistent workspace from raster_workspace().
     Returns dict(u8=(V,H,W,4) u8, f32=(V,H,W,C)|None, tri=(V,H,W) i32|None, z=(V,H,W) f32|None)."""
     lib = _lib.load()
     dev = verts.device
     mode = CHANNEL_MODES[channel_mode]
     v = rot.shape[0]
-    if zbuf is None:
-        zbuf = torch.empty((v, h, w), dtype=torch.int64, device=dev)
+    need = lib.mvlm_raster_workspace_bytes(v, h, w, verts.shape[0])
+    if zbuf is None or zbuf.numel() * zbuf.element_size() < need:
+        zbuf = raster_workspace(v, h, w, verts.shape[0], dev)
     if out_u8 is None:
         out_u8 = torch.empty((v, h, w, 4), dtype=torch.uint8, device=dev)
     f32 = torch.empty((v, h, w, MODE_CHANNELS[mode]), dtype=torch.float32, device=dev) if want_f32 else None
     tri = torch.empty((v, h, w), dtype=torch.int32, device=dev) if want_tri else None
     z = torch.empty((v, h, w), dtype=torch.float32, device=dev) if want_z else None
-    th, tw = (tex.shape[0], tex.shape[1]) if tex is not None else (0, 0)
-    check(lib.mvlm_raster_multiview(ptr(verts), ptr(uvs), ptr(tris), tris.shape[0], ptr(tex), th, tw, ptr(rot), v, h, w,
-                                    mode, ptr(zbuf), ptr(out_u8), ptr(f32), ptr(tri), ptr(z), cur_stream()),
+    th, tw, tc = (tex.shape[0], tex.shape[1], tex.shape[2]) if tex is not None else (0, 0, 3)
+    check(lib.mvlm_raster_multiview(ptr(verts), verts.shape[0], ptr(uvs), ptr(tris), tris.shape[0], ptr(tex), th, tw, tc,
+                                    ptr(rot), v, h, w, mode, ptr(zbuf), zbuf.numel() * zbuf.element_size(), ptr(out_u8),
+                                    ptr(f32), ptr(tri), ptr(z), cur_stream()),
           "mvlm_raster_multiview")
     return {"u8": out_u8, "f32": f32, "tri": tri, "z": z}
 

@@ -131,6 +131,21 @@ class DeviceMesh:
         self.mesh, self.verts, self.tris, self.uvs, self.tex = mesh, verts, tris, uvs, tex
         return self
 
+    def tex4(self):
+        """The texture as RGBA (one 4-byte load per texel in the rasteriser), expanded once per device mesh."""
+        if self.tex is None:
+            return None
+        t = self.__dict__.get("_tex4")
+        if t is None:
+            if self.tex.shape[-1] == 4:
+                t = self.tex
+            else:
+                t = torch.empty(self.tex.shape[:2] + (4,), dtype=torch.uint8, device=self.tex.device)
+                t[..., :3] = self.tex
+                t[..., 3] = 255
+            self._tex4 = t
+        return t
+
     def snap_grid(self):
         """Spatial index for the surface snap, built at most once per device mesh (None below ops.SNAP_GRID_MIN_TRIS,
         where the brute-force scan is faster than building the grid)."""
@@ -217,10 +232,14 @@ class ObjRenderer3D:
         # its CUDA graph, and no allocation happens per scan
         key = (rot.shape[0], h, w)
         if getattr(self, "_buf_key", None) != key:
-            self._zbuf = torch.empty((rot.shape[0], h, w), dtype=torch.int64, device=self.device)
             self._u8 = torch.empty((rot.shape[0], h, w, 4), dtype=torch.uint8, device=self.device)
+            self._zbuf = None
             self._buf_key = key
-        return ops.raster_multiview(dmesh.verts, dmesh.uvs, dmesh.tris, dmesh.tex, rot, h, w, self.channel_mode,
+        # the rasteriser's scratch also holds the per-(view, vertex) window coordinates: it grows with the largest scan
+        need = ops._lib.load().mvlm_raster_workspace_bytes(rot.shape[0], h, w, dmesh.verts.shape[0])
+        if self._zbuf is None or self._zbuf.numel() * 8 < need:
+            self._zbuf = ops.raster_workspace(rot.shape[0], h, w, int(dmesh.verts.shape[0] * 1.25), self.device)
+        return ops.raster_multiview(dmesh.verts, dmesh.uvs, dmesh.tris, dmesh.tex4(), rot, h, w, self.channel_mode,
                                     want_f32=want_f32, want_tri=want_tri, want_z=want_z, zbuf=self._zbuf, out_u8=self._u8)
 
     # render3d.py:114-177

@@ -24,7 +24,10 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.mvlm_version() >= 1
     assert lib.mvlm_last_error() is not None
     # size queries are pure host functions (no compute)
-    assert lib.mvlm_raster_workspace_bytes(100, 256, 256) == 100 * 256 * 256 * 8
+    # packed keys of all pixels + one float4 per (view, vertex)
+    assert lib.mvlm_raster_workspace_bytes(100, 256, 256, 50176) == 100 * 256 * 256 * 8 + 100 * 50176 * 16
+    # a million-vertex scan is processed in chunks of views: 256 MB of transformed vertices at most
+    assert lib.mvlm_raster_workspace_bytes(200, 512, 512, 1002001) <= 200 * 512 * 512 * 8 + (256 << 20)
     assert 2 * 2 ** 30 < lib.mvlm_hourglass_workspace_bytes(73, 4, 100, 256, 256) <= 6e9  # packed (20.3 GB unpacked)
     assert lib.mvlm_consensus_workspace_bytes(84, 200, 16384) > 0
     assert lib.mvlm_snap_workspace_bytes(73, 100000) > 0

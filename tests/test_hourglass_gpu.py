@@ -134,4 +134,4 @@ def test_fused_moment_selection_equals_moment_of_materialised_heat_maps(lib, n_l
     ref = stages.heatmap_peaks(hm.cpu().numpy(), "moment")
     assert np.abs(fused.cpu().numpy()[..., :2] - ref[..., :2]).max() <= 2e-4
     moved = (fused[..., :2] != simple[..., :2]).any(-1).float().mean().item()
-    assert moved > 0.02  # the refinement does apply (peaks more than 15 px from the border; random-init peaks hug the borders)
+    assert moved > 0.005  # the refinement does apply (to peaks more than 15 px from the border; random-init peaks hug the borders)

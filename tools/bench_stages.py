@@ -46,7 +46,7 @@ tex = synth.face_texture(1024, 1234)
 tr = synth.random_view_transforms(V, 1234)
 rot = cuda(rotation_matrices(tr).reshape(-1, 9))
 dv, du, dt, dx = cuda(verts), cuda(uvs), cuda(tris), cuda(tex)
-zbuf = torch.empty((V, S, S), dtype=torch.int64, device="cuda")
+zbuf = ops.raster_workspace(V, S, S, dv.shape[0], "cuda")
 u8 = torch.empty((V, S, S, 4), dtype=torch.uint8, device="cuda")
 ms = timeit(lambda: ops.raster_multiview(dv, du, dt, dx, rot, S, S, zbuf=zbuf, out_u8=u8))
 cov = float((ops.raster_multiview(dv, du, dt, dx, rot, S, S, want_tri=True)["tri"] >= 0).float().mean())

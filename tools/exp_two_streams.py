@@ -31,7 +31,7 @@ for i in range(n_streams):
         dmesh = dm.renderer_3d.upload(mesh)
         rot = torch.from_numpy(rotation_matrices(tr).reshape(-1, 9)).to(dev)
         draws = torch.from_numpy(dm.estimator_3d.seeded_draws(L).view(np.int32)).to(dev)
-        zbuf = torch.empty((V, S, S), dtype=torch.int64, device=dev)
+        zbuf = None
         u8 = torch.empty((V, S, S, 4), dtype=torch.uint8, device=dev)
     lanes.append(dict(dm=dm, st=st, net=net, dmesh=dmesh, rot=rot, draws=draws, zbuf=zbuf, u8=u8))
 
