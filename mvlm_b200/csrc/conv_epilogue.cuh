@@ -26,14 +26,17 @@ constexpr int kTraceTiles = 64;   // debug timeline: tiles traced on CTA 0
 enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
               F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */,
               F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */,
-              F_M64 = 1024 /* cout <= 64: UMMA M = 64, 16 channels per TMEM lane group */ };
+              F_M64 = 1024 /* cout <= 64: UMMA M = 64, 16 channels per TMEM lane group */,
+              F_POST2 = 2048 /* second full-resolution act copy (aux_mode 1) */,
+              F_POOLX = 4096 /* additional pooled raw + pooled act copies (aux_mode 2) */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 // feature mask of a planned layer (without F_M64)
 inline int feature_mask(const ConvEpilogue& e) {
   return (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
          (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0) |
-         (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0) | (e.res_up ? F_UP : 0);
+         (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0) | (e.res_up ? F_UP : 0) |
+         (e.aux_mode == 1 ? F_POST2 : 0) | (e.aux_mode == 2 ? F_POOLX : 0);
 }
 
 #ifdef __CUDACC__
@@ -111,7 +114,7 @@ struct TileCoord {
 // kernel, global memory in the dataflow kernel).
 struct ChannelParams {
   const float* bias;
-  const float* mid_s;
+  const float* mid_s;  // F_MID parameters, or the aux_scale / aux_shift of F_POST2 / F_POOLX (never both)
   const float* mid_t;
   const float* pre_s;
   const float* pre_t;
@@ -122,7 +125,7 @@ struct ChannelParams {
 // Image index of the tile inside each tensor the epilogue touches (ring buffers of the dataflow plan hold
 // fewer images than the layer processes; the per-layer kernel uses the tile's image for all of them).
 struct ImageSlots {
-  int pre, raw, post, res1, res2, up;
+  int pre, raw, post, res1, res2, up, aux1, aux2;
 };
 
 // running arg-max of the F_ARGMAX variants (lane = channel), flushed when the CTA moves to another image
@@ -207,6 +210,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   // F_POOL: raw / post live at half resolution
   const uint32_t rs_raw = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.raw_cs) * 2u;
   const uint32_t rs_post = static_cast<uint32_t>(((F & F_POOL) ? (s.w >> 1) : s.w) * e.post_cs) * 2u;
+  const uint32_t rs_aux1 = static_cast<uint32_t>(((F & F_POOLX) ? (s.w >> 1) : s.w) * e.aux1_cs) * 2u;
+  const uint32_t rs_aux2 = static_cast<uint32_t>((s.w >> 1) * e.aux2_cs) * 2u;
   // Residual inputs do not depend on the accumulator: they are fetched in BATCHES before they are needed -- all
   // units of a tile while its MMAs still run when they fit in ~64 registers, else half of them then and the other
   // half once the first are consumed.  (Loads issued one by one while earlier ones are being consumed do not work:
@@ -250,6 +255,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   uint8_t* const b_pre = (F & F_PRE) ? reinterpret_cast<uint8_t*>(e.out_pre + e.pre_co + c0 + static_cast<size_t>(pix_of(is.pre)) * e.pre_cs) : nullptr;
   uint8_t* const b_raw = (F & F_RAW) ? reinterpret_cast<uint8_t*>(e.out_raw + e.raw_co + c0 + static_cast<size_t>((F & F_POOL) ? ppix_of(is.raw) : pix_of(is.raw)) * e.raw_cs) : nullptr;
   uint8_t* const b_post = (F & F_POST) ? reinterpret_cast<uint8_t*>(e.out_post + e.post_co + c0 + static_cast<size_t>((F & F_POOL) ? ppix_of(is.post) : pix_of(is.post)) * e.post_cs) : nullptr;
+  uint8_t* const b_aux1 = (F & (F_POST2 | F_POOLX)) ? reinterpret_cast<uint8_t*>(e.out_aux1 + e.aux1_co + c0 + static_cast<size_t>((F & F_POOLX) ? ppix_of(is.aux1) : pix_of(is.aux1)) * e.aux1_cs) : nullptr;
+  uint8_t* const b_aux2 = (F & F_POOLX) ? reinterpret_cast<uint8_t*>(e.out_aux2 + e.aux2_co + c0 + static_cast<size_t>(ppix_of(is.aux2)) * e.aux2_cs) : nullptr;
   // rows at / below my first pixel that exist in the image (0 when my pixel column / channels do not):
   // unit r, pass ip is valid iff kUnitRows * r + kPassStep * ip < n_rows_ok
   const int n_rows_ok = vx ? s.h - y_first - my_i : 0;
@@ -437,16 +444,25 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
                 if (F & F_RES2) add8(r2[r % kPref][ip], f);
                 if (F & F_UP) add8(ru[r % kPref][M64 ? ip : 0], f);
               }
-              if (F & F_POOL) {
-                pool_cur[ip] = pack8(f);
-              } else if (valid) {
-                if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(row * rs_raw)) = pack8(f);
+              if (F & (F_POOL | F_POOLX)) pool_cur[ip] = pack8(f);
+              if (!(F & F_POOL) && valid) {
+                if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(row * rs_raw)) = (F & F_POOLX) ? pool_cur[ip] : pack8(f);
                 if (F & F_POST)
                   *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(row * rs_post)) = affine_relu_pack8(f, post_s, post_t);
+                if (F & F_POST2) {
+                  // parameters fetched at the point of use (shared memory in the per-layer kernel): 16 registers this
+                  // variant cannot hold across the tile
+                  // (applied to the bf16-rounded raw value, like the stand-alone pass that reads the stored tensor)
+                  float ax_s[8], ax_t[8], g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  add8(pack8(f), g);
+                  lds8(ep.mid_s + c0_ok, ax_s);
+                  lds8(ep.mid_t + c0_ok, ax_t);
+                  *reinterpret_cast<uint4*>(b_aux1 + static_cast<size_t>(row * rs_aux1)) = affine_relu_pack8(g, ax_s, ax_t);
+                }
               }
             }
             if (r < 2) MVLM_EPI_TRACE(10 + 4 * r);
-            if (F & F_POOL) {
+            if (F & (F_POOL | F_POOLX)) {
               // 2x2 max-pool of the bf16-rounded values; shuffles run on all lanes.
               //   M = 128: vertical partner = my other pass, horizontal (pixel column pj ^ 1) = lane ^ 4,
               //            one pooled row per unit;
@@ -474,11 +490,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
                 // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
                 const int prow = (kUnitRows / 2) * r + pp;  // pooled row relative to y_first / 2
                 if (2 * prow < n_rows_ok && my_i == 0 && (pj & 1) == 0) {
-                  if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(prow * rs_raw)) = m;
-                  if (F & F_POST) {
-                    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  if (F & F_POOL) {
+                    if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(prow * rs_raw)) = m;
+                    if (F & F_POST) {
+                      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                      add8(m, g);
+                      *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(prow * rs_post)) = affine_relu_pack8(g, post_s, post_t);
+                    }
+                  } else {  // F_POOLX: the pooled copies go to the aux tensors, raw / post were stored at full resolution
+                    *reinterpret_cast<uint4*>(b_aux1 + static_cast<size_t>(prow * rs_aux1)) = m;
+                    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ax_s[8], ax_t[8];
                     add8(m, g);
-                    *reinterpret_cast<uint4*>(b_post + static_cast<size_t>(prow * rs_post)) = affine_relu_pack8(g, post_s, post_t);
+                    lds8(ep.mid_s + c0_ok, ax_s);
+                    lds8(ep.mid_t + c0_ok, ax_t);
+                    *reinterpret_cast<uint4*>(b_aux2 + static_cast<size_t>(prow * rs_aux2)) = affine_relu_pack8(g, ax_s, ax_t);
                   }
                 }
               }

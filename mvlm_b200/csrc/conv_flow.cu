@@ -49,7 +49,7 @@ struct LayerSm {
   ChannelParams cp;
   int kind, f, tile_h, tail;
   int ring_in, ring_pre, ring_raw, ring_post, ring_res1, ring_res2, ring_up;
-  int pad_;
+  int ring_aux;
 };
 static_assert(sizeof(LayerSm) % 4 == 0, "copied word by word");
 
@@ -108,11 +108,16 @@ __device__ __forceinline__ Item decode_item(const int4& q) {
   X(F_UP | F_PRE | F_RES1 | F_RAW | F_POST)   \
   X(F_UP | F_PRE | F_RES1 | F_RAW)            \
   X(F_UP | F_RES1 | F_RAW | F_POST)           \
-  X(F_UP | F_RES1 | F_RAW)
+  X(F_UP | F_RES1 | F_RAW)                    \
+  X(F_POST2 | F_PRE | F_RES1 | F_RAW | F_POST) \
+  X(F_POST2 | F_RES1 | F_RAW | F_POST)        \
+  X(F_POOLX | F_PRE | F_RES1 | F_RAW | F_POST) \
+  X(F_POOLX | F_RES1 | F_RAW | F_POST)
 #define MVLM_FLOW_VARIANTS_128(X)     \
   X(F_PRE)                            \
   X(F_RES1 | F_RES2 | F_RAW | F_POST) \
-  X(F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST)
+  X(F_PRE | F_RES1 | F_RES2 | F_RAW | F_POST) \
+  X(F_POOLX | F_RES1 | F_RES2 | F_RAW | F_POST)
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -208,8 +213,8 @@ __device__ __forceinline__ void flow_epilogue(const LayerSm* L, const int mt, co
   const TileCoord tc = {mt, tx, ty, img};
   // image -> slot of each tensor's buffer; the division only runs for ring buffers shorter than the image index
   auto slot = [img](int ring) __attribute__((always_inline)) { return img < ring ? img : img % ring; };
-  const ImageSlots is = {slot(L->ring_pre), slot(L->ring_raw), slot(L->ring_post),
-                         slot(L->ring_res1), slot(L->ring_res2), slot(L->ring_up)};
+  const ImageSlots is = {slot(L->ring_pre), slot(L->ring_raw), slot(L->ring_post), slot(L->ring_res1),
+                         slot(L->ring_res2), slot(L->ring_up), slot(L->ring_aux), slot(L->ring_aux)};
   ArgmaxState am;
   EpiTrace tr;
   tr.trace = trace_row; tr.trace_i = 0; tr.t0 = trace_t0; tr.on = trace_row != nullptr;
@@ -577,7 +582,7 @@ int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, in
       MVLM_REQUIRE(s.in && s.cin % 8 == 0 && (e.out_raw || e.out_post), "flow: bad element-wise layer %d", l);
     }
     reads[l] = {s.in, e.res1, e.res2, e.res_up};
-    writes[l] = {e.out_pre, e.out_raw, e.out_post};
+    writes[l] = {e.out_pre, e.out_raw, e.out_post, e.out_aux1, e.out_aux2};
   }
   auto touches = [](const std::vector<const void*>& a, const std::vector<const void*>& b) {
     for (const void* x : a)
@@ -657,6 +662,7 @@ int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, in
     d.ring_in = std::max(1, g.ring_in); d.ring_pre = std::max(1, g.ring_pre); d.ring_raw = std::max(1, g.ring_raw);
     d.ring_post = std::max(1, g.ring_post); d.ring_res1 = std::max(1, g.ring_res1);
     d.ring_res2 = std::max(1, g.ring_res2); d.ring_up = std::max(1, g.ring_up);
+    d.ring_aux = std::max(1, g.ring_aux);
   }
   void* p = nullptr;
   MVLM_CHECK_CUDA(cudaMalloc(&p, sizeof(LayerSm) * nl));

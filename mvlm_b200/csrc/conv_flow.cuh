@@ -23,7 +23,7 @@
 
 namespace mvlm {
 
-constexpr int kFlowMaxLayers = 20;  // layers per segment (their parameters are staged in shared memory)
+constexpr int kFlowMaxLayers = 18;  // layers per segment (their parameters are staged in shared memory)
 constexpr int kFlowMaxDeps = 10;
 constexpr int kFlowEltRows = 8;  // element-wise items cover 8 px x 8 rows of their output (short items: a long one
                                  // delays every group that waits for its group)
@@ -40,7 +40,7 @@ struct alignas(64) FlowLayer {
   epi::ChannelParams cp;  // never-null per-channel arrays in global memory
   // images held by each tensor's buffer (ring buffers hold fewer than the layer processes): image i lives in
   // slot i % ring
-  int ring_in, ring_pre, ring_raw, ring_post, ring_res1, ring_res2, ring_up;
+  int ring_in, ring_pre, ring_raw, ring_post, ring_res1, ring_res2, ring_up, ring_aux;
 };
 
 // 16-byte work item: x = layer | img << 16, y = mt | tx << 8 | ty << 16, z = group, w = unused

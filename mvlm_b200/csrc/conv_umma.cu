@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
   for (int i = threadIdx.x; i < s.cout_pad; i += kThreads) {
     ep->bias[i] = e.bias ? e.bias[i] : 0.f;
-    ep->mid_s[i] = e.mid_scale ? e.mid_scale[i] : 1.f;
-    ep->mid_t[i] = e.mid_scale ? e.mid_shift[i] : 0.f;
+    ep->mid_s[i] = e.mid_scale ? e.mid_scale[i] : (e.aux_scale ? e.aux_scale[i] : 1.f);  // aux parameters share the slot
+    ep->mid_t[i] = e.mid_scale ? e.mid_shift[i] : (e.aux_shift ? e.aux_shift[i] : 0.f);
     ep->pre_s[i] = e.out_pre ? e.pre_scale[i] : 0.f;
     ep->pre_t[i] = e.out_pre ? e.pre_shift[i] : 0.f;
     ep->post_s[i] = e.out_post ? e.post_scale[i] : 0.f;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     tr.trace = trace; tr.t0 = t_kernel0; tr.on = warp == 2 && lane == 0;
     for (int t = t_begin; t < t_end; t += t_step) {
       const TileCoord tc = decode_tile(p, t);
-      const ImageSlots is = {tc.img, tc.img, tc.img, tc.img, tc.img, tc.img};
+      const ImageSlots is = {tc.img, tc.img, tc.img, tc.img, tc.img, tc.img, tc.img, tc.img};
       tr.trace_i = trace_i;
       epilogue_tile<F, false>(s, e, p.tile_h, cp, tc, is, &bar->t_full[acc], pacc,
                               tmem_base + static_cast<uint32_t>(acc * 256), stage, warp - 2, warp & 3, lane, am, prof, w0,
@@ -407,6 +407,12 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   MVLM_REQUIRE(!e.res_up || (s.h % 2 == 0 && s.w % 2 == 0 && !e.pool2 && !e.out_f32 && !e.argmax_keys),
                "conv_plan: res_up needs even H, W and bf16 outputs");
   MVLM_REQUIRE(!e.mid_scale || (e.mid_shift && !e.out_f32 && !e.argmax_keys), "conv_plan: mid affine needs mid_shift and bf16 outputs");
+  MVLM_REQUIRE(e.aux_mode >= 0 && e.aux_mode <= 2, "conv_plan: unknown aux_mode %d", e.aux_mode);
+  MVLM_REQUIRE(e.aux_mode == 0 || (e.aux_scale && e.aux_shift && e.out_aux1 && !e.mid_scale && !e.pool2 && !e.out_f32 &&
+                                   !e.argmax_keys && e.aux1_cs % 8 == 0),
+               "conv_plan: aux copies need aux_scale / aux_shift / out_aux1 and cannot be combined with mid / pool2 / fp32 outputs");
+  MVLM_REQUIRE(e.aux_mode != 2 || (e.out_aux2 && e.aux2_cs % 8 == 0 && s.h % 2 == 0 && s.w % 2 == 0),
+               "conv_plan: pooled aux copies need out_aux2 and even H, W");
   MVLM_REQUIRE(!((e.argmax_keys || e.out_f32) && (e.res1 || e.res2 || e.out_pre || e.out_raw || e.out_post)),
                "conv_plan: fp32 / arg-max outputs cannot be combined with bf16 outputs or residual inputs");
   // pixel indices are 32-bit (they are widened before the multiplication with a channel stride)
@@ -519,9 +525,7 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   p.prof = g_prof_buf;
   p.debug_mode = g_debug_mode;
   const ConvEpilogue& e = p.e;
-  const int f = (e.out_pre ? F_PRE : 0) | (e.res1 ? F_RES1 : 0) | (e.res2 ? F_RES2 : 0) | (e.out_raw ? F_RAW : 0) |
-                (e.out_post ? F_POST : 0) | (e.out_f32 ? F_F32 : 0) | (e.argmax_keys ? F_ARGMAX : 0) |
-                (e.mid_scale ? F_MID : 0) | (e.pool2 ? F_POOL : 0) | (e.res_up ? F_UP : 0);
+  const int f = feature_mask(e);
   // cout <= 64 layers run the M = 64 variant (conv_plan chose the ring geometry accordingly)
   const bool m64 = p.s.cout_pad <= 64;
 #define MVLM_CASE_BOTH(FLAGS) \
@@ -552,6 +556,12 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
     MVLM_CASE_BOTH(F_UP | F_PRE | F_RES1 | F_RAW);
     MVLM_CASE_BOTH(F_UP | F_RES1 | F_RAW | F_POST);
     MVLM_CASE_BOTH(F_UP | F_RES1 | F_RAW);
+    // producers that also write the copies of a fused BatchNorm+ReLU / max-pool pass (aux_mode 1 / 2)
+    MVLM_CASE_BOTH(F_POST2 | F_PRE | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_BOTH(F_POST2 | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_BOTH(F_POOLX | F_PRE | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_BOTH(F_POOLX | F_RES1 | F_RAW | F_POST);
+    MVLM_CASE_128(F_POOLX | F_RES1 | F_RES2 | F_RAW | F_POST);
   }
 #undef MVLM_CASE_BOTH
 #undef MVLM_CASE_128

@@ -44,6 +44,18 @@ struct ConvEpilogue {
   const float* post_shift = nullptr;
   __nv_bfloat16* out_post = nullptr;
   int post_cs = 0, post_co = 0;
+  // Copies for a second consumer, written next to raw / post (the plan's stand-alone BatchNorm+ReLU and max-pool
+  // passes fused into the producer, paulsenpredictor.py:263-265 and :309-329):
+  //   aux_mode 1: out_aux1 = relu(v*aux_scale+aux_shift) at full resolution (a second act_post)
+  //   aux_mode 2: out_aux1 = 2x2 max-pool of the bf16-rounded raw values, out_aux2 = relu(aux_scale*pooled+aux_shift),
+  //               both at half resolution (needs even H and W); raw / post stay at full resolution
+  int aux_mode = 0;
+  const float* aux_scale = nullptr;
+  const float* aux_shift = nullptr;
+  __nv_bfloat16* out_aux1 = nullptr;
+  int aux1_cs = 0, aux1_co = 0;
+  __nv_bfloat16* out_aux2 = nullptr;
+  int aux2_cs = 0, aux2_co = 0;
   // pool2: out_raw / out_post are written at HALF resolution: the 2x2 max-pool (F.max_pool2d(x, 2),
   // paulsenpredictor.py:411) of the bf16-rounded raw values, and relu(post_bn(pooled)); needs even H and W
   bool pool2 = false;

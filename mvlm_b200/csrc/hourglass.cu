@@ -152,7 +152,7 @@ void HourglassNet::note_use(const void* p) {
 
 void HourglassNet::note_conv(const void* in, const ConvEpilogue& e) {
   note_use(in); note_use(e.out_pre); note_use(e.res1); note_use(e.res2); note_use(e.res_up); note_use(e.out_raw);
-  note_use(e.out_post); note_use(e.argmax_keys);
+  note_use(e.out_post); note_use(e.argmax_keys); note_use(e.out_aux1); note_use(e.out_aux2);
 }
 
 void HourglassNet::assign_offsets() {
@@ -354,7 +354,7 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
 }
 
 int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act,
-                     T* y_out, T* pool_raw, const T* up_low) {
+                     T* y_out, T* pool_raw, const T* up_low, const RbAux* aux) {
   const int h = a_in.h, w = a_in.w;
   T y = alloc(h, w, cout);
   T skip = x;
@@ -373,6 +373,14 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
     *post_act = pool_raw ? alloc(h / 2, w / 2, cout) : alloc(h, w, cout);
   }
   if (pool_raw) *pool_raw = alloc(h / 2, w / 2, cout);
+  // copies for a second consumer written by the three convs' epilogues (conv_umma.cuh, aux_mode)
+  const float *as = nullptr, *at = nullptr;
+  if (aux) {
+    rc = bn(aux->bn, cout, &as, &at);
+    if (rc) return rc;
+    *aux->out1 = aux->mode == 2 ? alloc(h / 2, w / 2, cout) : alloc(h, w, cout);
+    if (aux->mode == 2) *aux->out2 = alloc(h / 2, w / 2, cout);
+  }
   const int c1 = cout / 2, c2 = cout / 4;
   // tightly packed intermediates (a 32-channel a2 in a 64-channel-stride buffer doubles its DRAM traffic); they die
   // with the block, and the packing reuses their memory
@@ -401,6 +409,13 @@ int HourglassNet::rb(const std::string& p, T x, T a_in, T ar, int cin, int cout,
       e.post_shift = dry_ ? nullptr : pt + offs[i];
       e.out_post = post_act->p; e.post_cs = cout; e.post_co = offs[i];
     }
+    if (aux) {
+      e.aux_mode = aux->mode;
+      e.aux_scale = dry_ ? nullptr : as + offs[i];
+      e.aux_shift = dry_ ? nullptr : at + offs[i];
+      e.out_aux1 = aux->out1->p; e.aux1_cs = cout; e.aux1_co = offs[i];
+      if (aux->mode == 2) { e.out_aux2 = aux->out2->p; e.aux2_cs = cout; e.aux2_co = offs[i]; }
+    }
     const int nt = widths[i] < 128 ? widths[i] : 128;
     rc = emit_conv("rb.conv", ins[i], cins[i], p + names[i], widths[i], widths[i], nt, 3, e, false);
     if (rc) return rc;
@@ -423,10 +438,12 @@ int HourglassNet::emit_pool(T in, T out_raw, const char* bn_name, T out_act) {
   return MVLM_OK;
 }
 
-int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
+int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out, const T* in_pooled, const T* in_pooled_act) {
   // HourGlassModule.forward (:301-361).  The skip-branch blocks (rb1, rb3, rb5, rb7, rb9) are scheduled on the way
   // UP, after the low path of their level has returned, so that `F.interpolate(low, 2) + skip` (:334-359) is one
-  // more residual of their epilogues instead of a separate elementwise pass over both tensors.
+  // more residual of their epilogues instead of a separate elementwise pass over both tensors.  The max-pools on
+  // the way DOWN (:309-329) are written by the epilogues of the block that produces their input (aux_mode 2): the
+  // first one by the caller's block (in_pooled / in_pooled_act), the others by this level's down-path block.
   const int F = 256;
   int rc;
   T none;
@@ -434,16 +451,30 @@ int HourglassNet::hourglass(const std::string& p, T x, T a_x, T* out) {
   T cur = x;
   const int low_blocks[5] = {2, 4, 6, 8, 10};
   const int skip_blocks[4] = {3, 5, 7, 9};
+  T pooled, a;
+  if (in_pooled) {
+    pooled = *in_pooled;
+    a = *in_pooled_act;
+  }
   for (int lvl = 0; lvl < 5; ++lvl) {
     const std::string lb = p + ".rb" + std::to_string(low_blocks[lvl]);
-    T pooled = alloc(cur.h / 2, cur.w / 2, F), a = alloc(cur.h / 2, cur.w / 2, F);
-    rc = emit_pool(cur, pooled, (lb + ".bn1").c_str(), a);
-    if (rc) return rc;
+    if (!(fuse_elt_ && (lvl > 0 || in_pooled))) {
+      pooled = alloc(cur.h / 2, cur.w / 2, F);
+      a = alloc(cur.h / 2, cur.w / 2, F);
+      rc = emit_pool(cur, pooled, (lb + ".bn1").c_str(), a);
+      if (rc) return rc;
+    }
     const int nxt = lvl < 4 ? skip_blocks[lvl] : 11;
     const std::string post = p + ".rb" + std::to_string(nxt) + ".bn1";
-    rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_lows[lvl], &lows[lvl]);
+    T next_pooled, next_a;
+    const std::string next_bn = lvl < 4 ? p + ".rb" + std::to_string(low_blocks[lvl + 1]) + ".bn1" : "";
+    RbAux aux = {2, next_bn.c_str(), &next_pooled, &next_a};
+    rc = rb(lb, pooled, a, none, F, F, post.c_str(), &a_lows[lvl], &lows[lvl], nullptr, nullptr,
+            (fuse_elt_ && lvl < 4) ? &aux : nullptr);
     if (rc) return rc;
     cur = lows[lvl];
+    pooled = next_pooled;
+    a = next_a;
   }
   T low2, a2, low3;
   rc = rb(p + ".rb11", cur, a_lows[4], none, F, F, (p + ".rb12.bn1").c_str(), &a2, &low2);
@@ -497,6 +528,11 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   // MVLM_HG_NO_REUSE=1: every buffer does (the round-1 layout, for A/B runs)
   keep_probes_ = getenv("MVLM_HG_KEEP_PROBES") != nullptr && atoi(getenv("MVLM_HG_KEEP_PROBES")) != 0;
   reuse_ = !(getenv("MVLM_HG_NO_REUSE") != nullptr && atoi(getenv("MVLM_HG_NO_REUSE")) != 0);
+  // MVLM_HG_ELT_FUSION=1: the hourglass max-pools and conv4's BatchNorm+ReLU copy are written by their producers'
+  // epilogues (aux_mode) instead of stand-alone passes.  Off by default: measured at 100 views of 256^2 the eleven
+  // passes it removes cost 0.58 ms (they run at 94 % of the HBM peak) and the producers, which are epilogue-bound, get
+  // 0.65 ms slower (conv7 0.85 -> 1.11 ms): 18.23 against 18.11 ms per scan (profiles/r2_elt_fusion.txt)
+  fuse_elt_ = getenv("MVLM_HG_ELT_FUSION") != nullptr && atoi(getenv("MVLM_HG_ELT_FUSION")) != 0;
   // layout pass: lifetimes and packed offsets
   bufs_.clear(); fake_off_ = 0; ws_needed_ = 0; next_buf_ = 0;
   dry_ = true; layout_pass_ = true;
@@ -573,10 +609,15 @@ int HourglassNet::emit() {
   T x1;
   if ((rc = rb("conv2", none, a_c2, ar_c2, 64, 128, "conv3.bn1", &a3, &y2, &x1))) return rc;
   probe("x1", x1);
-  if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3))) return rc;
-  probe("y3", y3);
-  ar4 = alloc(h2, w2, 128);
-  {
+  if (fuse_elt_) {
+    // conv4's resample branch reads relu(bn(y3)) (:263-265): a second act copy from the conv3 block's epilogues
+    RbAux aux = {1, "conv4.resample.0", &ar4, nullptr};
+    if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3, nullptr, nullptr, &aux))) return rc;
+    probe("y3", y3);
+  } else {
+    if ((rc = rb("conv3", x1, a3, none, 128, 128, "conv4.bn1", &a4, &y3))) return rc;
+    probe("y3", y3);
+    ar4 = alloc(h2, w2, 128);
     note_use(y3.p); note_use(ar4.p);
     NetOp op;
     op.kind = NetOp::BNRELU;
@@ -584,11 +625,14 @@ int HourglassNet::emit() {
     if ((rc = bn("conv4.resample.0", 128, &op.scale, &op.shift))) return rc;
     push_op(op);
   }
-  if ((rc = rb("conv4", y3, a4, ar4, 128, F, "hg1.rb1.bn1", &a_h1, &r3))) return rc;
+  // the first max-pool of each hourglass (:309) is written by the block that produces its input: conv4 / conv7
+  T p1, pa1, p2, pa2;
+  RbAux aux4 = {2, "hg1.rb2.bn1", &p1, &pa1};
+  if ((rc = rb("conv4", y3, a4, ar4, 128, F, "hg1.rb1.bn1", &a_h1, &r3, nullptr, nullptr, fuse_elt_ ? &aux4 : nullptr))) return rc;
   probe("r3", r3);
   // ---- hourglass 1 (:414), conv5+bn2+relu (:416), conv6 (:417), conv7 + sum (:420-422)
   T hg1;
-  if ((rc = hourglass("hg1", r3, a_h1, &hg1))) return rc;
+  if ((rc = hourglass("hg1", r3, a_h1, &hg1, fuse_elt_ ? &p1 : nullptr, fuse_elt_ ? &pa1 : nullptr))) return rc;
   probe("hg1", hg1);
   T ll1 = alloc(h2, w2, F);
   {
@@ -612,12 +656,20 @@ int HourglassNet::emit() {
     a_h2 = alloc(h2, w2, F);
     if ((rc = bn("hg2.rb1.bn1", F, &e.post_scale, &e.post_shift))) return rc;
     e.out_post = a_h2.p; e.post_cs = F; e.post_co = 0;
+    if (fuse_elt_) {
+      p2 = alloc(h2 / 2, w2 / 2, F);
+      pa2 = alloc(h2 / 2, w2 / 2, F);
+      if ((rc = bn("hg2.rb2.bn1", F, &e.aux_scale, &e.aux_shift))) return rc;
+      e.aux_mode = 2;
+      e.out_aux1 = p2.p; e.aux1_cs = F; e.aux1_co = 0;
+      e.out_aux2 = pa2.p; e.aux2_cs = F; e.aux2_co = 0;
+    }
     if ((rc = emit_conv("conv7", x6, Lp_, "conv7", F, F, 128, 3, e, true))) return rc;
   }
   probe("sum_temp", sum);
   // ---- hourglass 2 (:424), conv9+bn3+relu (:426), conv10 (:427)
   T hg2;
-  if ((rc = hourglass("hg2", sum, a_h2, &hg2))) return rc;
+  if ((rc = hourglass("hg2", sum, a_h2, &hg2, fuse_elt_ ? &p2 : nullptr, fuse_elt_ ? &pa2 : nullptr))) return rc;
   T ll2 = alloc(h2, w2, F);
   {
     ConvEpilogue e;
@@ -709,7 +761,7 @@ int HourglassNet::build_segments() {
       FlowLayerDesc d;
       memset(&d.layer, 0, sizeof(d.layer));
       FlowLayer& L = d.layer;
-      L.ring_in = L.ring_pre = L.ring_raw = L.ring_post = L.ring_res1 = L.ring_res2 = L.ring_up = V_;
+      L.ring_in = L.ring_pre = L.ring_raw = L.ring_post = L.ring_res1 = L.ring_res2 = L.ring_up = L.ring_aux = V_;
       L.cp = {zeros_, ones_, zeros_, zeros_, zeros_, zeros_, zeros_};
       if (op.kind == NetOp::CONV) {
         MVLM_REQUIRE(!op.is_head, "hourglass: head conv inside a dataflow segment");
@@ -721,6 +773,7 @@ int HourglassNet::build_segments() {
         if (e.mid_scale) { L.cp.mid_s = e.mid_scale; L.cp.mid_t = e.mid_shift; }
         if (e.out_pre) { L.cp.pre_s = e.pre_scale; L.cp.pre_t = e.pre_shift; }
         if (e.out_post) { L.cp.post_s = e.post_scale; L.cp.post_t = e.post_shift; }
+        if (e.aux_mode) { L.cp.mid_s = e.aux_scale; L.cp.mid_t = e.aux_shift; }
         d.tiles_x = op.conv.tiles_x; d.tiles_y = op.conv.tiles_y; d.n_nt = op.conv.n_nt;
         min_tiles = std::min(min_tiles, d.tiles_x * d.tiles_y * d.n_nt);
       } else if (op.kind == NetOp::POOL || op.kind == NetOp::BNRELU) {
@@ -921,7 +974,8 @@ std::string HourglassNet::describe_op(int i) const {
       const ConvEpilogue& e = op.conv.e;
       snprintf(buf, sizeof(buf), "%sconv %s %dx%d %d->%d k%d%s%s%s%s%s%s%s%s", in_seg, op.tag, s.h, s.w, s.cin, s.cout_pad, s.kh,
                e.out_pre ? " pre" : "", e.res1 ? " res1" : "", e.res2 ? " res2" : "", e.res_up ? " up" : "", e.out_raw ? " raw" : "",
-               e.out_post ? " post" : "", e.pool2 ? " pool" : "", e.argmax_keys ? " argmax" : "");
+               e.out_post ? " post" : "", e.pool2 ? " pool" : (e.aux_mode == 2 ? " +pooled" : (e.aux_mode == 1 ? " +act2" : "")),
+               e.argmax_keys ? " argmax" : "");
       break;
     }
     case NetOp::POOL: snprintf(buf, sizeof(buf), "%spool %dx%dx%d", in_seg, op.h, op.w, op.c); break;

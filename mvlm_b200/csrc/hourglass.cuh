@@ -97,7 +97,7 @@ class HourglassNet {
   void probe(const char* name, const T& t);
   std::vector<Buf> bufs_;
   size_t fake_off_ = 0, ws_needed_ = 0, next_buf_ = 0;
-  bool layout_pass_ = false, keep_probes_ = false, reuse_ = true;
+  bool layout_pass_ = false, keep_probes_ = false, reuse_ = true, fuse_elt_ = false;
   int bn(const std::string& name, int c, const float** scale, const float** shift);
   int packed(const std::string& name, int cout, int cin, int k, int cout_pad, int cin_pad, const __nv_bfloat16** out);
   int bias(const std::string& name, int cout, int cout_pad, const float** out);
@@ -107,9 +107,12 @@ class HourglassNet {
   // the three convs write the pooled raw tensor and relu(post_bn(pooled)) directly; no full-resolution output
   // up_low != nullptr: the nearest-x2 up-sampled half-resolution tensor is added to the block output
   // (hourglass up path, :334-359)
+  // aux: copies of the block output for a second consumer, written by the block's own epilogues (ConvEpilogue::aux_mode):
+  // mode 1 = relu(bn(y)) at full resolution -> *out1; mode 2 = max-pool(y) -> *out1 and relu(bn(max-pool(y))) -> *out2
+  struct RbAux { int mode; const char* bn; T* out1; T* out2; };
   int rb(const std::string& p, T x, T a_in, T ar, int cin, int cout, const char* post_bn, T* post_act, T* y_out,
-         T* pool_raw = nullptr, const T* up_low = nullptr);
-  int hourglass(const std::string& p, T x, T a_x, T* out);
+         T* pool_raw = nullptr, const T* up_low = nullptr, const RbAux* aux = nullptr);
+  int hourglass(const std::string& p, T x, T a_x, T* out, const T* in_pooled = nullptr, const T* in_pooled_act = nullptr);
   int emit_pool(T in, T out_raw, const char* bn_name, T out_act);
 
   // ---- dataflow segments (conv_flow.cuh): runs of consecutive ops executed by ONE persistent launch over view

@@ -88,3 +88,33 @@ def test_workspace_packing_is_bit_identical_and_small(lib):
         assert torch.equal(hm0.view(torch.int32), hm1.view(torch.int32))
     with pytest.raises(Exception):
         packed.probe("r3")
+
+
+@pytest.mark.parametrize("n_landmarks,mode,size,views", [(73, "RGB+depth", 128, 3), (84, "geometry+depth", 64, 2),
+                                                        (73, "RGB", 256, 2)])
+def test_fused_pool_and_act_copies_equal_standalone_passes(lib, n_landmarks, mode, size, views):
+    """The hourglass max-pools (paulsenpredictor.py:309-329) and the BatchNorm+ReLU copy of conv4's resample branch
+    (:263-265) written by their producers' epilogues (ConvEpilogue::aux_mode, opt-in: it is not faster) == the stand-alone
+    pool2_act / bn_relu passes of the default plan: every probe tensor, the heat maps and the peaks bit-identical."""
+    sd = seeded_state_dict(n_landmarks, mode, seed=77)
+    cin = IMAGE_CHANNELS[mode]
+    g = torch.Generator().manual_seed(13)
+    img = torch.randint(0, 256, (views, size, size, 4), generator=g, dtype=torch.uint8)
+    img[..., cin:] = 0
+    img = img.cuda()
+    args = (sd, n_landmarks, cin, views, size, size)
+    unfused = _build({"MVLM_HG_ELT_FUSION": "0"}, *args)
+    fused = _build({"MVLM_HG_ELT_FUSION": "1"}, *args)
+    assert fused.num_launches == unfused.num_launches - 11   # ten max-pools and one BatchNorm+ReLU pass are gone
+    pk0, hm0 = unfused.forward(img, want_heatmaps=True)
+    pk1, hm1 = fused.forward(img, want_heatmaps=True)
+    torch.cuda.synchronize()
+    for name in PROBES:
+        assert torch.equal(unfused.probe(name).view(torch.int16), fused.probe(name).view(torch.int16)), name
+    assert torch.equal(hm0.view(torch.int32), hm1.view(torch.int32))
+    assert torch.equal(pk0.view(torch.int32), pk1.view(torch.int32))
+    # the dataflow kernel runs the same variants (low levels in segments)
+    flow = _build({"MVLM_HG_ELT_FUSION": "1", "MVLM_FLOW": "1", "MVLM_FLOW_LO": "1", "MVLM_FLOW_HI": "32"}, *args)
+    pk2, hm2 = flow.forward(img, want_heatmaps=True)
+    torch.cuda.synchronize()
+    assert torch.equal(hm0.view(torch.int32), hm2.view(torch.int32)) and torch.equal(pk0.view(torch.int32), pk2.view(torch.int32))
