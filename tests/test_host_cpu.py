@@ -221,3 +221,54 @@ def test_pre_align_transform_matches_vtk_call_order():
     assert not prealign.is_identity({"align_center_of_mass": True})
     with pytest.raises(ValueError):
         prealign.affine(verts, {"rot_w": 1})
+
+
+def test_obj_loader_cases_documented_from_vtkobjreader(tmp_path):
+    """Scan files as vtkOBJReader / obj_to_actor (utils3d.py:10-36) treat them, checked against HAND-WRITTEN per-corner
+    arrays (independent of oracle/obj_ref.py, which restates the same rules): statements other than v / vt / f are
+    ignored (o, g, s, usemtl, mtllib, vn, comments); polygons become a triangle fan in corner order; a position used
+    with different vt indices appears once per (position, vt) pair so that the texture seam survives; a file whose faces
+    carry no vt loads without texture coordinates."""
+    text = """# exported by a scanner
+mtllib scan.mtl
+o head
+v 0 0 0
+v 2 0 0
+v 2 2 0
+v 0 2 0
+v 1 1 5
+vn 0 0 1
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vt 0.25 0.75
+g front
+usemtl skin
+s 1
+f 1/1/1 2/2/1 3/3/1 4/4/1
+g seam
+s off
+f 1/5 5/3 2/2
+"""
+    (tmp_path / "s.obj").write_text(text)
+    m = load_obj(tmp_path / "s.obj")
+    want_pos = np.array([[[0, 0, 0], [2, 0, 0], [2, 2, 0]],      # fan of the quad: (c0, c1, c2), (c0, c2, c3)
+                         [[0, 0, 0], [2, 2, 0], [0, 2, 0]],
+                         [[0, 0, 0], [1, 1, 5], [2, 0, 0]]], np.float32)
+    want_uv = np.array([[[0, 0], [1, 0], [1, 1]],
+                        [[0, 0], [1, 1], [0, 1]],
+                        [[0.25, 0.75], [1, 1], [1, 0]]], np.float32)
+    assert m.tris.shape == (3, 3) and m.tris.dtype == np.int32
+    assert np.array_equal(m.verts[m.tris], want_pos) and np.array_equal(m.uvs[m.tris], want_uv)
+    # position 1 carries vt 1 and vt 5 -> two vertices; position 3 carries vt 3 twice (both faces) -> one; 6 in total
+    assert m.verts.shape == (6, 3) and m.uvs.shape == (6, 2)
+    assert m.texture is None                                            # no s.jpg next to it: plain white actor (:61-64)
+    # a file whose faces carry no vt at all: no texture coordinates, even if vt lines exist
+    (tmp_path / "n.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 1\nusemtl m\nf 1 2 3\n")
+    n = load_obj(tmp_path / "n.obj")
+    assert n.uvs is None and n.verts.shape == (3, 3) and n.tris.tolist() == [[0, 1, 2]]
+    # a pentagon: fan of three triangles in corner order
+    (tmp_path / "p.obj").write_text("v 0 0 0\nv 1 0 0\nv 2 1 0\nv 1 2 0\nv 0 1 0\nf 1 2 3 4 5\n")
+    p = load_obj(tmp_path / "p.obj")
+    assert p.tris.tolist() == [[0, 1, 2], [0, 2, 3], [0, 3, 4]]
