@@ -690,7 +690,7 @@ int flow_build_segment(const std::vector<FlowLayerDesc>& layers, int n_views, in
 }
 
 namespace {
-long long* g_flow_prof = nullptr;
+thread_local long long* g_flow_prof = nullptr;
 // experiment switches (MVLM_FLOW_DEBUG): 1 = no dependency waits / no publication (timing only, results invalid),
 // 2 = red.release instead of fence + atomicAdd
 const int g_flow_debug = getenv("MVLM_FLOW_DEBUG") ? atoi(getenv("MVLM_FLOW_DEBUG")) : 0;

@@ -387,8 +387,9 @@ int launch_t(const ConvParams& p, cudaStream_t stream) {
   return MVLM_OK;
 }
 
-long long* g_prof_buf = nullptr;
-int g_debug_mode = 0;
+// debug hooks: set and read on the thread that profiles (thread-local: other threads' launches are unaffected)
+thread_local long long* g_prof_buf = nullptr;
+thread_local int g_debug_mode = 0;
 
 }  // namespace
 

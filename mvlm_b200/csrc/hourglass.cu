@@ -258,6 +258,15 @@ HourglassNet::T HourglassNet::alloc(int h, int w, int c) {
   return t;
 }
 
+// Device memory for the plan's parameters (packed bf16 weights, folded BatchNorm affines, padded biases): sized in the
+// layout pass, ONE cudaMalloc for the real pass (round 1 made 271 allocations and as many NULL-stream launches per plan).
+void* HourglassNet::param_alloc(size_t bytes) {
+  const size_t aligned = (bytes + 255) & ~static_cast<size_t>(255);
+  void* p = (layout_pass_ || params_ == nullptr || param_off_ + aligned > param_cap_) ? nullptr : params_ + param_off_;
+  param_off_ += aligned;
+  return p;
+}
+
 int HourglassNet::sd_get(const std::string& name, long long numel, const float** out) const {
   auto f = sd_->find(name);
   MVLM_REQUIRE(f != sd_->end(), "hourglass: missing state_dict key %s", name.c_str());
@@ -271,7 +280,10 @@ int HourglassNet::sd_get(const std::string& name, long long numel, const float**
 
 int HourglassNet::bn(const std::string& name, int c, const float** scale, const float** shift) {
   *scale = *shift = nullptr;
-  if (dry_) return MVLM_OK;
+  if (dry_) {
+    if (layout_pass_ && bn_seen_.insert(name).second) param_alloc(sizeof(float) * 2 * c);
+    return MVLM_OK;
+  }
   auto it = bn_cache_.find(name);
   if (it == bn_cache_.end()) {
     const char* suffix[4] = {".weight", ".bias", ".running_mean", ".running_var"};
@@ -280,10 +292,9 @@ int HourglassNet::bn(const std::string& name, int c, const float** scale, const 
       const int rc = sd_get(name + suffix[k], c, &src[k]);
       if (rc) return rc;
     }
-    float* buf = nullptr;
-    MVLM_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * 2 * c));
-    owned_.push_back(buf);
-    fold_bn_kernel<<<ceil_div(c, 128), 128>>>(src[0], src[1], src[2], src[3], 1e-5f, c, buf, buf + c);
+    float* buf = static_cast<float*>(param_alloc(sizeof(float) * 2 * c));
+    MVLM_REQUIRE(buf, "hourglass: parameter arena exhausted (%s)", name.c_str());
+    fold_bn_kernel<<<ceil_div(c, 128), 128, 0, build_stream_>>>(src[0], src[1], src[2], src[3], 1e-5f, c, buf, buf + c);
     MVLM_CHECK_CUDA(cudaGetLastError());
     it = bn_cache_.emplace(name, std::make_pair(buf, buf + c)).first;
   }
@@ -295,15 +306,17 @@ int HourglassNet::bn(const std::string& name, int c, const float** scale, const 
 int HourglassNet::packed(const std::string& name, int cout, int cin, int k, int cout_pad, int cin_pad,
                          const __nv_bfloat16** out) {
   *out = nullptr;
-  if (dry_) return MVLM_OK;
+  const size_t n = static_cast<size_t>(cout_pad) * k * k * cin_pad;
+  if (dry_) {
+    if (layout_pass_) param_alloc(n * sizeof(__nv_bfloat16));
+    return MVLM_OK;
+  }
   const float* src = nullptr;
   const int rc = sd_get(name, 1ll * cout * cin * k * k, &src);
   if (rc) return rc;
-  __nv_bfloat16* buf = nullptr;
-  const size_t n = static_cast<size_t>(cout_pad) * k * k * cin_pad;
-  MVLM_CHECK_CUDA(cudaMalloc(&buf, n * sizeof(__nv_bfloat16)));
-  owned_.push_back(buf);
-  pack_weight_kernel<<<256, 256>>>(src, cout, cin, k, cout_pad, cin_pad, buf);
+  __nv_bfloat16* buf = static_cast<__nv_bfloat16*>(param_alloc(n * sizeof(__nv_bfloat16)));
+  MVLM_REQUIRE(buf, "hourglass: parameter arena exhausted (%s)", name.c_str());
+  pack_weight_kernel<<<256, 256, 0, build_stream_>>>(src, cout, cin, k, cout_pad, cin_pad, buf);
   MVLM_CHECK_CUDA(cudaGetLastError());
   *out = buf;
   return MVLM_OK;
@@ -311,14 +324,16 @@ int HourglassNet::packed(const std::string& name, int cout, int cin, int k, int 
 
 int HourglassNet::bias(const std::string& name, int cout, int cout_pad, const float** out) {
   *out = nullptr;
-  if (dry_) return MVLM_OK;
+  if (dry_) {
+    if (layout_pass_) param_alloc(sizeof(float) * cout_pad);
+    return MVLM_OK;
+  }
   const float* src = nullptr;
   const int rc = sd_get(name, cout, &src);
   if (rc) return rc;
-  float* buf = nullptr;
-  MVLM_CHECK_CUDA(cudaMalloc(&buf, sizeof(float) * cout_pad));
-  owned_.push_back(buf);
-  pad_bias_kernel<<<ceil_div(cout_pad, 128), 128>>>(src, cout, cout_pad, buf);
+  float* buf = static_cast<float*>(param_alloc(sizeof(float) * cout_pad));
+  MVLM_REQUIRE(buf, "hourglass: parameter arena exhausted (%s)", name.c_str());
+  pad_bias_kernel<<<ceil_div(cout_pad, 128), 128, 0, build_stream_>>>(src, cout, cout_pad, buf);
   MVLM_CHECK_CUDA(cudaGetLastError());
   *out = buf;
   return MVLM_OK;
@@ -334,6 +349,12 @@ int HourglassNet::emit_conv(const char* tag, T in, int cin, const std::string& w
   op.kind = NetOp::CONV;
   op.tag = tag;
   op.h = in.h; op.w = in.w;
+  if (layout_pass_) {  // parameter bytes of this layer (packed weights, bias), allocated by the real pass below
+    const __nv_bfloat16* dw;
+    const float* db;
+    packed(wname + ".weight", cout, cin_real, k, cout_pad, cin, &dw);
+    if (with_bias) bias(wname + ".bias", cout, cout_pad, &db);
+  }
   if (!dry_) {
     ConvShape s;
     s.in = in.p; s.n = V_; s.h = in.h; s.w = in.w; s.cin = cin; s.in_cs = in.c;
@@ -535,6 +556,7 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   fuse_elt_ = getenv("MVLM_HG_ELT_FUSION") != nullptr && atoi(getenv("MVLM_HG_ELT_FUSION")) != 0;
   // layout pass: lifetimes and packed offsets
   bufs_.clear(); fake_off_ = 0; ws_needed_ = 0; next_buf_ = 0;
+  param_off_ = 0; bn_seen_.clear();
   dry_ = true; layout_pass_ = true;
   int rc = emit();
   layout_pass_ = false;
@@ -542,10 +564,26 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   assign_offsets();
   if (dry) return MVLM_OK;
   MVLM_REQUIRE(ws_needed_ <= ws_size_, "hourglass: workspace too small (%zu needed, %zu given)", ws_needed_, ws_size_);
+  // real pass: one arena for every parameter tensor, repacking kernels on a private stream (the state_dict tensors must
+  // be complete when this is called: mvlm_b200/ops.py synchronises its stream before mvlm_hourglass_create)
+  const size_t param_bytes = param_off_ + 4096;
+  MVLM_CHECK_CUDA(cudaMalloc(&params_, param_bytes));
+  owned_.push_back(params_);
+  param_cap_ = param_bytes;
+  param_off_ = 0;
+  MVLM_CHECK_CUDA(cudaStreamCreateWithFlags(&build_stream_, cudaStreamNonBlocking));
   dry_ = false;
-  if ((rc = emit())) return rc;
-  if ((rc = build_segments())) return rc;
-  MVLM_CHECK_CUDA(cudaDeviceSynchronize());
+  rc = emit();
+  if (rc == MVLM_OK && param_off_ > param_bytes) {
+    set_error("hourglass: parameter arena overrun (%zu of %zu bytes)", param_off_, param_bytes);
+    rc = MVLM_E_INVALID;
+  }
+  if (rc == MVLM_OK) rc = build_segments();
+  const cudaError_t ce = cudaStreamSynchronize(build_stream_);
+  cudaStreamDestroy(build_stream_);
+  build_stream_ = nullptr;
+  if (rc) return rc;
+  MVLM_CHECK_CUDA(ce);
   return MVLM_OK;
 }
 
@@ -582,13 +620,20 @@ int HourglassNet::emit() {
     cv.kind = NetOp::CONV;
     cv.tag = "conv1";
     cv.h = h; cv.w = w;
+    if (layout_pass_) {  // what the real pass allocates in this block, in the same order
+      param_alloc(sizeof(__nv_bfloat16) * 64 * 9 * 16);
+      const float* dummy;
+      bias("conv1.bias", 64, 64, &dummy);
+      bn("bn1", 64, &dummy, &dummy);
+      bn("conv2.bn1", 64, &dummy, &dummy);
+      bn("conv2.resample.0", 64, &dummy, &dummy);
+    }
     if (!dry_) {
       const float* w1 = nullptr;
       if ((rc = sd_get("conv1.weight", 64ll * cin * 9, &w1))) return rc;
-      __nv_bfloat16* wp = nullptr;
-      MVLM_CHECK_CUDA(cudaMalloc(&wp, sizeof(__nv_bfloat16) * 64 * 9 * 16));
-      owned_.push_back(wp);
-      pack_stem_weight_kernel<<<36, 256>>>(w1, 64, cin, 64, wp);
+      __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(param_alloc(sizeof(__nv_bfloat16) * 64 * 9 * 16));
+      MVLM_REQUIRE(wp, "hourglass: parameter arena exhausted (conv1)");
+      pack_stem_weight_kernel<<<36, 256, 0, build_stream_>>>(w1, 64, cin, 64, wp);
       MVLM_CHECK_CUDA(cudaGetLastError());
       ConvShape s;
       s.in = img16.p; s.n = V_; s.h = h; s.w = w; s.cin = 16; s.in_cs = 16;
@@ -706,13 +751,13 @@ int HourglassNet::emit() {
       op.is_head = true;
       op.tag = "conv11.phase";
       op.h = h2; op.w = w2;
+      if (layout_pass_) param_alloc(sizeof(__nv_bfloat16) * Lp_ * 4 * Lp_);
       if (!dry_) {
         const float* w11 = nullptr;
         if ((rc = sd_get("conv11.weight", 9ll * L_ * L_, &w11))) return rc;
-        __nv_bfloat16* wp = nullptr;
-        MVLM_CHECK_CUDA(cudaMalloc(&wp, sizeof(__nv_bfloat16) * Lp_ * 4 * Lp_));
-        owned_.push_back(wp);
-        pack_phase_weight_kernel<<<64, 256>>>(w11, L_, L_, a, b, Lp_, Lp_, wp);
+        __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(param_alloc(sizeof(__nv_bfloat16) * Lp_ * 4 * Lp_));
+        MVLM_REQUIRE(wp, "hourglass: parameter arena exhausted (conv11)");
+        pack_phase_weight_kernel<<<64, 256, 0, build_stream_>>>(w11, L_, L_, a, b, Lp_, Lp_, wp);
         MVLM_CHECK_CUDA(cudaGetLastError());
         phase_w_[2 * a + b] = wp;
         ConvShape s;
@@ -999,7 +1044,10 @@ int HourglassNet::forward_graph(const unsigned char* img_u8, const float* img_f3
   // first call with these buffers: warm every kernel attribute outside capture, then capture
   int rc = forward(img_u8, img_f32, out_heatmaps, out_peaks, stream);
   if (rc != MVLM_OK) return rc;
-  if (graphs_.size() >= 8) return MVLM_OK;  // too many distinct buffer sets: stay on plain launches
+  if (graphs_.size() >= kMaxGraphs) {  // many distinct buffer sets: the oldest graph makes room (never a silent fallback)
+    cudaGraphExecDestroy(graphs_.front().second);
+    graphs_.erase(graphs_.begin());
+  }
   cudaGraph_t graph = nullptr;
   if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();

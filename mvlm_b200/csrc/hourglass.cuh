@@ -1,6 +1,7 @@
 // Stacked-hourglass heat-map CNN plan: the whole network as a static list of fused launches.
 #pragma once
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -95,6 +96,12 @@ class HourglassNet {
   void note_conv(const void* in, const ConvEpilogue& e);
   void assign_offsets();
   void probe(const char* name, const T& t);
+  void* param_alloc(size_t bytes);
+  unsigned char* params_ = nullptr;  // one arena for packed weights / folded BatchNorm affines / biases
+  size_t param_off_ = 0, param_cap_ = 0;
+  std::set<std::string> bn_seen_;
+  cudaStream_t build_stream_ = nullptr;  // plan-build kernels (weight repacking) run here, not on the NULL stream
+  static constexpr size_t kMaxGraphs = 8;
   std::vector<Buf> bufs_;
   size_t fake_off_ = 0, ws_needed_ = 0, next_buf_ = 0;
   bool layout_pass_ = false, keep_probes_ = false, reuse_ = true, fuse_elt_ = false;

@@ -161,6 +161,8 @@ class Hourglass:
         arr_p = (C.c_void_p * len(names))(*[self._sd[n].data_ptr() for n in names])
         arr_k = (C.c_longlong * len(names))(*[self._sd[n].numel() for n in names])
         handle = C.c_void_p()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()  # the library repacks the weights on a stream of its own
         check(lib.mvlm_hourglass_create(arr_n, arr_p, arr_k, len(names), n_landmarks, cin, n_views, h, w,
                                         self.workspace.data_ptr(), nbytes, C.byref(handle)), "mvlm_hourglass_create")
         self._h = handle
