@@ -98,64 +98,6 @@ def allgather_bytes(array: np.ndarray, device, stage=None, name: str = "a", grou
     return recv[:raw.size].view(torch.from_numpy(a[:0].reshape(-1).copy()).dtype).view(a.shape)
 
 
-def _parallel_copy(dst: np.ndarray, src: np.ndarray) -> None:
-    """Host copy into the pinned staging buffer; pieces of several MB are split over the renderer's copy threads (one
-    core moves ~6 GB/s, and the copy is on the critical path of the view-split call)."""
-    from .utils.render3d import _COPY_THREADS, _PARALLEL_COPY_BYTES, _copy_pool
-
-    if src.nbytes < _PARALLEL_COPY_BYTES:
-        np.copyto(dst, src)
-        return
-    edges = np.linspace(0, src.size, _COPY_THREADS + 1).astype(np.int64)
-    list(_copy_pool().map(lambda i: np.copyto(dst[edges[i]:edges[i + 1]], src[edges[i]:edges[i + 1]]), range(_COPY_THREADS)))
-
-
-def allgather_arrays(arrays, device, stage=None, group=None) -> list:
-    """Several arrays every rank holds in host memory -> device tensors of all of them with ONE host -> device copy of
-    1/world of their concatenated bytes per rank and ONE all-gather (allgather_bytes does this per array: four
-    collectives and four copies per scan).  Arrays start at 256-byte offsets of the stream; None entries stay None."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    raws, offs, total = [], [], 0
-    for a in arrays:
-        if a is None:
-            raws.append(None)
-            offs.append(None)
-            continue
-        r = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
-        raws.append(r)
-        offs.append(total)
-        total += (r.size + 255) // 256 * 256
-    chunk = (-(-total // world) + 255) // 256 * 256
-    lo, hi = rank * chunk, (rank + 1) * chunk
-    use_pinned = stage is not None and torch.device(device).type == "cuda"
-    if use_pinned:
-        b = stage.buf.get("packed@shard")
-        if b is None or b.numel() < chunk:
-            b = stage.buf["packed@shard"] = torch.empty((chunk,), dtype=torch.uint8, pin_memory=True)
-        host = b[:chunk]
-    else:
-        host = torch.zeros((chunk,), dtype=torch.uint8)
-    hv = host.numpy()
-    for r, o in zip(raws, offs):  # the pieces of every array that fall into this rank's byte range
-        if r is None:
-            continue
-        a0, a1 = max(lo, o), min(hi, o + r.size)
-        if a1 > a0:
-            _parallel_copy(hv[a0 - lo:a1 - lo], r[a0 - o:a1 - o])
-    recv = torch.empty((world * chunk,), dtype=torch.uint8, device=device)
-    send = recv[rank * chunk:(rank + 1) * chunk]
-    send.copy_(host, non_blocking=use_pinned)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    out = []
-    for a, r, o in zip(arrays, raws, offs):
-        if a is None:
-            out.append(None)
-            continue
-        a = np.asarray(a)
-        out.append(recv[o:o + r.size].view(torch.from_numpy(a.reshape(-1)[:0].copy()).dtype).view(a.shape))
-    return out
-
-
 def upload_mesh_sharded(renderer, mesh, group=None):
     """DeviceMesh of a scan every rank holds in host memory, each rank uploading 1/world of it (allgather_bytes)."""
     from .utils.render3d import DeviceMesh, _PinnedStage
@@ -175,9 +117,11 @@ def upload_mesh_sharded(renderer, mesh, group=None):
         if tex.is_cuda:
             tex.record_stream(torch.cuda.current_stream())  # decoded on a loader stream: keep its memory until we are done
         tex_d = tex
-        verts, tris, uvs = allgather_arrays([mesh.verts, mesh.tris, mesh.uvs], device, stage, group)
     else:
-        verts, tris, uvs, tex_d = allgather_arrays([mesh.verts, mesh.tris, mesh.uvs, tex], device, stage, group)
+        tex_d = None if tex is None else allgather_bytes(tex, device, stage, "tex", group)
+    verts = allgather_bytes(mesh.verts, device, stage, "verts", group)
+    tris = allgather_bytes(mesh.tris, device, stage, "tris", group)
+    uvs = None if mesh.uvs is None else allgather_bytes(mesh.uvs, device, stage, "uvs", group)
     if stage is not None:
         stage.done = torch.cuda.Event()
         stage.done.record()
