@@ -121,13 +121,14 @@ __global__ void __launch_bounds__(256) raster_tris_kernel(const float4* __restri
 // views view0 .. view0 + n_chunk - 1 (sv holds the transformed vertices of exactly these views)
 __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g, const float4* __restrict__ sv, int view0,
                                                              int n_chunk) {
-  const size_t total = static_cast<size_t>(n_chunk) * g.h * g.w;
-  const size_t lpix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (lpix >= total) return;
-  const size_t pix = lpix + static_cast<size_t>(view0) * g.h * g.w;
-  const int px = static_cast<int>(pix % g.w);
-  const int py = static_cast<int>((pix / g.w) % g.h);
-  const int view = static_cast<int>(pix / (static_cast<size_t>(g.w) * g.h));
+  // grid = (pixel blocks of one view, views of the chunk): 32-bit index arithmetic (three 64-bit divisions per pixel
+  // were a large part of this kernel's 275 instructions per pixel)
+  const unsigned int vp = blockIdx.x * blockDim.x + threadIdx.x;  // pixel within the view
+  if (vp >= static_cast<unsigned int>(g.h * g.w) || static_cast<int>(blockIdx.y) >= n_chunk) return;
+  const int view = view0 + static_cast<int>(blockIdx.y);
+  const int py = static_cast<int>(vp / static_cast<unsigned int>(g.w));
+  const int px = static_cast<int>(vp - static_cast<unsigned int>(py) * static_cast<unsigned int>(g.w));
+  const size_t pix = static_cast<size_t>(view) * g.h * g.w + vp;
   const unsigned long long key = g.zbuf[pix];
   float r = 1.0f, gr = 1.0f, bl = 1.0f, zval = 1.0f, geo = 1.0f;
   unsigned char r8 = 255, g8 = 255, b8 = 255, geo8 = 255;
@@ -150,8 +151,9 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g, const
       const float v = (l0 * g.uvs[2 * i0 + 1] + l1 * g.uvs[2 * i1 + 1]) + l2 * g.uvs[2 * i2 + 1];
       int tx = static_cast<int>(floorf(u * static_cast<float>(g.tw)));
       int ty = static_cast<int>(floorf(v * static_cast<float>(g.th)));
-      tx %= g.tw; if (tx < 0) tx += g.tw;
-      ty %= g.th; if (ty < 0) ty += g.th;
+      // repeat wrap; texture coordinates inside [0, 1) (the usual case) skip the two integer divisions
+      if (tx < 0 || tx >= g.tw) { tx %= g.tw; if (tx < 0) tx += g.tw; }
+      if (ty < 0 || ty >= g.th) { ty %= g.th; if (ty < 0) ty += g.th; }
       const size_t ti = static_cast<size_t>(g.th - 1 - ty) * g.tw + tx;
       if (g.tex_c == 4) {  // RGBA texture: one 4-byte load per texel
         const uchar4 q4 = __ldg(reinterpret_cast<const uchar4*>(g.tex) + ti);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g, const
         const unsigned char* texel = g.tex + ti * 3;
         r8 = texel[0]; g8 = texel[1]; b8 = texel[2];
       }
-      r = static_cast<float>(r8) / 255.0f; gr = static_cast<float>(g8) / 255.0f; bl = static_cast<float>(b8) / 255.0f;
+
     }
     if (mode == 1 || mode == 4) {
       double p[3][3];
@@ -178,12 +180,19 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterArgs g, const
       const double nn = sqrt((nx * nx + ny * ny) + nz * nz);
       const double s = nn > 0.0 ? fabs(nz) / nn : 0.0;
       geo8 = static_cast<unsigned char>(static_cast<int>(s * 255.0 + 0.5));
-      geo = static_cast<float>(geo8) / 255.0f;
+
     }
   }
   const int di = static_cast<int>(-255.0f * zval);
   const unsigned char d8 = static_cast<unsigned char>(di & 0xFF);
-  const float depth = static_cast<float>(d8) / 255.0f;
+  // the fp32 stack (reference layout, /255 as render3d.py:191) is only computed when it is asked for: four IEEE
+  // divisions per pixel that the fused path (u8 image for the CNN stem) never needs
+  float depth = 0.f;
+  if (g.out_f32) {
+    r = static_cast<float>(r8) / 255.0f; gr = static_cast<float>(g8) / 255.0f; bl = static_cast<float>(b8) / 255.0f;
+    geo = static_cast<float>(geo8) / 255.0f;
+    depth = static_cast<float>(d8) / 255.0f;
+  }
   float o[4] = {0.f, 0.f, 0.f, 0.f};
   uchar4 q = make_uchar4(0, 0, 0, 0);
   int C = 4;
@@ -251,7 +260,7 @@ int raster_launch(const RasterArgs& g, cudaStream_t stream) {
     raster_xform_kernel<<<gx, 256, 0, stream>>>(g.verts, g.nv, g.rot + static_cast<size_t>(v0) * 9, g.h, g.w, sv);
     dim3 gt(std::min(ceil_div(g.nt, 256), 1024), nc);
     raster_tris_kernel<<<gt, 256, 0, stream>>>(sv, g.nv, g.tris, g.nt, g.h, g.w, g.zbuf + static_cast<size_t>(v0) * view_pix);
-    raster_resolve_kernel<<<static_cast<unsigned>((nc * view_pix + 255) / 256), 256, 0, stream>>>(g, sv, v0, nc);
+    raster_resolve_kernel<<<dim3(static_cast<unsigned>((view_pix + 255) / 256), nc), 256, 0, stream>>>(g, sv, v0, nc);
     count_launch(3);
   }
   MVLM_CHECK_CUDA(cudaGetLastError());
