@@ -198,6 +198,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// The .ws form of the same instruction (M = 32 / 64 / 128).  What matters here is its accumulator layout for
+// M < 128 (measured, tools/exp_ws.cu): the M x N tile is spread over ALL 128 TMEM lanes --
+//   M = 64: lane group g (32 lanes) holds rows 32 * (g % 2) + lane, columns (g / 2) * N/2 + c, c in [0, N/2)
+//   M = 32: lane group g holds rows lane, columns g * N/4 + c, c in [0, N/4)
+// -- and it issues every 84.5 cycles at N = 256 (the plain M = 64 form leaves half the lanes idle: 128.5 cycles,
+// the same as M = 128).  N must be 64, 128 or 256.
+__device__ __forceinline__ void umma_ws_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.ws.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // mbarrier arrives once all tcgen05.mma issued so far by this thread are done.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

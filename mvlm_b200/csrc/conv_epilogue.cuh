@@ -17,7 +17,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kTileW = 8;         // output tile: 8 px wide ...
 constexpr int kMaxTileH = 32;     // ... and up to 32 rows high (N = 256)
 constexpr int kMTile = 128;       // output channels per CTA tile (UMMA M)
-constexpr int kStageFloats = 32 * 20;  // per-warp transpose buffer: 16 px x (32 ch + 4 pad) | 32 px x (16 + 4)
+constexpr int kStageFloats = 16 * 36;  // per-warp transpose buffer: 16 px x (32 ch + 4 pad)
 constexpr int kMaxCout = 256;
 constexpr int kTraceTiles = 64;   // debug timeline: tiles traced on CTA 0
 
@@ -26,7 +26,7 @@ constexpr int kTraceTiles = 64;   // debug timeline: tiles traced on CTA 0
 enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 32 /* fp32 NCHW map */, F_ARGMAX = 64,
               F_MID = 128 /* affine + ReLU right after the bias */, F_POOL = 256 /* raw/post at half resolution */,
               F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */,
-              F_M64 = 1024 /* cout <= 64: UMMA M = 64, 16 channels per TMEM lane group */,
+              F_M64 = 1024 /* cout <= 64: tcgen05.mma.ws with M = 64 / 32, the tile's pixels split over the TMEM lane groups */,
               F_POST2 = 2048 /* second full-resolution act copy (aux_mode 1) */,
               F_POOLX = 4096 /* additional pooled raw + pooled act copies (aux_mode 2) */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
@@ -154,12 +154,16 @@ __device__ __forceinline__ uint4 load_res(const uint8_t* p) {
   else return *reinterpret_cast<const uint4*>(p);
 }
 
-// One accumulator tile.  Accumulator column n = 8 * (row in tile) + (pixel in row).  One "unit" (one TMEM load,
-// one transpose) =
-//   M = 128: 16 columns = 2 image rows x 8 px of the warp's 32 channels,
-//   M = 64 : 32 columns = 4 image rows x 8 px of the warp's 16 channels (lanes 0..15 of the lane group),
-// i.e. 512 values either way.  The epilogue is latency-bound (two warps per scheduler, dependent
-// TMEM -> shared -> registers -> global chain per unit), so fewer, fatter units matter.
+// One accumulator tile.  Pixel n of the tile = 8 * (row in tile) + (pixel in row).  One "unit" (one TMEM load,
+// one transpose) = 16 pixels = 2 image rows x 8 px of the warp's 32 channels.
+//   M = 128 (plain tcgen05.mma): TMEM lane = output channel, TMEM column = pixel n.
+//   F_M64 (tcgen05.mma.ws, cout <= 64): the tile is spread over all 128 lanes (ptx::umma_ws_bf16) --
+//     M = 64: lane group g = channels 32 * (g % 2) .., pixels (g / 2) * N/2 + column,
+//     M = 32: lane group g = channels 0 .. 31,         pixels g * N/4 + column
+//     -- so every epilogue warp holds 32 channels in its 32 lanes, like at M = 128, and the lane groups that hold the
+//     same channels ("replicas") split the tile's pixel rows.
+// The epilogue is latency-bound (two warps per scheduler, dependent TMEM -> shared -> registers -> global chain
+// per unit), so fewer, fatter units matter.
 //
 // `tmem_acc` = TMEM address of column 0 of this tile's accumulator stage; `t_full` / `parity` = the barrier the
 // MMA warp commits to.  The caller releases the stage (tcgen05 fence + arrive on its t_empty barrier) afterwards.
@@ -169,41 +173,35 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
                                               uint64_t* t_full, const uint32_t parity, const uint32_t tmem_acc,
                                               float* stage, const int ew, const int lane_grp, const int lane,
                                               ArgmaxState& am, const bool prof, long long& w0, EpiTrace& tr) {
-  constexpr bool M64 = (F & F_M64) != 0;
-  constexpr int kM = M64 ? 64 : kMTile;
-  constexpr int kChGrp = M64 ? 16 : 32;      // channels per TMEM lane group
-  constexpr int kPitch = M64 ? 20 : 36;      // floats per pixel row of the transpose buffer
-  constexpr int kCols = M64 ? 32 : 16;       // accumulator columns per unit
+  constexpr bool WS = (F & F_M64) != 0;
+  constexpr int kM = kMTile;
+  constexpr int kChGrp = 32;                 // channels per TMEM lane group
+  constexpr int kPitch = 36;                 // floats per pixel row of the transpose buffer
+  constexpr int kCols = 16;                  // accumulator columns per unit
   constexpr int kUnitRows = kCols / 8;       // image rows per unit
-  constexpr int kPassStep = M64 ? 2 : 1;     // image rows between my pixel in pass 0 and in pass 1
-  constexpr bool kFrag = M64 && (F & F_HEAD) == 0;  // M = 64 accumulators read with the 16x256b shape
   static_assert(kCols * kPitch <= kStageFloats, "transpose buffer");
-  const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
-  // cout < M: the weight rows are replicated `rep` = kM / w_rows (1, 2 or 4) times along M, so that all four TMEM
-  // lane groups (and therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows
-  // instead.  Shifts, not divisions: in the dataflow kernel this runs once per tile.
-  const int rep_log2 = (4 * w_rows <= kM) ? 2 : ((2 * w_rows <= kM) ? 1 : 0);
-  const int rep = 1 << rep_log2;
+  // F_M64: `rep` = 2 (M = 64: 33 .. 64 channels) or 4 (M = 32) lane groups hold the same channels and different pixel
+  // rows of the tile.  Shifts, not divisions: in the dataflow kernel this runs once per tile.
+  const int rep_log2 = !WS ? 0 : (s.cout_pad <= 32 ? 2 : 1);
   // ew = index of this epilogue warp (0..7), lane_grp = its hardware warp id % 4: the TMEM lanes it may read are
   // 32 * lane_grp ..
   const int n_cgrp = 4 >> rep_log2;  // distinct channel groups along M
   const int cgrp = lane_grp & (n_cgrp - 1);
   const int replica = lane_grp >> (2 - rep_log2);
   const int n_units = max(1, tile_h / kUnitRows);
-  const int upw = max(1, n_units >> (1 + rep_log2));        // units per warp
-  const int u_begin = ((ew >> 2) * rep + replica) * upw;    // first unit handled by this warp
+  const int upr = max(1, n_units >> rep_log2);              // units per replica (= TMEM columns / 16 of the tile)
+  const int upw = max(1, upr >> 1);                         // units per warp (two warps share a lane group)
+  const int u_local = (ew >> 2) * upw;                      // my first unit among my replica's
+  const int u_begin = replica * upr + u_local;              // ... and among the tile's
   const int oh = s.h * e.up_sy, ow = s.w * e.up_sx;
-  // channel-major role (TMEM load, bias, transpose store): lane = channel; M = 64 -> lanes 0..15 only.
+  // channel-major role (TMEM load, bias, transpose store): lane = channel.
   // pixel-major role after the transpose, two passes per unit:
-  //   M = 128: lane -> (pixel column pj = lane/4, channels (lane%4)*8 .. +7), unit row ip in pass ip
-  //   M = 64 : lane -> (pixel column pj = (lane/2)%8, channels (lane%2)*8 .. +7), unit row lane/16 + 2*ip in pass ip
-  const bool cm_lane = !M64 || lane < 16;
-  const int pj = M64 ? ((lane >> 1) & 7) : (lane >> 2);
-  const int my_i = M64 ? (lane >> 4) : 0;
-  const int cq = M64 ? (lane & 1) * 8 : (lane & 3) * 8;
+  //   lane -> (pixel column pj = lane/4, channels (lane%4)*8 .. +7), unit row ip in pass ip
+  const int pj = lane >> 2;
+  const int cq = (lane & 3) * 8;
   constexpr bool kBf16Out = (F & (F_PRE | F_RAW | F_POST)) != 0;
   // byte strides of one image row in every tensor the epilogue touches: an access of unit r, pass ip is then
-  // (per-tile base pointer) + (kUnitRows * r + kPassStep * ip) * stride with a compile-time row offset
+  // (per-tile base pointer) + (kUnitRows * r + ip) * stride with a compile-time row offset
   const uint32_t rs_pre = static_cast<uint32_t>(s.w * e.pre_cs) * 2u, rs_res1 = static_cast<uint32_t>(s.w * e.res1_cs) * 2u;
   const uint32_t rs_res2 = static_cast<uint32_t>(s.w * e.res2_cs) * 2u;
   const uint32_t rs_up = static_cast<uint32_t>((s.w >> 1) * e.up_cs) * 2u;
@@ -217,8 +215,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   // half once the first are consumed.  (Loads issued one by one while earlier ones are being consumed do not work:
   // the few hardware scoreboards are shared, so every use then waits for the newest load; measured.)
   constexpr bool kHasRes = (F & (F_RES1 | F_RES2 | F_UP)) != 0;
-  constexpr int kMaxUpw = M64 ? 4 : 8;  // units per warp at N = 256
-  constexpr int kResRegs = 4 * (2 * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + (M64 ? 2 : 1) * ((F & F_UP) ? 1 : 0));
+  constexpr int kMaxUpw = WS ? 4 : 8;  // units per warp at N = 256
+  constexpr int kResRegs = 4 * (2 * (((F & F_RES1) ? 1 : 0) + ((F & F_RES2) ? 1 : 0)) + ((F & F_UP) ? 1 : 0));
   // Dataflow kernel: the first batch is issued AFTER the accumulator wait (below).  Issued before it, as in the
   // per-layer kernel, the buffer is live across the wait loop and ptxas keeps it on the stack in the dataflow kernel's
   // many-variant epilogue: every prefetched line was stored to local memory as it arrived, one exposed L2 round trip
@@ -226,26 +224,26 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   // exposed round trip per tile (~1.5k cycles under load) is the price.
   constexpr int kResBudget = kFlow ? MVLM_FLOW_RES_BUDGET : 64;
   constexpr int kPref = !kHasRes ? 1 : (kResRegs * kMaxUpw <= kResBudget ? kMaxUpw : (kResRegs * kMaxUpw <= 2 * kResBudget ? kMaxUpw / 2 : (kMaxUpw >= 4 ? kMaxUpw / 4 : 1)));  // units per batch
-  uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1][M64 ? 2 : 1];
+  uint4 r1[kPref][2], r2[(F & F_RES2) ? kPref : 1][2], ru[(F & F_UP) ? kPref : 1][1];
 
   const int m0 = tc.mt * kM;
   const int c_lane = m0 + cgrp * kChGrp + lane;       // channel-major role: my output channel
   const int c0 = m0 + cgrp * kChGrp + cq;             // pixel-major role: first of my 8 channels
   const bool grp_active = m0 + cgrp * kChGrp < s.cout_pad;
   const int y_first = tc.ty * tile_h + kUnitRows * u_begin;  // first image row handled by this warp
-  const bool rows_active = u_begin < n_units && y_first < s.h;
+  const bool rows_active = u_local < upr && y_first < s.h;
   const bool ch_ok = c0 < s.cout_pad;  // weight rows beyond cout_pad are never loaded
   const int xa = tc.tx * kTileW + pj;
   const bool vx = ch_ok && xa < s.w;
-  // PIXEL index of my pixel in pass 0 of the first unit of image `img`: (img, y_first + my_i, xa); 32-bit (checked in
+  // PIXEL index of my pixel in pass 0 of the first unit of image `img`: (img, y_first, xa); 32-bit (checked in
   // conv_plan), widened before it is multiplied with a channel stride
-  auto pix_of = [&](int img) __attribute__((always_inline)) { return (static_cast<uint32_t>(img) * s.h + y_first + my_i) * s.w + xa; };
+  auto pix_of = [&](int img) __attribute__((always_inline)) { return (static_cast<uint32_t>(img) * s.h + y_first) * s.w + xa; };
   // element index of the half-resolution pixel (img, y_first/2, xa/2): F_POOL outputs, F_UP input
   auto ppix_of = [&](int img) __attribute__((always_inline)) {
     return (static_cast<uint32_t>(img) * (s.h >> 1) + (y_first >> 1)) * (s.w >> 1) + (xa >> 1);
   };
   if ((F & F_ARGMAX) && tc.img != am.cur_img) {
-    if (am.cur_img >= 0 && am.best_hi != 0u && cm_lane && c_lane < e.cout_real)
+    if (am.cur_img >= 0 && am.best_hi != 0u && c_lane < e.cout_real)
       atomicMax(e.argmax_keys + static_cast<size_t>(am.cur_img) * e.cout_real + c_lane,
                 (static_cast<unsigned long long>(am.best_hi) << 32) | am.best_lo);
     am.best_hi = 0u; am.best_lo = 0u;
@@ -258,8 +256,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   uint8_t* const b_aux1 = (F & (F_POST2 | F_POOLX)) ? reinterpret_cast<uint8_t*>(e.out_aux1 + e.aux1_co + c0 + static_cast<size_t>((F & F_POOLX) ? ppix_of(is.aux1) : pix_of(is.aux1)) * e.aux1_cs) : nullptr;
   uint8_t* const b_aux2 = (F & F_POOLX) ? reinterpret_cast<uint8_t*>(e.out_aux2 + e.aux2_co + c0 + static_cast<size_t>(ppix_of(is.aux2)) * e.aux2_cs) : nullptr;
   // rows at / below my first pixel that exist in the image (0 when my pixel column / channels do not):
-  // unit r, pass ip is valid iff kUnitRows * r + kPassStep * ip < n_rows_ok
-  const int n_rows_ok = vx ? s.h - y_first - my_i : 0;
+  // unit r, pass ip is valid iff kUnitRows * r + ip < n_rows_ok
+  const int n_rows_ok = vx ? s.h - y_first : 0;
   // (kFlow: lanes whose pixel column / channels / rows do not exist point at the tensor's first element, see
   // prefetch_batch)
   const bool res_ok = !kFlow || n_rows_ok > 0;
@@ -273,7 +271,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
       if (kFlow || u < upw) {
 #pragma unroll
         for (int ip = 0; ip < 2; ++ip) {
-          const int row = kUnitRows * u + kPassStep * ip;
+          const int row = kUnitRows * u + ip;
           if constexpr (kFlow) {
             // unconditional loads (rows that do not exist re-read the tile's first row and are never used): with
             // conditionally defined buffer entries ptxas keeps the whole buffer in local memory in the non-inlined
@@ -281,15 +279,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
             const int rr = (u < upw && row < n_rows_ok) ? row : 0;
             if (F & F_RES1) r1[q][ip] = load_res<kFlow>(b_res1 + static_cast<size_t>(rr * rs_res1));
             if (F & F_RES2) r2[q][ip] = load_res<kFlow>(b_res2 + static_cast<size_t>(rr * rs_res2));
-            if ((F & F_UP) && (M64 || ip == 0))
-              ru[q][M64 ? ip : 0] = load_res<kFlow>(b_up + static_cast<size_t>((rr >> 1) * rs_up));
+            if ((F & F_UP) && ip == 0)
+              ru[q][0] = load_res<kFlow>(b_up + static_cast<size_t>((rr >> 1) * rs_up));
           } else if (row < n_rows_ok) {
             if (F & F_RES1) r1[q][ip] = load_res<kFlow>(b_res1 + static_cast<size_t>(row * rs_res1));
             if (F & F_RES2) r2[q][ip] = load_res<kFlow>(b_res2 + static_cast<size_t>(row * rs_res2));
             // nearest x2: rows 2k, 2k+1 and columns xa, xa^1 all read low-res pixel (k, xa/2);
-            // M = 128: both passes share one low-res row per unit, M = 64: pass ip reads low-res row 2u + ip
-            if ((F & F_UP) && (M64 || ip == 0))
-              ru[q][M64 ? ip : 0] = load_res<kFlow>(b_up + static_cast<size_t>((row >> 1) * rs_up));
+            // both passes share one low-res row per unit
+            if ((F & F_UP) && ip == 0)
+              ru[q][0] = load_res<kFlow>(b_up + static_cast<size_t>((row >> 1) * rs_up));
           }
         }
       }
@@ -304,17 +302,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   const int c_lane_ok = c_lane < s.cout_pad ? c_lane : 0;
   const float bias_c = ep.bias[c_lane_ok];
   const float mid_s_c = ep.mid_s[c_lane_ok], mid_t_c = ep.mid_t[c_lane_ok];
-  // kFrag: the two channels this thread holds after the 16x256b load (lane/4 and lane/4 + 8 of the warp's 16)
-  float fbias[2] = {0.f, 0.f}, fms[2] = {1.f, 1.f}, fmt[2] = {0.f, 0.f};
-  if constexpr (kFrag && kBf16Out) {
-    const int cb = m0 + cgrp * kChGrp + (lane >> 2);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ch = (cb + 8 * h) < s.cout_pad ? cb + 8 * h : 0;
-      fbias[h] = ep.bias[ch];
-      if (F & F_MID) { fms[h] = ep.mid_s[ch]; fmt[h] = ep.mid_t[ch]; }
-    }
-  }
   if constexpr (kFlow) {
     // no call inside this wait, see ptx::mbar_wait_trap
     if (!prof) {
@@ -330,17 +317,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
   ptx::tc_fence_after();
   MVLM_EPI_TRACE(5);
   if (grp_active && rows_active) {
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>(u_begin * kCols);
+    // TMEM column of my first unit: the tile's own pixel index at M = 128, the index within my replica's share of
+    // the tile for the .ws layouts
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(lane_grp * 32) << 16) + static_cast<uint32_t>((WS ? u_local : u_begin) * kCols);
     // one register buffer: the load of unit r+1 is issued as soon as unit r has left the registers
-    // M = 64 without channel-major consumers: the 16 data lanes of the lane group are read with the 16x256b shape,
-    // which spreads them over all 32 threads (2 channels x 16 pixels each): half the registers and, above all,
-    // full 32-lane transpose stores -- the shared-memory pipe is what bounds these layers
-    uint32_t vr[kFrag ? 16 : kCols];
-    auto tmem_load = [&](int u) __attribute__((always_inline)) {
-      if constexpr (kFrag) ptx::tmem_ld_16x256b_x4(taddr + u * kCols, vr);
-      else if constexpr (M64) ptx::tmem_ld32(taddr + u * kCols, vr);
-      else ptx::tmem_ld16(taddr + u * kCols, vr);
-    };
+    uint32_t vr[kCols];
+    auto tmem_load = [&](int u) __attribute__((always_inline)) { ptx::tmem_ld16(taddr + u * kCols, vr); };
     tmem_load(0);
 #pragma unroll
     for (int r = 0; r < kMaxUpw; ++r) {
@@ -354,7 +336,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
             // channel-major consumers: lane = channel c_lane, vr[j] = pixel (y + j/8, x0 + j%8)
             const int x0 = tc.tx * kTileW;
             const int nvx = s.w - x0;  // >= 8 for interior tiles
-            if (cm_lane && c_lane < e.cout_real) {
+            if (c_lane < e.cout_real) {
 #pragma unroll
               for (int i = 0; i < kUnitRows; ++i) {
                 if (y + i < s.h) {
@@ -400,22 +382,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
             // bias in the channel-major role (one register), then transpose the unit through shared memory:
             // row = pixel, 36 (20)-float pitch (conflict-free STS.32; LDS.128 conflict-free at 36)
             __syncwarp();
-            if constexpr (kFrag) {
-              // register 4k + 2h + e = (channel lane/4 + 8h, pixel 8k + 2(lane%4) + e); conflict-free at pitch 20
-              const int p0 = 2 * (lane & 3);
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                  for (int e2 = 0; e2 < 2; ++e2) {
-                    float f = __uint_as_float(vr[4 * k + 2 * h + e2]) + fbias[h];
-                    if (F & F_MID) f = fmaxf(fmaf(f, fms[h], fmt[h]), 0.f);
-                    stage[(8 * k + p0 + e2) * kPitch + (lane >> 2) + 8 * h] = f;
-                  }
-                }
-              }
-            } else if (cm_lane) {
+            {
 #pragma unroll
               for (int j = 0; j < kCols; ++j) {
                 float f = __uint_as_float(vr[j]) + bias_c;
@@ -433,16 +400,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
             uint4 pool_cur[2];
 #pragma unroll
             for (int ip = 0; ip < 2; ++ip) {
-              const int row = kUnitRows * r + kPassStep * ip;  // my image row in this pass, relative to my first
+              const int row = kUnitRows * r + ip;  // my image row in this pass, relative to my first
               const bool valid = row < n_rows_ok;
               float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               if (valid) {
-                lds8(stage + (pj + 8 * (my_i + kPassStep * ip)) * kPitch + cq, f);
+                lds8(stage + (pj + 8 * ip) * kPitch + cq, f);
                 if (F & F_PRE)
                   *reinterpret_cast<uint4*>(b_pre + static_cast<size_t>(row * rs_pre)) = affine_relu_pack8(f, pre_s, pre_t);
                 if (F & F_RES1) add8(r1[r % kPref][ip], f);
                 if (F & F_RES2) add8(r2[r % kPref][ip], f);
-                if (F & F_UP) add8(ru[r % kPref][M64 ? ip : 0], f);
+                if (F & F_UP) add8(ru[r % kPref][0], f);
               }
               if (F & (F_POOL | F_POOLX)) pool_cur[ip] = pack8(f);
               if (!(F & F_POOL) && valid) {
@@ -463,33 +430,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
             }
             if (r < 2) MVLM_EPI_TRACE(10 + 4 * r);
             if (F & (F_POOL | F_POOLX)) {
-              // 2x2 max-pool of the bf16-rounded values; shuffles run on all lanes.
-              //   M = 128: vertical partner = my other pass, horizontal (pixel column pj ^ 1) = lane ^ 4,
-              //            one pooled row per unit;
-              //   M = 64 : vertical partner = lane ^ 16 (same pass), horizontal = lane ^ 2, pass ip is pooled row
-              //            2r + ip of my part of the tile.
-#pragma unroll
-              for (int pp = 0; pp < (M64 ? 2 : 1); ++pp) {
-                uint4 m = pool_cur[pp];
-                if (M64) {
-                  uint4 o;
-                  o.x = __shfl_xor_sync(0xffffffffu, m.x, 16);
-                  o.y = __shfl_xor_sync(0xffffffffu, m.y, 16);
-                  o.z = __shfl_xor_sync(0xffffffffu, m.z, 16);
-                  o.w = __shfl_xor_sync(0xffffffffu, m.w, 16);
-                  m = max_bf16x8(m, o);
-                } else {
-                  m = max_bf16x8(m, pool_cur[1]);
-                }
+              // 2x2 max-pool of the bf16-rounded values; shuffles run on all lanes.  Vertical partner = my other
+              // pass, horizontal (pixel column pj ^ 1) = lane ^ 4, one pooled row per unit.
+              {
+                uint4 m = max_bf16x8(pool_cur[0], pool_cur[1]);
                 uint4 o;
-                o.x = __shfl_xor_sync(0xffffffffu, m.x, M64 ? 2 : 4);
-                o.y = __shfl_xor_sync(0xffffffffu, m.y, M64 ? 2 : 4);
-                o.z = __shfl_xor_sync(0xffffffffu, m.z, M64 ? 2 : 4);
-                o.w = __shfl_xor_sync(0xffffffffu, m.w, M64 ? 2 : 4);
+                o.x = __shfl_xor_sync(0xffffffffu, m.x, 4);
+                o.y = __shfl_xor_sync(0xffffffffu, m.y, 4);
+                o.z = __shfl_xor_sync(0xffffffffu, m.z, 4);
+                o.w = __shfl_xor_sync(0xffffffffu, m.w, 4);
                 m = max_bf16x8(m, o);
                 // H, W even: row y+1 and column xa+1 exist whenever (y, xa) does
-                const int prow = (kUnitRows / 2) * r + pp;  // pooled row relative to y_first / 2
-                if (2 * prow < n_rows_ok && my_i == 0 && (pj & 1) == 0) {
+                const int prow = r;  // pooled row relative to y_first / 2
+                if (2 * prow < n_rows_ok && (pj & 1) == 0) {
                   if (F & F_POOL) {
                     if (F & F_RAW) *reinterpret_cast<uint4*>(b_raw + static_cast<size_t>(prow * rs_raw)) = m;
                     if (F & F_POST) {
@@ -521,13 +474,10 @@ template <int F>
 __device__ __forceinline__ void epilogue_argmax_flush(const ConvShape& s, const ConvEpilogue& e, const int lane_grp,
                                                       const int lane, const ArgmaxState& am) {
   if ((F & F_ARGMAX) && am.cur_img >= 0 && am.best_hi != 0u) {
-    constexpr bool M64 = (F & F_M64) != 0;
-    constexpr int kM = M64 ? 64 : kMTile;
-    constexpr int kChGrp = M64 ? 16 : 32;
-    const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;
-    const int n_cgrp = (4 * w_rows <= kM) ? 1 : ((2 * w_rows <= kM) ? 2 : 4);
-    const int c_lane = (lane_grp & (n_cgrp - 1)) * kChGrp + lane;
-    if ((!M64 || lane < 16) && c_lane < e.cout_real)
+    constexpr bool WS = (F & F_M64) != 0;
+    const int n_cgrp = !WS ? 4 : (s.cout_pad <= 32 ? 1 : 2);
+    const int c_lane = (lane_grp & (n_cgrp - 1)) * 32 + lane;
+    if (c_lane < e.cout_real)
       atomicMax(e.argmax_keys + static_cast<size_t>(am.cur_img) * e.cout_real + c_lane,
                 (static_cast<unsigned long long>(am.best_hi) << 32) | am.best_lo);
   }

@@ -359,7 +359,6 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         const FlowLayer& GL = layers[it.layer];
         const int kM = (L.f & F_M64) ? 64 : kMTile;
         const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;
-        const int rep = (4 * w_rows <= kM) ? 4 : ((2 * w_rows <= kM) ? 2 : 1);
         const int n_chunks = (s.cin + 63) >> 6;
         for (int c = 0; c < n_chunks; ++c) {
           const bool is_tail = L.tail != 0 && c == n_chunks - 1;
@@ -368,10 +367,8 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
           const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
           for (int tap = 0; tap < s.kw * s.kh; ++tap) {  // tap = kx * KH + ky
             ptx::mbar_wait(&bar->w_empty[sw], pw ^ 1);
-            ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
-            for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
-              ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes + q * w_rows * row_b,
-                               tap * s.cin + c * 64, it.mt * kM);
+            ptx::mbar_expect_tx(&bar->w_full[sw], wb);
+            ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * kWSlotBytes, tap * s.cin + c * 64, it.mt * kM);
             if (++sw == kWSlots) { sw = 0; pw ^= 1; }
           }
         }
@@ -391,8 +388,9 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
         const LayerSm& L = lsm[it.layer];
         if (L.kind != FLOW_CONV) continue;
         const ConvShape& s = L.s;
-        const int kM = (L.f & F_M64) ? 64 : kMTile;
-        const uint32_t idesc = ptx::umma_idesc_bf16(kM, L.tile_h * kTileW);
+        // cout <= 64: tcgen05.mma.ws with M = 64 / 32 (see conv_umma.cu)
+        const bool ws = (L.f & F_M64) != 0;
+        const uint32_t idesc = ptx::umma_idesc_bf16(ws ? (s.cout_pad <= 32 ? 32 : 64) : kMTile, L.tile_h * kTileW);
         const int n_chunks = (s.cin + 63) >> 6;
         const int halo_px = kTileW + s.kw - 1;
         timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
@@ -417,7 +415,10 @@ conv_flow_kernel(const FlowLayer* __restrict__ layers, const void* __restrict__ 
               const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * kWSlotBytes) >> 4) & 0x3FFFu) | (1u << 16);
               // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
               const uint32_t x_lo = h_lo + ((static_cast<uint32_t>(ky * halo_px + kx) * row_b) >> 4);
-              if (nk == 4) {
+              if (ws) {
+                for (int kk = 0; kk < nk; ++kk)
+                  ptx::umma_ws_bf16(d, a_hi | (w_lo + 2 * kk), b_hi | (x_lo + 2 * kk), idesc, (kk == 0) ? accumulate : 1u);
+              } else if (nk == 4) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                   ptx::umma_bf16(d, a_hi | (w_lo + 2 * kk), b_hi | (x_lo + 2 * kk), idesc, (kk == 0) ? accumulate : 1u);

@@ -103,15 +103,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const int n_hslots = p.n_hslots, n_wslots = p.n_wslots;
   const int halo_px = kTileW + s.kw - 1;            // pixels per halo row
   const int halo_rows = p.tile_h + s.kh - 1;
-  // cout <= 64 runs with UMMA M = 64 (same cycles per instruction as M = 128, measured in tools/exp_m64.cu, but
-  // half the weight bytes through shared memory, which is the binding resource): output row i sits in TMEM lane
-  // 32 * (i / 16) + i % 16, i.e. every lane group (every epilogue warp) holds 16 channels in its lanes 0..15.
+  // cout <= 64 runs with tcgen05.mma.ws, M = 64 (33 .. 64 channels) or 32: the plain M = 64 form leaves half of the
+  // tensor core's 128 lanes idle (128.5 cycles per instruction at N = 256, like M = 128; tools/exp_m64.cu), the .ws
+  // form spreads the 64 (32) x N tile over all 128 TMEM lanes and issues every 84.5 cycles (tools/exp_ws.cu), so
+  // every epilogue warp holds 32 channels in its 32 lanes and the lane groups split the tile's pixel rows.
   constexpr bool M64 = (F & F_M64) != 0;
   constexpr int kM = M64 ? 64 : kMTile;
   const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
-  // cout < M: the weight rows are replicated `rep` times along M, so that all four TMEM lane groups (and
-  // therefore all eight epilogue warps) hold the same channels and split the tile's pixel rows instead.
-  const int rep = kM / w_rows;
+  const int mma_m = M64 ? (s.cout_pad <= 32 ? 32 : 64) : kMTile;
   const uint32_t w_slot_bytes = static_cast<uint32_t>(kM) * 128u;
   // stationary weights: all (chunk, tap) tiles of the layer fit in the ring -> loaded once per CTA, never released
   const bool w_stat = p.w_stationary != 0;
@@ -227,10 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
           for (int tap = 0; tap < s.kw * s.kh; ++tap) {  // tap = kx * KH + ky
             if (!w_stat) timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
-            ptx::mbar_expect_tx(&bar->w_full[sw], wb * rep);
-            for (int q = 0; q < rep; ++q)  // small cout: the same rows again for the other TMEM lane groups
-              ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * w_slot_bytes + q * w_rows * row_b,
-                               tap * s.cin + c * 64, mt * kM);
+            ptx::mbar_expect_tx(&bar->w_full[sw], wb);
+            ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * w_slot_bytes, tap * s.cin + c * 64, mt * kM);
             if (++sw == n_wslots) { sw = 0; pw ^= 1; }
           }
         }
@@ -245,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // elect.sync (not `lane == 0`): the compiler then knows a single lane is active and emits the
     // UTCHMMA / UTCBAR uniform-datapath instructions without a per-lane serialisation loop.
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(kM, p.tile_h * kTileW);
+      const uint32_t idesc = ptx::umma_idesc_bf16(mma_m, p.tile_h * kTileW);
       // descriptor = {lo: start>>4 | LBO, hi: SBO | version | swizzle}; only lo changes per MMA.
       //   A (weights): 8-row groups 8 rows apart.  B (halo tile): 8-row group = the 8 pixels of one image row,
       //   groups one halo row (halo_px pixels) apart.
@@ -278,13 +275,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * w_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
               // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
               const uint32_t x_lo = h_lo + ((static_cast<uint32_t>(ky * halo_px + kx) * row_b) >> 4);
+              auto mma = [&](int k) __attribute__((always_inline)) {
+                if constexpr (M64) ptx::umma_ws_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
+                else ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
+              };
               if (nk == 4) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
+                for (int k = 0; k < 4; ++k) mma(k);
               } else {
-                for (int k = 0; k < nk; ++k)
-                  ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
+                for (int k = 0; k < nk; ++k) mma(k);
               }
               accumulate = 1;
               if (p.debug_mode == 0 && !w_stat) ptx::umma_commit(&bar->w_empty[sw]);
@@ -430,14 +429,15 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
   memset(&p, 0, sizeof(p));
   p.s = s;
   p.e = e;
-  // output tile: 8 px x tile_h rows (N = 8 * tile_h columns), tile_h = 32 unless the map is lower
-  const int tile_h = s.h >= 32 ? kMaxTileH : (s.h >= 16 ? 16 : (s.h >= 8 ? 8 : 4));
+  // output tile: 8 px x tile_h rows (N = 8 * tile_h columns), tile_h = 32 unless the map is lower; the .ws MMA of the
+  // cout <= 64 layers needs N >= 64 (rows beyond the map are TMA zero fill and never stored)
+  const int tile_h = s.h >= 32 ? kMaxTileH : (s.h >= 16 ? 16 : ((s.h >= 8 || s.cout_pad <= 64) ? 8 : 4));
   p.tile_h = tile_h;
   {
     // ring depths: the halo slot holds the whole (8+KW-1) x (tile_h+KH-1) pixel tile of one 64-channel chunk
     const int hbytes = (kTileW + s.kw - 1) * (tile_h + s.kh - 1) * 128;
     p.h_slot_bytes = (hbytes + 1023) & ~1023;
-    // cout <= 64 -> UMMA M = 64, 8 KB weight slots; all (chunk, tap) tiles resident when they fit the ring
+    // cout <= 64 -> tcgen05.mma.ws with M <= 64, 8 KB weight slots; all (chunk, tap) tiles resident when they fit the ring
     const int m_tile = s.cout_pad <= 64 ? 64 : kMTile;
     const int wslot = m_tile * 128;
     const int n_wtiles = ((s.cin + 63) / 64) * s.kh * s.kw;
