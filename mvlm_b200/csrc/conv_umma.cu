@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // Its own thread, so that the halo prefetch runs n_hslots chunks ahead of the MMAs whatever the state of the
     // weight ring (measured: behind the weight loads in one queue the next halo tile was issued ~4k cycles before
     // it was needed, about the DRAM + queueing latency of the load, and the tensor pipe waited for it every tile).
-    if (ptx::elect_one() && p.debug_mode == 0) {
+    if (ptx::elect_one() && (p.debug_mode & 1) == 0) {
       int sh = 0;
       uint32_t ph = 0;
       for (int t = t_begin; t < t_end; t += t_step) {
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
   } else if (warp == 10) {
     // ===================== TMA producer: weights =====================
-    if (ptx::elect_one() && p.debug_mode == 0) {
+    if (ptx::elect_one() && (p.debug_mode & 1) == 0) {
       int sw = 0;
       uint32_t pw = 0;
       for (int t = t_begin; t < t_end; t += t_step) {
@@ -242,14 +242,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // elect.sync (not `lane == 0`): the compiler then knows a single lane is active and emits the
     // UTCHMMA / UTCBAR uniform-datapath instructions without a per-lane serialisation loop.
     if (ptx::elect_one()) {
+      // This loop is ONE thread's dependent scalar code: with ~80 instructions per tap (barrier bookkeeping, constant-bank
+      // reloads, descriptor arithmetic) it took ~450 cycles per tap whatever the number of MMAs in it (measured with
+      // operands and epilogue switched off, tools/exp_ws_inkernel.py) -- hidden behind 4 x 128 cycles of math at M = 128,
+      // not behind 4 (2, 1) x 80 cycles of the .ws layers.  So: everything that does not change per tap is hoisted, the
+      // descriptors advance by integer adds, stationary weights are waited for once per CTA, and there is no
+      // tcgen05.fence in the tap loop (the mbarrier wait orders the TMA writes before the MMA's reads).
       const uint32_t idesc = ptx::umma_idesc_bf16(mma_m, p.tile_h * kTileW);
       // descriptor = {lo: start>>4 | LBO, hi: SBO | version | swizzle}; only lo changes per MMA.
       //   A (weights): 8-row groups 8 rows apart.  B (halo tile): 8-row group = the 8 pixels of one image row,
       //   groups one halo row (halo_px pixels) apart.
+      // full 64-channel chunks: 128-byte rows, SWIZZLE_128B; tail chunk: SWIZZLE_32B (16 ch: 32-byte rows) or
+      // SWIZZLE_64B (32 ch: 64-byte rows)
+      const bool live = (p.debug_mode & 1) == 0;
+      const int n_kx = s.kw, n_ky = s.kh;
+      const uint32_t tail_row_b = p.tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;
+      const uint32_t tail_swz = !p.tail ? 2u : (p.tail == 16 ? 6u : 4u);
+      const uint64_t a_hi_full = static_cast<uint64_t>(((8u * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32;
+      const uint64_t b_hi_full = static_cast<uint64_t>(((static_cast<uint32_t>(halo_px) * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32;
+      const uint64_t a_hi_tail = static_cast<uint64_t>(((8u * tail_row_b) >> 4) | (1u << 14) | (tail_swz << 29)) << 32;
+      const uint64_t b_hi_tail = static_cast<uint64_t>(((static_cast<uint32_t>(halo_px) * tail_row_b) >> 4) | (1u << 14) | (tail_swz << 29)) << 32;
+      // shared-memory addresses are below 2^18: (address >> 4) needs no mask and slot offsets are plain adds
+      const uint32_t h_lo0 = (ptx::smem_u32(h_slots) >> 4) | (1u << 16), h_step = static_cast<uint32_t>(p.h_slot_bytes) >> 4;
+      const uint32_t w_lo0 = (ptx::smem_u32(w_slots) >> 4) | (1u << 16), w_step = w_slot_bytes >> 4;
+      const int last_chunk = n_chunks - 1;
+      const int nk_last = (s.cin - last_chunk * 64) >= 64 ? 4 : ((s.cin - last_chunk * 64) >> 4);
       int sh = 0, sw = 0;
       uint32_t ph = 0, pw = 0;
       int acc = 0;
       uint32_t pacc = 0;
+      bool w_wait = live;  // stationary weights: the slots are waited for during the first tile only
       for (int t = t_begin; t < t_end; t += t_step) {
         timed_wait(&bar->t_empty[acc], pacc ^ 1, prof, w1);
         ptx::tc_fence_after();
@@ -257,45 +279,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const uint32_t d = tmem_base + static_cast<uint32_t>(acc * 256);
         uint32_t accumulate = 0;
         for (int c = 0; c < n_chunks; ++c) {
-          const int rem = s.cin - c * 64;
-          const int nk = rem >= 64 ? 4 : (rem >> 4);
-          // tail chunk: SWIZZLE_32B (16 ch: 32-byte rows) or SWIZZLE_64B (32 ch: 64-byte rows)
-          const bool is_tail = p.tail != 0 && c == n_chunks - 1;
-          const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;
-          const uint32_t swz = !is_tail ? 2u : (p.tail == 16 ? 6u : 4u);
-          const uint64_t a_hi = static_cast<uint64_t>(((8u * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
-          const uint64_t b_hi = static_cast<uint64_t>(((static_cast<uint32_t>(halo_px) * row_b) >> 4) | (1u << 14) | (swz << 29)) << 32;
-          if (p.debug_mode == 0) timed_wait(&bar->h_full[sh], ph, prof, w0);
+          const bool is_tail = p.tail != 0 && c == last_chunk;
+          const int nk = c == last_chunk ? nk_last : 4;
+          const uint32_t rb16 = (is_tail ? tail_row_b : 128u) >> 4;  // 16-byte units per pixel row
+          const uint64_t a_hi = is_tail ? a_hi_tail : a_hi_full;
+          const uint64_t b_hi = is_tail ? b_hi_tail : b_hi_full;
+          const uint32_t ky_step = static_cast<uint32_t>(halo_px) * rb16;
+          if (live) timed_wait(&bar->h_full[sh], ph, prof, w0);
           if (c == 0) MVLM_TRACE(3);
-          const uint32_t h_lo = ((ptx::smem_u32(h_slots + sh * p.h_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-          for (int kx = 0; kx < s.kw; ++kx) {
-            for (int ky = 0; ky < s.kh; ++ky) {
-              if (p.debug_mode == 0) timed_wait(&bar->w_full[sw], w_stat ? 0u : pw, prof, w0);
-              ptx::tc_fence_after();
-              const uint32_t w_lo = ((ptx::smem_u32(w_slots + sw * w_slot_bytes) >> 4) & 0x3FFFu) | (1u << 16);
-              // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
-              const uint32_t x_lo = h_lo + ((static_cast<uint32_t>(ky * halo_px + kx) * row_b) >> 4);
-              auto mma = [&](int k) __attribute__((always_inline)) {
-                if constexpr (M64) ptx::umma_ws_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
-                else ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, (k == 0) ? accumulate : 1u);
+          uint32_t x_col = h_lo0 + static_cast<uint32_t>(sh) * h_step;
+          for (int kx = 0; kx < n_kx; ++kx, x_col += rb16) {
+            // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
+            uint32_t x_lo = x_col;
+            for (int ky = 0; ky < n_ky; ++ky, x_lo += ky_step) {
+              if (w_wait) timed_wait(&bar->w_full[sw], w_stat ? 0u : pw, prof, w0);
+              const uint32_t w_lo = w_lo0 + static_cast<uint32_t>(sw) * w_step;
+              auto mma = [&](int k, uint32_t en) __attribute__((always_inline)) {
+                if constexpr (M64) ptx::umma_ws_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, en);
+                else ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, en);
               };
+              mma(0, accumulate);
               if (nk == 4) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mma(k);
+                mma(1, 1u); mma(2, 1u); mma(3, 1u);
               } else {
-                for (int k = 0; k < nk; ++k) mma(k);
+                for (int k = 1; k < nk; ++k) mma(k, 1u);
               }
               accumulate = 1;
-              if (p.debug_mode == 0 && !w_stat) ptx::umma_commit(&bar->w_empty[sw]);
+              if (live && !w_stat) ptx::umma_commit(&bar->w_empty[sw]);
               if (++sw == n_wslots) { sw = 0; pw ^= 1; }
             }
           }
-          if (p.debug_mode == 0) ptx::umma_commit(&bar->h_empty[sh]);
+          if (live) ptx::umma_commit(&bar->h_empty[sh]);
           if (++sh == n_hslots) { sh = 0; ph ^= 1; }
         }
         ptx::umma_commit(&bar->t_full[acc]);
         MVLM_TRACE(4);
         ++trace_i;
+        if (w_stat) w_wait = false;
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
       if (prof) { p.prof[blockIdx.x * 8 + 2] = w0; p.prof[blockIdx.x * 8 + 3] = w1; p.prof[blockIdx.x * 8 + 4] = clock64() - t_kernel0; }
@@ -314,9 +334,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const TileCoord tc = decode_tile(p, t);
       const ImageSlots is = {tc.img, tc.img, tc.img, tc.img, tc.img, tc.img, tc.img, tc.img};
       tr.trace_i = trace_i;
-      epilogue_tile<F, false>(s, e, p.tile_h, cp, tc, is, &bar->t_full[acc], pacc,
-                              tmem_base + static_cast<uint32_t>(acc * 256), stage, warp - 2, warp & 3, lane, am, prof, w0,
-                              tr);
+      if (p.debug_mode & 2) {  // experiment: accumulators are dropped (results invalid)
+        timed_wait(&bar->t_full[acc], pacc, prof, w0);
+        ptx::tc_fence_after();
+      } else {
+        epilogue_tile<F, false>(s, e, p.tile_h, cp, tc, is, &bar->t_full[acc], pacc,
+                                tmem_base + static_cast<uint32_t>(acc * 256), stage, warp - 2, warp & 3, lane, am, prof, w0,
+                                tr);
+      }
       // all tcgen05.ld of this accumulator stage have completed (wait::ld above)
       ptx::tc_fence_before();
       __syncwarp();
