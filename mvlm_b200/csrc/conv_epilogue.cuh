@@ -28,7 +28,8 @@ enum : int { F_PRE = 1, F_RES1 = 2, F_RES2 = 4, F_RAW = 8, F_POST = 16, F_F32 = 
               F_UP = 512 /* + nearest-x2 up-sampled half-resolution tensor */,
               F_M64 = 1024 /* cout <= 64: tcgen05.mma.ws with M = 64 / 32, the tile's pixels split over the TMEM lane groups */,
               F_POST2 = 2048 /* second full-resolution act copy (aux_mode 1) */,
-              F_POOLX = 4096 /* additional pooled raw + pooled act copies (aux_mode 2) */ };
+              F_POOLX = 4096 /* additional pooled raw + pooled act copies (aux_mode 2) */,
+              F_STAT = 8192 /* (per-layer kernel only) 3 x 3 taps over stationary weights: straight-line MMA issue */ };
 constexpr int F_HEAD = F_F32 | F_ARGMAX;
 
 // feature mask of a planned layer (without F_M64)

@@ -33,6 +33,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <atomic>
 
 namespace mvlm {
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   // form spreads the 64 (32) x N tile over all 128 TMEM lanes and issues every 84.5 cycles (tools/exp_ws.cu), so
   // every epilogue warp holds 32 channels in its 32 lanes and the lane groups split the tile's pixel rows.
   constexpr bool M64 = (F & F_M64) != 0;
+  constexpr bool STAT = (F & F_STAT) != 0;  // stationary weights and 3 x 3 taps (conv_launch)
   constexpr int kM = M64 ? 64 : kMTile;
   const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
   const int mma_m = M64 ? (s.cout_pad <= 32 ? 32 : 64) : kMTile;
@@ -288,6 +290,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           if (live) timed_wait(&bar->h_full[sh], ph, prof, w0);
           if (c == 0) MVLM_TRACE(3);
           uint32_t x_col = h_lo0 + static_cast<uint32_t>(sh) * h_step;
+          if (STAT && !w_wait && (nk == 4 || nk == 2 || nk == 1)) {
+            // 3 x 3 taps over stationary weights that have been waited for, straight-line: the B descriptor of tap
+            // (kx, ky), K-step k is x_col + a compile-time offset (halo rows are 10 pixels of NK * 32 bytes), the A
+            // descriptor is slot chunk * 9 + tap: two uniform adds per MMA, no barrier in sight.  (The same unrolling
+            // with the weight ring's wait / commit per tap made the 128- and 256-channel layers 3-4 % slower.)
+            auto taps = [&](auto nk_c) __attribute__((always_inline)) {
+              constexpr int NK = decltype(nk_c)::value;
+              constexpr uint32_t kRb16 = NK * 2;
+              const uint32_t w_base = w_lo0 + static_cast<uint32_t>(c * 9) * w_step;
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t x_lo = x_col + static_cast<uint32_t>(((tap % 3) * 10 + tap / 3)) * kRb16;  // tap = kx * 3 + ky
+                const uint32_t w_lo = w_base + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(kM) * 128u >> 4);
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                  const uint32_t en = (tap == 0 && k == 0) ? accumulate : 1u;
+                  if constexpr (M64) ptx::umma_ws_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, en);
+                  else ptx::umma_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, en);
+                }
+              }
+              accumulate = 1;
+            };
+            if (nk == 4) taps(std::integral_constant<int, 4>());
+            else if (nk == 2) taps(std::integral_constant<int, 2>());
+            else taps(std::integral_constant<int, 1>());
+          } else
           for (int kx = 0; kx < n_kx; ++kx, x_col += rb16) {
             // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
             uint32_t x_lo = x_col;
@@ -554,8 +582,11 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   const int f = feature_mask(e);
   // cout <= 64 layers run the M = 64 variant (conv_plan chose the ring geometry accordingly)
   const bool m64 = p.s.cout_pad <= 64;
+  // ... and, with 3 x 3 taps over stationary weights, the variant whose MMA warp issues a tile's MMAs straight-line
+  const bool stat = m64 && p.w_stationary && p.s.kw == 3 && p.s.kh == 3;
 #define MVLM_CASE_BOTH(FLAGS) \
-  case (FLAGS): return m64 ? launch_t<(FLAGS) | F_M64>(p, stream) : launch_t<(FLAGS)>(p, stream)
+  case (FLAGS):               \
+    return m64 ? (stat ? launch_t<(FLAGS) | F_M64 | F_STAT>(p, stream) : launch_t<(FLAGS) | F_M64>(p, stream)) : launch_t<(FLAGS)>(p, stream)
 #define MVLM_CASE_128(FLAGS) \
   case (FLAGS):              \
     if (!m64) return launch_t<(FLAGS)>(p, stream); \
