@@ -6,10 +6,12 @@ caller gets an exception.  PyTorch is used only to own device memory and streams
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libmvlm_b200.so"
+# MVLM_B200_LIB: another build of the same library (A/B timing of two builds on one box, tools/ab_cnn.py)
+LIB_PATH = Path(os.environ.get("MVLM_B200_LIB") or _HERE / "libmvlm_b200.so")
 
 
 class MvlmError(RuntimeError):

@@ -198,6 +198,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// pull one box of a 4-D tensor map into L2: no shared memory, no register, no completion to wait for
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // The .ws form of the same instruction (M = 32 / 64 / 128).  What matters here is its accumulator layout for
 // M < 128 (measured, tools/exp_ws.cu): the M x N tile is spread over ALL 128 TMEM lanes --
 //   M = 64: lane group g (32 lanes) holds rows 32 * (g % 2) + lane, columns (g / 2) * N/2 + c, c in [0, N/2)

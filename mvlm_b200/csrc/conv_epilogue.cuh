@@ -313,6 +313,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
       w0 += clock64() - t0;
     }
   } else {
+    MVLM_EPI_TRACE(7);  // per-layer kernel: residual prefetch issued, parameters loaded, about to wait
     timed_wait(t_full, parity, prof, w0);
   }
   ptx::tc_fence_after();

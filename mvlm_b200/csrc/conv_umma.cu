@@ -82,6 +82,28 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   return c;
 }
 
+// Tile coordinates of a role's tile sequence t_begin, t_begin + t_step, ...: the three integer divisions are done once
+// for the first tile and once for the step; every further tile is three additions with carry.  (Per tile they were a
+// ~450-cycle dependent chain at the head of the epilogue warps' preamble, which the epilogue-bound layers pay in full.)
+struct TileIter {
+  TileCoord c, d;
+  int n_nt, tiles_x, tiles_y;
+  __device__ __forceinline__ TileIter(const ConvParams& p, int t_begin, int t_step)
+      : c(decode_tile(p, t_begin)), d(decode_tile(p, t_step)), n_nt(p.n_nt), tiles_x(p.tiles_x), tiles_y(p.tiles_y) {}
+  __device__ __forceinline__ void next() {
+    c.mt += d.mt;
+    int carry = c.mt >= n_nt ? 1 : 0;
+    c.mt -= carry ? n_nt : 0;
+    c.tx += d.tx + carry;
+    carry = c.tx >= tiles_x ? 1 : 0;
+    c.tx -= carry ? tiles_x : 0;
+    c.ty += d.ty + carry;
+    carry = c.ty >= tiles_y ? 1 : 0;
+    c.ty -= carry ? tiles_y : 0;
+    c.img += d.img + carry;
+  }
+};
+
 template <int F>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
   constexpr bool ARGMAX = (F & F_ARGMAX) != 0;  // arg-max variants use the contiguous tile schedule
@@ -143,6 +165,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     ptx::tma_prefetch_desc(&p.tm_a);
     ptx::tma_prefetch_desc(&p.tm_b);
     if (p.tail) { ptx::tma_prefetch_desc(&p.tm_a2); ptx::tma_prefetch_desc(&p.tm_b2); }
+    if (F & F_RES1) ptx::tma_prefetch_desc(&p.tm_r1);
+    if (F & F_RES2) ptx::tma_prefetch_desc(&p.tm_r2);
+    if (F & F_UP) ptx::tma_prefetch_desc(&p.tm_up);
     for (int i = 0; i < n_hslots; ++i) {
       ptx::mbar_init(&bar->h_full[i], 1);
       ptx::mbar_init(&bar->h_empty[i], 1);
@@ -195,8 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (ptx::elect_one() && (p.debug_mode & 1) == 0) {
       int sh = 0;
       uint32_t ph = 0;
-      for (int t = t_begin; t < t_end; t += t_step) {
-        const TileCoord tc = decode_tile(p, t);
+      TileIter it(p, t_begin, t_step);
+      for (int t = t_begin; t < t_end; t += t_step, it.next()) {
+        const TileCoord tc = it.c;
         const int x0 = tc.tx * kTileW + s.x_off0;
         const int y0 = tc.ty * p.tile_h + s.y_off0;
         for (int c = 0; c < n_chunks; ++c) {
@@ -209,6 +235,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           ptx::tma_load_4d(is_tail ? &p.tm_a2 : &p.tm_a, &bar->h_full[sh], h_slots + sh * p.h_slot_bytes, c * 64, x0, y0, tc.img);
           if (c == 0) MVLM_TRACE(0);
           if (++sh == n_hslots) { sh = 0; ph ^= 1; }
+        }
+        // Residual inputs of this tile -> L2, now, i.e. one to two tiles before the epilogue warps load them: this
+        // thread is idle between halo loads, the epilogue warps are not (their loads for a tile are issued ~1.5k
+        // cycles before the first use, DRAM latency under load is ~2.5k: the first unit of every tile waited 1.9k
+        // cycles on the 256^2 64->64 layer).  One TMA box per residual tensor (per-pixel bulk prefetches made this
+        // thread the bottleneck: ~35 cycles each).
+        if constexpr ((F & (F_RES1 | F_RES2 | F_UP)) != 0) {
+          const int xa = tc.tx * kTileW, ya = tc.ty * p.tile_h, c_lo = tc.mt * kM;
+          if (F & F_RES1) ptx::tma_prefetch_l2_4d(&p.tm_r1, c_lo, xa, ya, tc.img);
+          if (F & F_RES2) ptx::tma_prefetch_l2_4d(&p.tm_r2, c_lo, xa, ya, tc.img);
+          if (F & F_UP) ptx::tma_prefetch_l2_4d(&p.tm_up, c_lo, xa >> 1, ya >> 1, tc.img);
         }
         ++trace_i;
       }
@@ -358,8 +395,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     ArgmaxState am;
     EpiTrace tr;
     tr.trace = trace; tr.t0 = t_kernel0; tr.on = warp == 2 && lane == 0;
-    for (int t = t_begin; t < t_end; t += t_step) {
-      const TileCoord tc = decode_tile(p, t);
+    TileIter it(p, t_begin, t_step);
+    for (int t = t_begin; t < t_end; t += t_step, it.next()) {
+      const TileCoord tc = it.c;
       const ImageSlots is = {tc.img, tc.img, tc.img, tc.img, tc.img, tc.img, tc.img, tc.img};
       tr.trace_i = trace_i;
       if (p.debug_mode & 2) {  // experiment: accumulators are dropped (results invalid)
@@ -558,6 +596,27 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
       set_error("conv_plan: cuTensorMapEncodeTiled(tail %d) failed with %d / %d", p.tail, (int)r, (int)r2);
+      return MVLM_E_CUDA;
+    }
+  }
+  {
+    // residual inputs: (channel slice of cout_pad, W, H, N) from the slice's first channel; box = one output tile
+    // (half of it for the half-resolution up-sample input), prefetch only -> no swizzle
+    auto res_map = [&](CUtensorMap* tm, const __nv_bfloat16* base, int co, int cs, int hh, int ww, int box_w, int box_h) -> bool {
+      if (!base) return true;
+      cuuint64_t gdim[4] = {(cuuint64_t)s.cout_pad, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)s.n};
+      cuuint64_t gstr[3] = {(cuuint64_t)cs * 2, (cuuint64_t)cs * 2 * ww, (cuuint64_t)cs * 2 * ww * hh};
+      cuuint32_t box[4] = {(cuuint32_t)std::min(s.cout_pad, s.cout_pad <= 64 ? 64 : kMTile), (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base + co), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    const bool ok = res_map(&p.tm_r1, e.res1, e.res1_co, e.res1_cs, s.h, s.w, kTileW, tile_h) &&
+                    res_map(&p.tm_r2, e.res2, e.res2_co, e.res2_cs, s.h, s.w, kTileW, tile_h) &&
+                    res_map(&p.tm_up, e.res_up, e.up_co, e.up_cs, s.h >> 1, s.w >> 1, kTileW / 2, std::max(1, tile_h / 2));
+    if (!ok) {
+      set_error("conv_plan: cuTensorMapEncodeTiled(residual) failed (cout_pad=%d w=%d h=%d)", s.cout_pad, s.w, s.h);
       return MVLM_E_CUDA;
     }
   }

@@ -84,6 +84,8 @@ struct alignas(64) ConvParams {
   CUtensorMap tm_b;   // weights,     64-channel chunks (SWIZZLE_128B)
   CUtensorMap tm_a2;  // tail chunk of `tail` (16 | 32) channels: SWIZZLE_32B | SWIZZLE_64B boxes
   CUtensorMap tm_b2;
+  // residual inputs (res1, res2, res_up) as (channel slice, W, H, N) tensors: L2 prefetch boxes of one output tile
+  CUtensorMap tm_r1, tm_r2, tm_up;
   int tail;           // cin % 64 if it is 16 or 32, else 0 (a 48-wide tail uses a zero-filled 64-wide box)
   ConvShape s;
   ConvEpilogue e;

@@ -43,7 +43,7 @@ elif trace_op >= 0:
           "M acc-acquired, M halo-landed, M issued | E acc-ready, E released")
     for t in range(24):
         r = [trace[t * 16 + k] for k in range(16)]
-        print(f"  tile {t:2d} | {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[4]:8d} | {r[5]:8d} {r[6]:8d}   "
+        print(f"  tile {t:2d} | {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d} {r[4]:8d} | pre-wait {r[7]:8d} {r[5]:8d} {r[6]:8d}   "
               f"mma-span {r[4] - r[2]:6d} epi-span {r[6] - r[5]:6d} | unit0: ld {r[8] - r[5]:5d} sts {r[9] - r[8]:5d} "
               f"out {r[10] - r[9]:5d} end {r[11] - r[10]:5d} | unit1: ld {r[12] - r[11]:5d} sts {r[13] - r[12]:5d} "
               f"out {r[14] - r[13]:5d} end {r[15] - r[14]:5d}")
