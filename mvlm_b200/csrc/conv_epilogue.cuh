@@ -99,11 +99,13 @@ __device__ __forceinline__ void lds8(const float* src, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// role timing: wait on an mbarrier and add the stalled cycles to `acc` when profiling is on
+// role timing: wait on an mbarrier and add the stalled cycles to `acc` when profiling is on.  The wait is the bounded one
+// WITHOUT the printf: a call in the loop makes every value that is live across it caller-saved, and the MMA thread then
+// re-materialises its descriptors in uniform registers (seven R2UR) on every tap
 __device__ __forceinline__ void timed_wait(uint64_t* b, uint32_t parity, bool prof, long long& acc) {
-  if (!prof) { ptx::mbar_wait(b, parity); return; }
+  if (!prof) { ptx::mbar_wait_trap(b, parity); return; }
   const long long t0 = clock64();
-  ptx::mbar_wait(b, parity);
+  ptx::mbar_wait_trap(b, parity);
   acc += clock64() - t0;
 }
 

@@ -135,7 +135,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   constexpr int kM = M64 ? 64 : kMTile;
   const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
   const int mma_m = M64 ? (s.cout_pad <= 32 ? 32 : 64) : kMTile;
-  const uint32_t w_slot_bytes = static_cast<uint32_t>(kM) * 128u;
+  // Weight ring.  M = 128: one slot = one (chunk, tap) tile of 16 KB.  .ws layers (M64): one slot = the KH taps of a
+  // (chunk, kx) column, 8 KB apart (narrow tail chunks likewise): one barrier round trip per column -- per tap the
+  // wait + commit + ring bookkeeping of the issuing thread take ~250-350 cycles (tools/exp_issue.cu), which 4 x 128
+  // cycles of M = 128 math hide and 4 x 80 cycles of .ws math do not.
+  const uint32_t w_tap_bytes = static_cast<uint32_t>(kM) * 128u;  // tap stride inside a slot
+  const uint32_t w_slot_bytes = w_tap_bytes * static_cast<uint32_t>(M64 ? s.kh : 1);
   // stationary weights: all (chunk, tap) tiles of the layer fit in the ring -> loaded once per CTA, never released
   const bool w_stat = p.w_stationary != 0;
 
@@ -263,6 +268,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           const void* tmb = is_tail ? &p.tm_b2 : &p.tm_b;
           const uint32_t row_b = is_tail ? static_cast<uint32_t>(p.tail) * 2u : 128u;  // bytes per weight row
           const uint32_t wb = static_cast<uint32_t>(w_rows) * row_b;
+          if constexpr (M64) {
+            for (int kx = 0; kx < s.kw; ++kx) {  // one slot per column of taps (tap = kx * KH + ky)
+              if (!w_stat) timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
+              ptx::mbar_expect_tx(&bar->w_full[sw], wb * static_cast<uint32_t>(s.kh));
+              for (int ky = 0; ky < s.kh; ++ky)
+                ptx::tma_load_2d(tmb, &bar->w_full[sw], w_slots + sw * w_slot_bytes + ky * w_tap_bytes,
+                                 (kx * s.kh + ky) * s.cin + c * 64, mt * kM);
+              if (++sw == n_wslots) { sw = 0; pw ^= 1; }
+            }
+          } else
           for (int tap = 0; tap < s.kw * s.kh; ++tap) {  // tap = kx * KH + ky
             if (!w_stat) timed_wait(&bar->w_empty[sw], pw ^ 1, prof, w1);
             ptx::mbar_expect_tx(&bar->w_full[sw], wb);
@@ -335,11 +350,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             auto taps = [&](auto nk_c) __attribute__((always_inline)) {
               constexpr int NK = decltype(nk_c)::value;
               constexpr uint32_t kRb16 = NK * 2;
-              const uint32_t w_base = w_lo0 + static_cast<uint32_t>(c * 9) * w_step;
+              const uint32_t w_base = w_lo0 + static_cast<uint32_t>(c * 3) * w_step;  // slot = (chunk, kx): 3 taps, 8 KB apart
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const uint32_t x_lo = x_col + static_cast<uint32_t>(((tap % 3) * 10 + tap / 3)) * kRb16;  // tap = kx * 3 + ky
-                const uint32_t w_lo = w_base + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(kM) * 128u >> 4);
+                const uint32_t w_lo = w_base + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(kM) * 128u >> 4);  // 3 * 8 KB = one slot
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
                   const uint32_t en = (tap == 0 && k == 0) ? accumulate : 1u;
@@ -352,6 +367,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             if (nk == 4) taps(std::integral_constant<int, 4>());
             else if (nk == 2) taps(std::integral_constant<int, 2>());
             else taps(std::integral_constant<int, 1>());
+          } else if constexpr (M64) {
+            // .ws layers: one ring slot per column of taps
+            for (int kx = 0; kx < n_kx; ++kx, x_col += rb16) {
+              if (w_wait) timed_wait(&bar->w_full[sw], w_stat ? 0u : pw, prof, w0);
+              uint32_t x_lo = x_col;
+              uint32_t w_lo = w_lo0 + static_cast<uint32_t>(sw) * w_step;
+              for (int ky = 0; ky < n_ky; ++ky, x_lo += ky_step, w_lo += (w_tap_bytes >> 4)) {
+                ptx::umma_ws_bf16(d, a_hi | w_lo, b_hi | x_lo, idesc, accumulate);
+                if (nk == 4) {
+                  ptx::umma_ws_bf16(d, a_hi | (w_lo + 2), b_hi | (x_lo + 2), idesc, 1u);
+                  ptx::umma_ws_bf16(d, a_hi | (w_lo + 4), b_hi | (x_lo + 4), idesc, 1u);
+                  ptx::umma_ws_bf16(d, a_hi | (w_lo + 6), b_hi | (x_lo + 6), idesc, 1u);
+                } else {
+                  for (int k = 1; k < nk; ++k) ptx::umma_ws_bf16(d, a_hi | (w_lo + 2 * k), b_hi | (x_lo + 2 * k), idesc, 1u);
+                }
+                accumulate = 1;
+              }
+              if (live && !w_stat) ptx::umma_commit(&bar->w_empty[sw]);
+              if (++sw == n_wslots) { sw = 0; pw ^= 1; }
+            }
           } else
           for (int kx = 0; kx < n_kx; ++kx, x_col += rb16) {
             // tap (kx, ky) = the same halo tile shifted by ky halo rows + kx pixels
@@ -530,10 +565,11 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     p.h_slot_bytes = (hbytes + 1023) & ~1023;
     // cout <= 64 -> tcgen05.mma.ws with M <= 64, 8 KB weight slots; all (chunk, tap) tiles resident when they fit the ring
     const int m_tile = s.cout_pad <= 64 ? 64 : kMTile;
-    const int wslot = m_tile * 128;
-    const int n_wtiles = ((s.cin + 63) / 64) * s.kh * s.kw;
+    // ring slot: the KH taps of one (chunk, kx) column for the .ws layers, one tap otherwise (see the kernel)
+    const int wslot = m_tile * 128 * (m_tile == 64 ? s.kh : 1);
+    const int n_wtiles = ((s.cin + 63) / 64) * (m_tile == 64 ? s.kw : s.kh * s.kw);  // slots of one pass over the layer
     int nh = s.kh * s.kw == 1 ? 3 : 2, nw = s.kh * s.kw == 1 ? 6 : (m_tile == 64 ? kMaxWSlots : 7);
-    p.w_stationary = (m_tile == 64 && n_wtiles <= kMaxWSlots && getenv("MVLM_CONV_NO_STATIONARY") == nullptr) ? 1 : 0;
+    p.w_stationary = (m_tile == 64 && n_wtiles * wslot <= kMaxWSlots * 8192 && getenv("MVLM_CONV_NO_STATIONARY") == nullptr) ? 1 : 0;
     if (p.w_stationary) nw = n_wtiles;
     if (const char* env = getenv("MVLM_CONV_RING")) {  // experiment knob: "halo_slots,weight_slots"
       int a = 0, b = 0;
