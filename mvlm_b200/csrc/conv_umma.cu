@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   // (chunk, kx) column, 8 KB apart (narrow tail chunks likewise): one barrier round trip per column -- per tap the
   // wait + commit + ring bookkeeping of the issuing thread take ~250-350 cycles (tools/exp_issue.cu), which 4 x 128
   // cycles of M = 128 math hide and 4 x 80 cycles of .ws math do not.
-  const uint32_t w_tap_bytes = static_cast<uint32_t>(kM) * 128u;  // tap stride inside a slot
+  // (M = 128 slots hold the rows that are loaded, rounded up to the 1 KB swizzle atom: 10 KB for the 80-channel heads.)
+  const uint32_t w_tap_bytes = M64 ? 64u * 128u : ((static_cast<uint32_t>(w_rows) * 128u + 1023u) & ~1023u);  // tap stride inside a slot
   const uint32_t w_slot_bytes = w_tap_bytes * static_cast<uint32_t>(M64 ? s.kh : 1);
   // stationary weights: all (chunk, tap) tiles of the layer fit in the ring -> loaded once per CTA, never released
   const bool w_stat = p.w_stationary != 0;
@@ -566,10 +567,16 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     // cout <= 64 -> tcgen05.mma.ws with M <= 64, 8 KB weight slots; all (chunk, tap) tiles resident when they fit the ring
     const int m_tile = s.cout_pad <= 64 ? 64 : kMTile;
     // ring slot: the KH taps of one (chunk, kx) column for the .ws layers, one tap otherwise (see the kernel)
-    const int wslot = m_tile * 128 * (m_tile == 64 ? s.kh : 1);
+    const int w_tap = m_tile == 64 ? 64 * 128 : ((std::min(s.cout_pad, kMTile) * 128 + 1023) & ~1023);
+    const int wslot = w_tap * (m_tile == 64 ? s.kh : 1);
     const int n_wtiles = ((s.cin + 63) / 64) * (m_tile == 64 ? s.kw : s.kh * s.kw);  // slots of one pass over the layer
     int nh = s.kh * s.kw == 1 ? 3 : 2, nw = s.kh * s.kw == 1 ? 6 : (m_tile == 64 ? kMaxWSlots : 7);
-    p.w_stationary = (m_tile == 64 && n_wtiles * wslot <= kMaxWSlots * 8192 && getenv("MVLM_CONV_NO_STATIONARY") == nullptr) ? 1 : 0;
+    // stationary weights: every slot of the layer resident (loaded once per CTA, no barrier traffic afterwards) -- the
+    // .ws layers up to K = 768, and single-M-tile M = 128 layers whose weights fit next to the halo ring (the four
+    // conv11 phase kernels: 8 x 10 KB; the 64 -> 128 resample)
+    const bool fits_128 = m_tile == kMTile && s.cout_pad <= kMTile && n_wtiles <= kMaxWSlots &&
+                          nh * p.h_slot_bytes + n_wtiles * wslot <= kPoolBytes;
+    p.w_stationary = ((m_tile == 64 ? n_wtiles * wslot <= kMaxWSlots * 8192 : fits_128) && getenv("MVLM_CONV_NO_STATIONARY") == nullptr) ? 1 : 0;
     if (p.w_stationary) nw = n_wtiles;
     if (const char* env = getenv("MVLM_CONV_RING")) {  // experiment knob: "halo_slots,weight_slots"
       int a = 0, b = 0;
