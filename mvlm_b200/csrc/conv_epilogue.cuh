@@ -5,6 +5,8 @@
 #pragma once
 #include "conv_umma.cuh"
 
+#include <type_traits>
+
 #ifndef MVLM_FLOW_RES_BUDGET
 #define MVLM_FLOW_RES_BUDGET 32  // registers of the residual prefetch buffer in the dataflow kernel's variants
 #endif
@@ -58,6 +60,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   r.y = *reinterpret_cast<uint32_t*>(&b);
   r.z = *reinterpret_cast<uint32_t*>(&c);
   r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+// IEEE maximum that returns NaN when any input is NaN
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
 // relu + round to bf16 in one instruction per pair (cvt.rn.relu.bf16x2.f32: first source -> upper half)
@@ -340,7 +353,49 @@ __device__ __forceinline__ void epilogue_tile(const ConvShape& s, const ConvEpil
             // channel-major consumers: lane = channel c_lane, vr[j] = pixel (y + j/8, x0 + j%8)
             const int x0 = tc.tx * kTileW;
             const int nvx = s.w - x0;  // >= 8 for interior tiles
-            if (c_lane < e.cout_real) {
+            // Arg-max only (the conv11 phase kernels, whose epilogue is their bound: ~130 instructions per unit for a
+            // per-row tournament over ordered keys).  Most units cannot change the running maximum of their channel,
+            // and those that can need the position of ONE value: a NaN-propagating 3-input max over the unit (+ bias:
+            // the addition is monotonic, so max(v) + b == max(v + b) bit for bit) is compared with the running best
+            // (">=": an equal value at a lower pixel index must still win, tiles are not visited in pixel order); only
+            // then the first pixel whose biased value has exactly those bits is looked up.  A NaN in the unit takes the
+            // exact per-row search below, which is also what the fp32-map variants run.
+            bool exact_search = c_lane < e.cout_real;
+            if constexpr ((F & F_HEAD) == F_ARGMAX) {
+              if (c_lane < e.cout_real) {
+                // two instantiations: every pixel of the unit exists (no masks at all) | edge tiles
+                auto unit = [&](auto interior_c) __attribute__((always_inline)) {
+                  constexpr bool kInterior = decltype(interior_c)::value;
+                  auto ok = [&](int j) __attribute__((always_inline)) { return kInterior || ((j & 7) < nvx && y + (j >> 3) < s.h); };
+                  float w[kCols];
+#pragma unroll
+                  for (int j = 0; j < kCols; ++j) w[j] = ok(j) ? __uint_as_float(vr[j]) : -INFINITY;
+                  float m = fmax3_nan(w[0], w[1], w[2]);
+#pragma unroll
+                  for (int j = 3; j + 1 < kCols; j += 2) m = fmax3_nan(m, w[j], w[j + 1]);
+                  m = fmax_nan(m, w[kCols - 1]);
+                  const float mb = m + bias_c;
+                  const uint32_t key = order_f32(mb);
+                  exact_search = mb != mb;
+                  if (key >= am.best_hi && !exact_search) {
+                    const uint32_t mbits = __float_as_uint(mb);
+                    int jf = kCols - 1;  // (masked pixels hold -inf: they must not stand in for a real -inf)
+#pragma unroll
+                    for (int j = kCols - 2; j >= 0; --j)
+                      if (__float_as_uint(w[j] + bias_c) == mbits && ok(j)) jf = j;
+                    const int oy = (y + (jf >> 3)) * e.up_sy + e.up_py;
+                    const uint32_t lo = 0xFFFFFFFFu - static_cast<uint32_t>(oy * ow + (x0 + (jf & 7)) * e.up_sx + e.up_px);
+                    if (key > am.best_hi || lo > am.best_lo) {
+                      am.best_hi = key;
+                      am.best_lo = lo;
+                    }
+                  }
+                };
+                if (nvx >= kTileW && y + kUnitRows <= s.h) unit(std::true_type());
+                else unit(std::false_type());
+              }
+            }
+            if (exact_search) {
 #pragma unroll
               for (int i = 0; i < kUnitRows; ++i) {
                 if (y + i < s.h) {

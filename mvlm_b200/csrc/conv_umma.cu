@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   // form spreads the 64 (32) x N tile over all 128 TMEM lanes and issues every 84.5 cycles (tools/exp_ws.cu), so
   // every epilogue warp holds 32 channels in its 32 lanes and the lane groups split the tile's pixel rows.
   constexpr bool M64 = (F & F_M64) != 0;
-  constexpr bool STAT = (F & F_STAT) != 0;  // stationary weights and 3 x 3 taps (conv_launch)
+  constexpr bool STAT = (F & F_STAT) != 0;  // stationary weights and 3 x 3 (.ws) or 2 x 2 (M = 128) taps (conv_launch)
   constexpr int kM = M64 ? 64 : kMTile;
   const int w_rows = s.cout_pad < kM ? s.cout_pad : kM;  // weight rows actually loaded per tile
   const int mma_m = M64 ? (s.cout_pad <= 32 ? 32 : 64) : kMTile;
@@ -344,18 +344,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           if (c == 0) MVLM_TRACE(3);
           uint32_t x_col = h_lo0 + static_cast<uint32_t>(sh) * h_step;
           if (STAT && !w_wait && (nk == 4 || nk == 2 || nk == 1)) {
-            // 3 x 3 taps over stationary weights that have been waited for, straight-line: the B descriptor of tap
-            // (kx, ky), K-step k is x_col + a compile-time offset (halo rows are 10 pixels of NK * 32 bytes), the A
-            // descriptor is slot chunk * 9 + tap: two uniform adds per MMA, no barrier in sight.  (The same unrolling
-            // with the weight ring's wait / commit per tap made the 128- and 256-channel layers 3-4 % slower.)
-            auto taps = [&](auto nk_c) __attribute__((always_inline)) {
+            // Stationary weights that have been waited for, 3 x 3 (.ws layers) or 2 x 2 taps (the conv11 phase kernels),
+            // straight-line: the B descriptor of tap (kx, ky), K-step k is x_col + a compile-time offset (halo rows are
+            // 8 + KW - 1 pixels of NK * 32 bytes), the A descriptor is tile chunk * taps + tap: two uniform adds per MMA,
+            // no barrier in sight.  (The same unrolling with the weight ring's wait / commit per tap made the 128- and
+            // 256-channel layers 3-4 % slower.)
+            auto taps = [&](auto nk_c, auto kk_c) __attribute__((always_inline)) {
               constexpr int NK = decltype(nk_c)::value;
+              constexpr int KK = decltype(kk_c)::value;  // KW = KH
               constexpr uint32_t kRb16 = NK * 2;
-              const uint32_t w_base = w_lo0 + static_cast<uint32_t>(c * 3) * w_step;  // slot = (chunk, kx): 3 taps, 8 KB apart
+              const uint32_t tap16 = M64 ? (64u * 128u >> 4) : w_step;  // tap stride: 8 KB inside a column slot | one slot
+              const uint32_t w_base = w_lo0 + static_cast<uint32_t>(c * KK * KK) * tap16;
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t x_lo = x_col + static_cast<uint32_t>(((tap % 3) * 10 + tap / 3)) * kRb16;  // tap = kx * 3 + ky
-                const uint32_t w_lo = w_base + static_cast<uint32_t>(tap) * (static_cast<uint32_t>(kM) * 128u >> 4);  // 3 * 8 KB = one slot
+              for (int tap = 0; tap < KK * KK; ++tap) {  // tap = kx * KH + ky
+                const uint32_t x_lo = x_col + static_cast<uint32_t>(((tap % KK) * (kTileW + KK - 1) + tap / KK)) * kRb16;
+                const uint32_t w_lo = w_base + static_cast<uint32_t>(tap) * tap16;
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
                   const uint32_t en = (tap == 0 && k == 0) ? accumulate : 1u;
@@ -365,9 +368,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               }
               accumulate = 1;
             };
-            if (nk == 4) taps(std::integral_constant<int, 4>());
-            else if (nk == 2) taps(std::integral_constant<int, 2>());
-            else taps(std::integral_constant<int, 1>());
+            using std::integral_constant;
+            if constexpr (M64) {
+              if (nk == 4) taps(integral_constant<int, 4>(), integral_constant<int, 3>());
+              else if (nk == 2) taps(integral_constant<int, 2>(), integral_constant<int, 3>());
+              else taps(integral_constant<int, 1>(), integral_constant<int, 3>());
+            } else {
+              if (nk == 4) taps(integral_constant<int, 4>(), integral_constant<int, 2>());
+              else if (nk == 2) taps(integral_constant<int, 2>(), integral_constant<int, 2>());
+              else taps(integral_constant<int, 1>(), integral_constant<int, 2>());
+            }
           } else if constexpr (M64) {
             // .ws layers: one ring slot per column of taps
             for (int kx = 0; kx < n_kx; ++kx, x_col += rb16) {
@@ -693,6 +703,8 @@ int conv_launch(const ConvParams& p_in, cudaStream_t stream) {
   case (FLAGS):              \
     if (!m64) return launch_t<(FLAGS)>(p, stream); \
     break
+  // the conv11 phase kernels: 2 x 2 taps over stationary weights at M = 128, straight-line issue as well
+  if (f == F_ARGMAX && !m64 && p.w_stationary && p.s.kw == 2 && p.s.kh == 2) return launch_t<F_ARGMAX | F_STAT>(p, stream);
   switch (f) {
     // the combinations the network plan uses (hourglass.cu)
     MVLM_CASE_BOTH(F_PRE | F_RES1 | F_RAW | F_POST);  // RB conv1/2
