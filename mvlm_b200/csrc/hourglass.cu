@@ -549,11 +549,12 @@ int HourglassNet::build(const StateDict* sd, int n_landmarks, int cin, int n_vie
   // MVLM_HG_NO_REUSE=1: every buffer does (the round-1 layout, for A/B runs)
   keep_probes_ = getenv("MVLM_HG_KEEP_PROBES") != nullptr && atoi(getenv("MVLM_HG_KEEP_PROBES")) != 0;
   reuse_ = !(getenv("MVLM_HG_NO_REUSE") != nullptr && atoi(getenv("MVLM_HG_NO_REUSE")) != 0);
-  // MVLM_HG_ELT_FUSION=1: the hourglass max-pools and conv4's BatchNorm+ReLU copy are written by their producers'
-  // epilogues (aux_mode) instead of stand-alone passes.  Off by default: measured at 100 views of 256^2 the eleven
-  // passes it removes cost 0.58 ms (they run at 94 % of the HBM peak) and the producers, which are epilogue-bound, get
-  // 0.65 ms slower (conv7 0.85 -> 1.11 ms): 18.23 against 18.11 ms per scan (profiles/r2_elt_fusion.txt)
-  fuse_elt_ = getenv("MVLM_HG_ELT_FUSION") != nullptr && atoi(getenv("MVLM_HG_ELT_FUSION")) != 0;
+  // The hourglass max-pools and conv4's BatchNorm+ReLU copy are written by their producers' epilogues (aux_mode) instead
+  // of stand-alone passes (155 -> 144 launches); MVLM_HG_ELT_FUSION=0 restores the passes.  History: in the first half of
+  // round 2 the eleven passes it removes cost 0.58 ms (they run at 94 % of the HBM peak) and the producers, then
+  // epilogue-bound, got 0.65 ms slower (profiles/r2_elt_fusion.txt); after the .ws / preamble / residual-prefetch work
+  // the same switch measures 0.18 ms (1.1 %) faster, A/B on one box.
+  fuse_elt_ = !(getenv("MVLM_HG_ELT_FUSION") != nullptr && atoi(getenv("MVLM_HG_ELT_FUSION")) == 0);
   // layout pass: lifetimes and packed offsets
   bufs_.clear(); fake_off_ = 0; ws_needed_ = 0; next_buf_ = 0;
   param_off_ = 0; bn_seen_.clear();
