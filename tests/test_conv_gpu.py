@@ -39,6 +39,14 @@ CASES = [
     (2, 24, 40, 64, 64, 64, 64, 3, 3),       # ragged: rows not a multiple of the tile height
     (2, 80, 20, 64, 64, 64, 64, 3, 3),       # ragged: width not a multiple of 8, 2.5 tiles high
     (3, 2, 2, 256, 256, 128, 128, 3, 3),     # 2x2 map (hourglass bottom of a 64^2 image)
+    # cout <= 64: tcgen05.mma.ws, M = 64 (33..64 channels) or M = 32, accumulator tile spread over all four lane groups
+    (2, 32, 32, 64, 64, 48, 48, 3, 3),       # M = 64 with 48 weight rows
+    (2, 32, 32, 64, 64, 16, 16, 3, 3),       # M = 32 with 16 weight rows
+    (3, 2, 2, 128, 128, 32, 32, 3, 3),       # 8-row tile (N = 64, the .ws minimum) on a 2x2 map
+    (2, 16, 24, 16, 16, 64, 64, 3, 3),       # the stem's shape: one 16-channel (32-byte row) chunk, stationary weights
+    (2, 40, 16, 128, 128, 64, 64, 3, 3),     # streamed weights, one ring slot per column of taps
+    (2, 32, 32, 64, 64, 64, 64, 2, 2),       # 2x2 taps: two-tap columns
+    (2, 32, 32, 96, 96, 32, 32, 1, 1),       # 1x1, 64 + 32-channel tail chunk
 ]
 
 
