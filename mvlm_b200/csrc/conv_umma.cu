@@ -657,9 +657,10 @@ int conv_plan(const ConvShape& s, const ConvEpilogue& e, ConvParams* out) {
     // (half of it for the half-resolution up-sample input), prefetch only -> no swizzle
     auto res_map = [&](CUtensorMap* tm, const __nv_bfloat16* base, int co, int cs, int hh, int ww, int box_w, int box_h) -> bool {
       if (!base) return true;
-      cuuint64_t gdim[4] = {(cuuint64_t)s.cout_pad, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)s.n};
+      const int c_ext = std::min(s.cout_pad, cs);  // the slice never extends past the pixel's channels
+      cuuint64_t gdim[4] = {(cuuint64_t)c_ext, (cuuint64_t)ww, (cuuint64_t)hh, (cuuint64_t)s.n};
       cuuint64_t gstr[3] = {(cuuint64_t)cs * 2, (cuuint64_t)cs * 2 * ww, (cuuint64_t)cs * 2 * ww * hh};
-      cuuint32_t box[4] = {(cuuint32_t)std::min(s.cout_pad, s.cout_pad <= 64 ? 64 : kMTile), (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+      cuuint32_t box[4] = {(cuuint32_t)std::min(c_ext, s.cout_pad <= 64 ? 64 : kMTile), (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base + co), gdim, gstr, box, estr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
