@@ -270,3 +270,44 @@ def test_conv_random_shape_sweep(lib):
         if with_post:
             post_ref = torch.relu(v2 * s2 + t2)
             assert (out_post.float() - post_ref).abs().max().item() <= tol * s2.abs().max().item() + post_ref.abs().max().item() * 2.0 ** -8, tag
+
+
+def test_conv_fused_argmax_fast_path_matches_exact_search(lib):
+    """The arg-max-only epilogue (unit maximum + position lookup, the conv11 phase kernels) must return the keys of the
+    exact per-row search (the variant that also writes the fp32 map), bit for bit: ties (also those created by a large
+    bias swallowing the low bits), -inf maps, NaN pixels, +0 / -0, ragged widths and heights."""
+    from mvlm_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(77)
+    c = 128
+    eye = torch.eye(c, device="cuda").reshape(c, c, 1, 1)
+    wp = ops.pack_conv_weight(eye, c, c)
+    for case, (n, h, w, co) in enumerate(((2, 64, 32, 128), (1, 40, 20, 73), (3, 8, 8, 128), (2, 36, 44, 80))):
+        for kind in ("random", "quantised", "equal", "bias_ties", "neg_inf_bias", "nan", "zeros"):
+            x = torch.randn((n, h, w, c), generator=g, device="cuda")
+            bias = torch.zeros(c, device="cuda")
+            if kind == "quantised":
+                x = torch.randint(-2, 3, (n, h, w, c), generator=g, device="cuda").float()
+            elif kind == "equal":
+                x = torch.full((n, h, w, c), 1.5, device="cuda")
+            elif kind == "bias_ties":
+                bias = torch.full((c,), 3.0e5, device="cuda")       # ulp(3e5) = 1/32: many different v give equal v + b
+            elif kind == "neg_inf_bias":
+                bias[::3] = float("-inf")
+            elif kind == "nan":
+                x[0, h // 2, w // 3, :] = float("nan")              # 0 * NaN: every channel is NaN at that pixel
+                x[-1, h - 1, w - 1, 5] = float("nan")
+            elif kind == "zeros":
+                x = torch.where(torch.rand((n, h, w, c), generator=g, device="cuda") < 0.5, 0.0, -0.0) * 1.0
+            xb = x.to(torch.bfloat16)
+            keys_exact = torch.zeros((n * co,), device="cuda", dtype=torch.int64)
+            keys_fast = torch.zeros((n * co,), device="cuda", dtype=torch.int64)
+            out_f32 = torch.zeros((n, co, h, w), device="cuda")
+            ops.conv2d_bf16(xb, wp, n_tile=c, kh=1, kw=1, bias=bias, out_f32=out_f32, argmax_keys=keys_exact, cout_real=co)
+            ops.conv2d_bf16(xb, wp, n_tile=c, kh=1, kw=1, bias=bias, argmax_keys=keys_fast, cout_real=co)
+            torch.cuda.synchronize()
+            assert torch.equal(keys_exact, keys_fast), (case, kind)
+            if kind in ("random", "quantised", "equal", "bias_ties"):
+                idx = 0xFFFFFFFF - (keys_fast.view(n, co) & 0xFFFFFFFF)
+                assert torch.equal(idx, out_f32.view(n, co, -1).argmax(dim=-1)), (case, kind)
